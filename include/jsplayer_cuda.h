@@ -1,0 +1,126 @@
+/*
+ * jsplayer_cuda.h -- C ABI of libjsplayer_cuda, the B200 (sm_100a) batch video
+ * decoder that drops in for thedeemon/jsplayer's two codec hot paths.
+ *
+ * The reference has no FFI (it is Haxe compiled to JavaScript); the boundary
+ * replaced here is `interface IVideoCodec` (reference src/IVideoCodec.hx:16-29)
+ * as constructed by Manager.video_info_cb (src/Manager.hx:105-111) and driven by
+ * Manager.worker (src/Manager.hx:454-525).  Every entry point below cites the
+ * member it replaces.  Plain pointers and sizes only; no CUDA or torch types.
+ * A Haxe/hxcpp extern for these symbols is in haxe/JsplayerCuda.hx and the
+ * reference-side change is described in INTEGRATION.md.
+ *
+ * There is NO CPU fallback: every decode entry point fails (JSP_ERROR_OCCURED /
+ * negative return) when no CUDA device is usable.
+ */
+#ifndef JSPLAYER_CUDA_H
+#define JSPLAYER_CUDA_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JSP_API __attribute__((visibility("default")))
+
+/* enum DecoderState -- IVideoCodec.hx:5-9 */
+typedef enum { JSP_ZERO_STATE = 0, JSP_IN_PROGRESS = 1, JSP_ERROR_OCCURED = 2 } jsp_state;
+/* enum CodecType -- VideoData.hx:75-80 */
+typedef enum { JSP_CODEC_SCREENPRESSOR = 0, JSP_CODEC_MSVC16 = 1, JSP_CODEC_MSVC8 = 2 } jsp_codec;
+/* typedef PFrameResult -- IVideoCodec.hx:11-14. data_pnt is dst, the retained previous
+ * buffer (unchanged frame), or NULL (nothing decoded yet). */
+typedef struct { int32_t *data_pnt; int32_t significant_changes; } jsp_pframe_result;
+
+typedef struct jsp_dec jsp_dec;
+
+/* ---- library ---- */
+JSP_API int         jsp_device_count(void);            /* usable CUDA devices, 0 if none */
+JSP_API const char *jsp_last_error(void);              /* thread-local, never NULL */
+JSP_API const char *jsp_version(void);
+/* pinned host memory for frame / bitstream buffers (what DataLoaderAVIIndexed's frame table holds) */
+JSP_API void *jsp_host_alloc(size_t bytes);
+JSP_API void  jsp_host_free(void *p);
+
+/* ---- per-stream drop-in: one stateful codec per stream, frames in order, host buffers ----
+ * new MSVideo1_16bit(w,h) MSVideo1.hx:20-31 | new MSVideo1_8bit(w,h,palette) :267-274 |
+ * new ScreenPressor(w,h,bpp) ScreenPressor.hx:53-64.  palette = strf bytes from offset 40
+ * (AVIParser.hx:79-85), little-endian B,G,R,x quads.  device < 0 selects the current device. */
+JSP_API jsp_dec  *jsp_create(jsp_codec codec, int width, int height, int bpp,
+                             const uint8_t *palette, int palette_bytes, int device);
+JSP_API void      jsp_destroy(jsp_dec *d);
+JSP_API void      jsp_preinit(jsp_dec *d, int insignificant_lines);            /* IVideoCodec.Preinit        */
+JSP_API int32_t  *jsp_previous_frame(jsp_dec *d);                               /* IVideoCodec.PreviousFrame  */
+JSP_API int       jsp_is_key_frame(jsp_dec *d, const uint8_t *data, int len);   /* IVideoCodec.IsKeyFrame (host-side parse, no GPU) */
+JSP_API jsp_state jsp_state_of(jsp_dec *d);                                     /* IVideoCodec.State          */
+JSP_API jsp_state jsp_decompress_i(jsp_dec *d, const uint8_t *src, int len, int32_t *dst);   /* IVideoCodec.DecompressI */
+JSP_API jsp_state jsp_continue_i(jsp_dec *d);                                   /* IVideoCodec.ContinueI (never in_progress, ScreenPressor.hx:210-215) */
+JSP_API jsp_pframe_result jsp_decompress_p(jsp_dec *d, const uint8_t *src, int len, int32_t *dst); /* IVideoCodec.DecompressP */
+JSP_API int       jsp_needs_index(jsp_dec *d);                                  /* IVideoCodec.NeedsIndex     */
+JSP_API void      jsp_stop_and_clean(jsp_dec *d);                               /* IVideoCodec.StopAndClean   */
+
+/* ---- batch path: many independent streams / GOPs per call (what the benchmarks drive) ----
+ * One descriptor per stream; the frame table is what DataLoader keeps per stream
+ * (DataLoader.hx:31 `frames`, VideoData.hx:68-73 CompressedFrame{key,data}). */
+typedef struct {
+    int32_t codec;               /* jsp_codec */
+    int32_t width, height, bpp;
+    const uint8_t *palette;      /* MSVC8 only */
+    int32_t palette_bytes;
+    int32_t n_frames;
+    const uint8_t  *bytes;       /* compressed bytes of this stream (host; pinned for async copies) */
+    const uint64_t *frame_off;   /* n_frames offsets into bytes */
+    const uint32_t *frame_len;   /* n_frames lengths */
+    const uint8_t  *frame_key;   /* n_frames: 1 = key frame (DecompressI), 0 = DecompressP (Manager.hx:505-512) */
+} jsp_stream_desc;
+
+typedef struct jsp_batch jsp_batch;
+
+enum {
+    JSP_BATCH_SIGNIFICANCE = 1,  /* also compute PFrameResult.significant_changes exactly (extra previous-frame reads) */
+};
+
+/* Per-frame result flags written by jsp_batch_results(). */
+enum {
+    JSP_FRAME_CHANGED     = 1,   /* data_pnt == dst (the frame altered pixels)              */
+    JSP_FRAME_SIGNIFICANT = 2,   /* PFrameResult.significant_changes                         */
+    JSP_FRAME_ERROR       = 4,   /* DecoderState.error_occured / malformed bitstream         */
+};
+
+JSP_API jsp_batch *jsp_batch_create(int device, int insignificant_lines, int flags);
+JSP_API void       jsp_batch_destroy(jsp_batch *b);
+/* Builds the frame / GOP tables, (re)allocates device memory for bitstreams and output pictures.
+ * Frame order of every output array: stream 0 frames, stream 1 frames, ...  Returns total frames or <0. */
+JSP_API int64_t    jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *streams, int n_streams);
+JSP_API int        jsp_batch_upload(jsp_batch *b);      /* host bitstreams -> HBM (async on the batch's stream) */
+JSP_API int        jsp_batch_run(jsp_batch *b);         /* decode kernels only; inputs and outputs stay in HBM   */
+JSP_API int        jsp_batch_sync(jsp_batch *b);
+/* out_frames[i] (host, i in output order) receives picture i: width*height int32 0x00RRGGBB, bitstream
+ * row order; NULL entries are skipped.  flags[i] = JSP_FRAME_* bits. */
+JSP_API int        jsp_batch_download(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags);
+JSP_API int        jsp_batch_results(jsp_batch *b, uint8_t *flags);             /* flags only */
+/* upload + run + download, chunked and double-buffered over PCIe (the end-to-end path). */
+JSP_API int        jsp_batch_decode_host(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags);
+/* device pointer (as integer) of output picture i and of the output arena; for device-resident consumers */
+JSP_API uint64_t   jsp_batch_device_frame(jsp_batch *b, int64_t i);
+/* Times `iters` back-to-back jsp_batch_run() passes with CUDA events on the batch's own stream after
+ * `warmup` untimed passes.  ms_total = whole region; kernel_ms[k] (may be NULL, k < JSP_N_KERNELS) =
+ * summed device time of kernel class k over the timed passes, launches[k] = launch count. */
+enum { JSP_K_MSV1_DECODE = 0, JSP_K_FRAME_COPY = 1, JSP_K_SP_ENTROPY_RC = 2, JSP_K_SP_ENTROPY_ANS = 3,
+       JSP_K_SP_RECON = 4, JSP_K_SIGNIF = 5, JSP_N_KERNELS = 8 };
+JSP_API int        jsp_batch_time_runs(jsp_batch *b, int warmup, int iters, int flush_l2,
+                                       float *ms_total, float *kernel_ms, int64_t *launches);
+/* Algorithmic bytes one jsp_batch_run() moves: output store + compressed read +
+ * previous-frame reads for copied pixels; in_bytes/out_bytes = PCIe bytes of the end-to-end path. */
+JSP_API int        jsp_batch_stats(jsp_batch *b, uint64_t *pixels, uint64_t *alg_bytes,
+                                   uint64_t *in_bytes, uint64_t *out_bytes);
+
+/* One-shot convenience with the signature SURVEY.md 8b sketches; shards streams longest-first over
+ * n_gpus devices of this process (no collectives: GOPs/streams are independent). */
+JSP_API int jsp_batch_decode(const jsp_stream_desc *streams, int n_streams, int n_gpus,
+                             int32_t *const *out_frames, uint8_t *out_changed,
+                             uint8_t *out_significant, int32_t *out_status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

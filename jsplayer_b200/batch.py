@@ -1,0 +1,214 @@
+"""Batch driver: many independent streams / GOPs decoded per call (the throughput path).
+
+Host-side counterpart of the frame table the reference's loaders keep per stream
+(src/DataLoader.hx:31, src/VideoData.hx:68-73), handed to jsp_batch_* of the C ABI.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .codec import CodecType
+
+
+@dataclass
+class StreamSpec:
+    codec: int
+    width: int
+    height: int
+    bpp: int
+    frames: Sequence[bytes] = ()                 # compressed frames in order (copied into one buffer), or
+    bytes_buf: Optional[np.ndarray] = None        # ... a prebuilt uint8 buffer with frame_off / frame_len
+    frame_off: Optional[np.ndarray] = None
+    frame_len: Optional[np.ndarray] = None
+    keys: Optional[Sequence[int]] = None          # 1 = key frame; default: frame 0 only
+    palette: Optional[bytes] = None
+
+    @property
+    def n_frames(self):
+        return len(self.frame_len) if self.frame_len is not None else len(self.frames)
+
+
+class PinnedBuffer:
+    """cudaHostAlloc'ed memory exposed as a numpy array (jsp_host_alloc / jsp_host_free)."""
+
+    def __init__(self, nbytes, dtype=np.uint8):
+        self._lib = _lib.load()
+        self.nbytes = int(nbytes)
+        self.ptr = self._lib.jsp_host_alloc(max(1, self.nbytes))
+        if not self.ptr:
+            raise MemoryError("jsp_host_alloc(%d) failed: %s" % (nbytes, _lib.last_error()))
+        raw = (C.c_uint8 * max(1, self.nbytes)).from_address(self.ptr)
+        self.array = np.frombuffer(raw, dtype=np.uint8, count=self.nbytes).view(dtype)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self._lib.jsp_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchDecoder:
+    def __init__(self, device=-1, insignificant_lines=0, significance=False):
+        self._lib = _lib.require_gpu()
+        self._h = self._lib.jsp_batch_create(int(device), int(insignificant_lines),
+                                             _lib.JSP_BATCH_SIGNIFICANCE if significance else 0)
+        if not self._h:
+            raise RuntimeError("jsp_batch_create failed: " + _lib.last_error())
+        self._keep = []
+        self.specs: List[StreamSpec] = []
+        self.n_frames = 0
+
+    def close(self):
+        h, self._h = self._h, None
+        if h:
+            self._lib.jsp_batch_destroy(h)
+        self._keep = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise RuntimeError("%s failed: %s" % (what, _lib.last_error()))
+        return rc
+
+    def configure(self, specs: Sequence[StreamSpec], pinned=False):
+        """Builds the C descriptors. With pinned=True frame bytes are gathered into ONE pinned buffer
+        (16-byte aligned frames), which is what the end-to-end path wants."""
+        self.specs = list(specs)
+        keep = []
+        descs = (_lib.StreamDescC * len(self.specs))()
+        total = 0
+        if pinned:
+            for sp in self.specs:
+                if sp.bytes_buf is None:
+                    total += sum((len(f) + 15) & ~15 for f in sp.frames)
+            arena = PinnedBuffer(total + 64) if total else None
+            keep.append(arena)
+            cur = 0
+        for i, sp in enumerate(self.specs):
+            if sp.bytes_buf is not None:
+                buf = sp.bytes_buf
+                off = np.ascontiguousarray(sp.frame_off, dtype=np.uint64)
+                ln = np.ascontiguousarray(sp.frame_len, dtype=np.uint32)
+            else:
+                n = len(sp.frames)
+                ln = np.array([len(f) for f in sp.frames], dtype=np.uint32)
+                al = (ln.astype(np.uint64) + 15) & ~np.uint64(15)
+                off = np.zeros(n, dtype=np.uint64)
+                if n:
+                    off[1:] = np.cumsum(al)[:-1]
+                size = int(al.sum())
+                if pinned:
+                    buf = arena.array[cur:cur + size]
+                    cur += size
+                else:
+                    buf = np.zeros(size + 64, dtype=np.uint8)
+                for f, o in zip(sp.frames, off):
+                    if len(f):
+                        buf[int(o):int(o) + len(f)] = np.frombuffer(f, dtype=np.uint8)
+            keys = np.zeros(len(ln), dtype=np.uint8)
+            if sp.keys is None:
+                if len(keys):
+                    keys[0] = 1
+            else:
+                keys[:] = np.asarray(sp.keys, dtype=np.uint8)
+            pal = np.frombuffer(sp.palette, dtype=np.uint8).copy() if sp.palette else None
+            keep += [buf, off, ln, keys, pal]
+            d = descs[i]
+            d.codec, d.width, d.height, d.bpp = int(sp.codec), int(sp.width), int(sp.height), int(sp.bpp)
+            d.palette = pal.ctypes.data if pal is not None else None
+            d.palette_bytes = int(pal.size) if pal is not None else 0
+            d.n_frames = len(ln)
+            d.bytes = buf.ctypes.data if buf.size else None
+            d.frame_off, d.frame_len, d.frame_key = off.ctypes.data, ln.ctypes.data, keys.ctypes.data
+        self._keep = keep + [descs]
+        self.n_frames = int(self._check(self._lib.jsp_batch_configure(self._h, descs, len(self.specs)), "jsp_batch_configure"))
+        return self.n_frames
+
+    def frame_shapes(self):
+        out = []
+        for sp in self.specs:
+            out += [(sp.height, sp.width)] * sp.n_frames
+        return out
+
+    def upload(self):
+        self._check(self._lib.jsp_batch_upload(self._h), "jsp_batch_upload")
+
+    def run(self):
+        self._check(self._lib.jsp_batch_run(self._h), "jsp_batch_run")
+
+    def sync(self):
+        self._check(self._lib.jsp_batch_sync(self._h), "jsp_batch_sync")
+
+    def _out_ptrs(self, outs):
+        ptrs = (C.c_void_p * self.n_frames)()
+        for i, a in enumerate(outs):
+            if a is not None:
+                assert a.dtype == np.int32 and a.flags.c_contiguous
+                ptrs[i] = a.ctypes.data
+        return ptrs
+
+    def alloc_outputs(self, pinned=False):
+        shapes = self.frame_shapes()
+        if pinned:
+            total = sum(h * w for h, w in shapes)
+            pb = PinnedBuffer(total * 4, np.int32)
+            self._keep.append(pb)
+            outs, cur = [], 0
+            for h, w in shapes:
+                outs.append(pb.array[cur:cur + h * w].reshape(h, w))
+                cur += h * w
+            return outs
+        return [np.zeros((h, w), dtype=np.int32) for h, w in shapes]
+
+    def download(self, outs=None):
+        if outs is None:
+            outs = self.alloc_outputs()
+        flags = np.zeros(self.n_frames, dtype=np.uint8)
+        self._check(self._lib.jsp_batch_download(self._h, self._out_ptrs(outs), flags.ctypes.data), "jsp_batch_download")
+        return outs, flags
+
+    def results(self):
+        flags = np.zeros(self.n_frames, dtype=np.uint8)
+        self._check(self._lib.jsp_batch_results(self._h, flags.ctypes.data), "jsp_batch_results")
+        return flags
+
+    def decode_host(self, outs=None):
+        """upload + decode + download through host buffers (the end-to-end call)."""
+        if outs is None:
+            outs = self.alloc_outputs()
+        flags = np.zeros(self.n_frames, dtype=np.uint8)
+        self._check(self._lib.jsp_batch_decode_host(self._h, self._out_ptrs(outs), flags.ctypes.data), "jsp_batch_decode_host")
+        return outs, flags
+
+    def decode(self, specs, significance=None):
+        self.configure(specs)
+        return self.decode_host()
+
+    def time_runs(self, warmup=3, iters=10, flush_l2=True):
+        ms = C.c_float(0)
+        kms = (C.c_float * _lib.JSP_N_KERNELS)()
+        cnt = (C.c_int64 * _lib.JSP_N_KERNELS)()
+        self._check(self._lib.jsp_batch_time_runs(self._h, warmup, iters, 1 if flush_l2 else 0, C.byref(ms), kms, cnt), "jsp_batch_time_runs")
+        return ms.value, list(kms), list(cnt)
+
+    def stats(self):
+        v = [C.c_uint64(0) for _ in range(4)]
+        self._lib.jsp_batch_stats(self._h, *[C.byref(x) for x in v])
+        return dict(pixels=v[0].value, alg_bytes=v[1].value, in_bytes=v[2].value, out_bytes=v[3].value)
+
+    def device_frame_ptr(self, i):
+        return int(self._lib.jsp_batch_device_frame(self._h, int(i)))

@@ -1,0 +1,676 @@
+// batch.cu -- host side of the batch decode path of libjsplayer_cuda (C ABI: include/jsplayer_cuda.h).
+//
+// Takes the per-stream frame tables the reference's loaders build (src/DataLoader.hx:31 `frames`,
+// src/VideoData.hx:68-73 CompressedFrame) for MANY streams, lays bitstreams and output pictures out in
+// HBM, orders frames into dependency levels (a frame that copies from the previous picture runs one
+// level after it; key frames and frames of other streams run concurrently -- the GOP independence the
+// reference relies on when seeking, src/Manager.hx:244-249) and launches the sm_100a kernels.
+// No CPU decode path exists here: without a CUDA device every entry point fails.
+#include "batch.cuh"
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+
+namespace jsp {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+bool cuda_ok(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return true;
+    set_error("CUDA error %s: %s", cudaGetErrorString(e), what);
+    return false;
+}
+
+template <typename T>
+static bool grow(T *&p, size_t &cap, size_t need, bool zero = false)
+{
+    if (need <= cap && p) return true;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t n = need + need / 8 + 64;
+    if (!JSP_CUDA(cudaMalloc((void **)&p, n * sizeof(T)))) return false;
+    if (zero && !JSP_CUDA(cudaMemset(p, 0, n * sizeof(T)))) return false;
+    cap = n;
+    return true;
+}
+
+// MSVideo1.hx:86-104
+static bool msv16_just_skips(const uint8_t *src, uint32_t len, uint32_t nblocks)
+{
+    uint32_t si = 0, n = 0;
+    while (si < len) {
+        if (si + 1 >= len) return false;                 // (undefined & 0xFC) != 0x84
+        const uint32_t a = src[si], b = src[si + 1];
+        if ((b & 0xFC) != 0x84) return false;
+        n += ((b - 0x84) << 8) + a;
+        if (n >= nblocks) return true;
+        si += 2;
+    }
+    return true;
+}
+
+// MSVideo1.hx:109-110: the RGB555 decoder returns the previous buffer untouched
+bool msv16_unchanged(int w, int h, const uint8_t *src, uint32_t len)
+{
+    const uint32_t nblocks = (uint32_t)(w >> 2) * (uint32_t)(h >> 2);
+    const uint32_t sjs = nblocks / 1023 * 2 + 10;         // MSVideo1.hx:29-30
+    return len == 0 || nblocks == 0 || (len < sjs && msv16_just_skips(src, len, nblocks));
+}
+
+static int classify(const StreamRec &S, const uint8_t *src, uint32_t len)
+{
+    if (S.codec == JSP_CODEC_MSVC16) return msv16_unchanged(S.w, S.h, src, len) ? FK_COPY : FK_MSV16;
+    if (S.codec == JSP_CODEC_MSVC8) {
+        if ((S.w >> 2) == 0 || (S.h >> 2) == 0) return FK_COPY;
+        return FK_MSV8;
+    }
+    return FK_SP;
+}
+
+struct HostTables {
+    std::vector<Msv1Frame> mframes;
+    std::vector<uint2> tile_tab;
+    std::vector<CopyJob> jobs;
+};
+
+// Builds the launch list of `plan` for streams [s_lo, s_hi).
+static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables &T, size_t &state_cursor, size_t &ticket_cursor)
+{
+    plan.launches.clear(); plan.uploads.clear();
+    plan.frame_lo = b->streams[s_lo].first_frame;
+    plan.frame_hi = b->streams[s_hi - 1].first_frame + b->streams[s_hi - 1].n_frames;
+    plan.tile_tab_off = T.tile_tab.size();
+    plan.job_off = T.jobs.size();
+    plan.state_off = state_cursor;
+    plan.ticket_off = ticket_cursor;
+
+    int max_level = 0;
+    for (int64_t f = plan.frame_lo; f < plan.frame_hi; f++) max_level = std::max(max_level, b->frames[f].level);
+    std::vector<std::vector<int64_t>> by_level(max_level + 1);
+    for (int64_t f = plan.frame_lo; f < plan.frame_hi; f++) by_level[b->frames[f].level].push_back(f);
+
+    for (int lv = 0; lv <= max_level; lv++) {
+        // whole-picture copies (unchanged frames)
+        {
+            const size_t first = T.jobs.size(); uint32_t maxv = 0;
+            for (int64_t f : by_level[lv]) {
+                FrameRec &R = b->frames[f];
+                if (R.kind != FK_COPY) continue;
+                const StreamRec &S = b->streams[R.stream];
+                CopyJob J;
+                J.dst = b->d_out + R.out_off;
+                J.src = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
+                J.value = 0;
+                J.n_vec4 = (uint32_t)(((size_t)S.w * S.h * 4 + 15) / 16);
+                maxv = std::max(maxv, J.n_vec4);
+                T.jobs.push_back(J);
+            }
+            if (T.jobs.size() > first)
+                plan.launches.push_back({JSP_K_FRAME_COPY, FK_COPY, first, (uint32_t)(T.jobs.size() - first), maxv, 0});
+        }
+        // MSVideo1, one launch per pixel format; tiles are listed tile-major so that a tile's
+        // predecessors in its frame were handed out a whole "row" of frames earlier
+        for (int kind = FK_MSV16; kind <= FK_MSV8; kind++) {
+            std::vector<int64_t> fr;
+            uint32_t max_tiles = 0;
+            for (int64_t f : by_level[lv])
+                if (b->frames[f].kind == kind) { fr.push_back(f); max_tiles = std::max(max_tiles, b->frames[f].n_tiles); }
+            if (fr.empty()) continue;
+            std::sort(fr.begin(), fr.end(), [&](int64_t x, int64_t y) {
+                return b->frames[x].n_tiles != b->frames[y].n_tiles ? b->frames[x].n_tiles > b->frames[y].n_tiles : x < y; });
+            const size_t first = T.tile_tab.size();
+            for (int64_t f : fr) { b->frames[f].state_base = (uint32_t)state_cursor; state_cursor += b->frames[f].n_tiles; }
+            size_t live = fr.size();
+            for (uint32_t t = 0; t < max_tiles; t++) {
+                while (live > 0 && b->frames[fr[live - 1]].n_tiles <= t) live--;
+                for (size_t i = 0; i < live; i++) T.tile_tab.push_back(make_uint2((uint32_t)fr[i], t));
+            }
+            plan.launches.push_back({JSP_K_MSV1_DECODE, kind, first, (uint32_t)(T.tile_tab.size() - first), 0, (uint32_t)ticket_cursor});
+            ticket_cursor++;
+        }
+    }
+    plan.n_tile_entries = T.tile_tab.size() - plan.tile_tab_off;
+    plan.n_jobs = T.jobs.size() - plan.job_off;
+    plan.n_states = state_cursor - plan.state_off;
+    plan.n_tickets = ticket_cursor - plan.ticket_off;
+
+    // uploads: one range per stream, merged when the host ranges are (nearly) adjacent
+    for (int s = s_lo; s < s_hi; s++) {
+        const StreamRec &S = b->streams[s];
+        if (S.h_hi <= S.h_lo) continue;
+        CopyRange r{S.h_bytes + S.h_lo, S.d_base, (size_t)(S.h_hi - S.h_lo)};
+        if (!plan.uploads.empty()) {
+            CopyRange &p = plan.uploads.back();
+            const uint8_t *pend = p.h + p.bytes;
+            if (r.h >= pend && (size_t)(r.h - pend) < 4096 && r.d_off == p.d_off + (size_t)(r.h - p.h)) {
+                p.bytes = (size_t)(r.h - p.h) + r.bytes;
+                continue;
+            }
+        }
+        plan.uploads.push_back(r);
+    }
+}
+
+static void fill_mframes(jsp_batch *b, HostTables &T)
+{
+    T.mframes.assign(b->frames.size(), Msv1Frame{});
+    for (size_t f = 0; f < b->frames.size(); f++) {
+        const FrameRec &R = b->frames[f];
+        if (R.kind != FK_MSV16 && R.kind != FK_MSV8) continue;
+        const StreamRec &S = b->streams[R.stream];
+        Msv1Frame &M = T.mframes[f];
+        M.src = b->d_bytes + R.d_src;
+        M.out = b->d_out + R.out_off;
+        // a frame scheduled at level 0 is not ordered after its predecessor: it must not read it
+        M.prev = (R.prev >= 0 && R.level > 0) ? b->d_out + b->frames[R.prev].out_off
+                                               : (R.prev < 0 ? b->ext_prev : nullptr);
+        M.pal = S.pal_off != SIZE_MAX ? b->d_pal + S.pal_off : nullptr;
+        M.status = b->d_status + f;
+        M.len = R.len;
+        M.X = (uint32_t)S.w;
+        M.nbx = (uint32_t)(S.w >> 2);
+        M.nblocks = (uint32_t)(S.w >> 2) * (uint32_t)(S.h >> 2);
+        M.n_tiles = R.n_tiles;
+        M.state_base = R.state_base;
+        M.insign_blocks = (uint32_t)std::max(0, (b->insign_lines + 3) >> 2);
+        M.flags = R.prev >= 0 ? MSV1_F_HAS_PRED : 0u;
+    }
+}
+
+static bool upload_tables(jsp_batch *b, HostTables &T, size_t n_states, size_t n_tickets)
+{
+    if (!grow(b->d_mframes, b->mframes_cap, T.mframes.size())) return false;
+    if (!grow(b->d_tile_tab, b->tile_tab_cap, T.tile_tab.size() + 1)) return false;
+    if (!grow(b->d_jobs, b->jobs_cap, T.jobs.size() + 1)) return false;
+    if (n_states + 1 > b->states_cap) {
+        if (b->d_tile_map) cudaFree(b->d_tile_map);
+        if (b->d_tile_cnt) cudaFree(b->d_tile_cnt);
+        b->d_tile_map = b->d_tile_cnt = nullptr; b->states_cap = 0;
+        const size_t n = n_states + n_states / 8 + 64;
+        if (!JSP_CUDA(cudaMalloc((void **)&b->d_tile_map, n * 8))) return false;
+        if (!JSP_CUDA(cudaMalloc((void **)&b->d_tile_cnt, n * 8))) return false;
+        b->states_cap = n;
+    }
+    if (!grow(b->d_tickets, b->tickets_cap, n_tickets + 1)) return false;
+    if (!T.mframes.empty() && !JSP_CUDA(cudaMemcpy(b->d_mframes, T.mframes.data(), T.mframes.size() * sizeof(Msv1Frame), cudaMemcpyHostToDevice))) return false;
+    if (!T.tile_tab.empty() && !JSP_CUDA(cudaMemcpy(b->d_tile_tab, T.tile_tab.data(), T.tile_tab.size() * sizeof(uint2), cudaMemcpyHostToDevice))) return false;
+    if (!T.jobs.empty() && !JSP_CUDA(cudaMemcpy(b->d_jobs, T.jobs.data(), T.jobs.size() * sizeof(CopyJob), cudaMemcpyHostToDevice))) return false;
+    return true;
+}
+
+static bool run_plan(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *ev = nullptr, std::vector<int> *ev_class = nullptr)
+{
+    if (P.n_states) {
+        if (!JSP_CUDA(cudaMemsetAsync(b->d_tile_map + P.state_off, 0, P.n_states * 8, st))) return false;
+        if (!JSP_CUDA(cudaMemsetAsync(b->d_tile_cnt + P.state_off, 0, P.n_states * 8, st))) return false;
+    }
+    if (P.n_tickets && !JSP_CUDA(cudaMemsetAsync(b->d_tickets + P.ticket_off, 0, P.n_tickets * 4, st))) return false;
+    if (P.frame_hi > P.frame_lo &&
+        !JSP_CUDA(cudaMemsetAsync(b->d_status + P.frame_lo, 0, (size_t)(P.frame_hi - P.frame_lo) * 4, st))) return false;
+    int k = 0;
+    for (const Launch &L : P.launches) {
+        if (ev) { cudaEventRecord(ev[k], st); ev_class->push_back(L.kclass); k++; }
+        switch (L.kclass) {
+        case JSP_K_FRAME_COPY:
+            launch_frame_copy(b->d_jobs + L.first, L.count, L.max_vec4, b->sm_count, st);
+            break;
+        case JSP_K_MSV1_DECODE:
+            launch_msv1_decode(L.kind == FK_MSV8, b->d_mframes, b->d_tile_tab + L.first, L.count,
+                               b->d_tile_map, b->d_tile_cnt, b->d_tickets + L.ticket, st);
+            break;
+        default: break;
+        }
+    }
+    if (ev) cudaEventRecord(ev[k], st);
+    return JSP_CUDA(cudaGetLastError());
+}
+
+
+// (Re)computes dependency levels from the key flags, rebuilds the launch plan and uploads the tables.
+static bool plan_and_upload(jsp_batch *b)
+{
+    for (const StreamRec &S : b->streams) {
+        int level = -1;
+        for (int f = 0; f < S.n_frames; f++) {
+            FrameRec &R = b->frames[S.first_frame + f];
+            // key frames do not depend on the previous picture; everything else runs one level later
+            const bool independent = R.key && R.kind != FK_COPY;
+            level = (independent || f == 0) ? 0 : level + 1;
+            R.level = level;
+        }
+    }
+    HostTables T;
+    size_t state_cursor = 0, ticket_cursor = 0;
+    build_plan(b, b->whole, 0, (int)b->streams.size(), T, state_cursor, ticket_cursor);
+    fill_mframes(b, T);
+    return upload_tables(b, T, state_cursor, ticket_cursor);
+}
+
+// prevFrame bookkeeping + significance (post-pass over the frames of a plan)
+static bool run_status(jsp_batch *b, cudaStream_t st)
+{
+    launch_status_scan(b->d_status, b->d_stream_first, b->d_stream_count, (uint32_t)b->streams.size(), b->ext_has_prev, st);
+    const int exact = (b->flags & JSP_BATCH_SIGNIFICANCE) ? 1 : 0;
+    if (exact && b->n_sig)
+        launch_signif(b->d_sig_cur, b->d_sig_prev, b->d_sig_status, b->d_sig_first, b->d_sig_npx, (uint32_t)b->n_sig, b->sm_count, st);
+    launch_status_final(b->d_status, b->d_frame_codec, (uint32_t)b->frames.size(), exact, st);
+    return JSP_CUDA(cudaGetLastError());
+}
+
+}  // namespace jsp
+
+using namespace jsp;
+
+extern "C" {
+
+int jsp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+const char *jsp_last_error(void) { return g_err; }
+const char *jsp_version(void) { return "jsplayer_cuda 0.1 (sm_100a)"; }
+
+void *jsp_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (!JSP_CUDA(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable))) return nullptr;
+    return p;
+}
+void jsp_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+jsp_batch *jsp_batch_create(int device, int insignificant_lines, int flags)
+{
+    int n = jsp_device_count();
+    if (n <= 0) { set_error("no CUDA device: libjsplayer_cuda has no CPU fallback"); return nullptr; }
+    if (device < 0) { if (!JSP_CUDA(cudaGetDevice(&device))) return nullptr; }
+    if (device >= n) { set_error("device %d out of range (%d devices)", device, n); return nullptr; }
+    if (!JSP_CUDA(cudaSetDevice(device))) return nullptr;
+    jsp_batch *b = new jsp_batch();
+    b->device = device; b->insign_lines = insignificant_lines; b->flags = flags;
+    cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (!JSP_CUDA(cudaStreamCreateWithFlags(&b->st_compute, cudaStreamNonBlocking)) ||
+        !JSP_CUDA(cudaStreamCreateWithFlags(&b->st_in, cudaStreamNonBlocking)) ||
+        !JSP_CUDA(cudaStreamCreateWithFlags(&b->st_out, cudaStreamNonBlocking))) { delete b; return nullptr; }
+    return b;
+}
+
+void jsp_batch_destroy(jsp_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaDeviceSynchronize();
+    for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
+    void *ptrs[] = {b->d_bytes, b->d_out, b->d_pal, b->d_status, b->d_mframes, b->d_tile_tab, b->d_jobs, b->d_tile_map,
+                    b->d_tile_cnt, b->d_tickets, b->d_sig_cur, b->d_sig_prev, b->d_sig_status, b->d_sig_first, b->d_sig_npx,
+                    b->d_stream_first, b->d_stream_count, b->d_frame_codec, b->d_flush};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (b->h_status) cudaFreeHost(b->h_status);
+    if (b->st_compute) cudaStreamDestroy(b->st_compute);
+    if (b->st_in) cudaStreamDestroy(b->st_in);
+    if (b->st_out) cudaStreamDestroy(b->st_out);
+    delete b;
+}
+
+int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_streams)
+{
+    if (!b || !sd || n_streams <= 0) { set_error("jsp_batch_configure: bad arguments"); return -1; }
+    if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
+    b->streams.clear(); b->frames.clear(); b->chunks.clear();
+    size_t bytes_cur = 0, out_cur = 0, pal_cur = 0;
+    int64_t nf = 0;
+    bool remainder = false;
+    b->stat_pixels = b->stat_alg_bytes = b->stat_in_bytes = b->stat_out_bytes = 0;
+    for (int s = 0; s < n_streams; s++) {
+        const jsp_stream_desc &D = sd[s];
+        if (D.width <= 0 || D.height <= 0 || D.n_frames < 0 || (D.n_frames > 0 && (!D.frame_off || !D.frame_len || !D.frame_key))) {
+            set_error("stream %d: bad descriptor", s); return -1;
+        }
+        if (D.codec != JSP_CODEC_MSVC16 && D.codec != JSP_CODEC_MSVC8 && D.codec != JSP_CODEC_SCREENPRESSOR) {
+            set_error("stream %d: unknown codec %d", s, D.codec); return -1;
+        }
+        StreamRec S{};
+        S.codec = D.codec; S.w = D.width; S.h = D.height; S.bpp = D.bpp; S.n_frames = D.n_frames;
+        S.first_frame = nf; S.h_bytes = D.bytes; S.pal_off = SIZE_MAX;
+        if (D.codec == JSP_CODEC_MSVC8) { S.pal_off = pal_cur; pal_cur += 256; }
+        if (D.codec != JSP_CODEC_SCREENPRESSOR && ((D.width & 3) || (D.height & 3))) remainder = true;
+        uint64_t lo = UINT64_MAX, hi = 0;
+        for (int f = 0; f < D.n_frames; f++) {
+            if (D.frame_len[f] == 0) continue;
+            lo = std::min<uint64_t>(lo, D.frame_off[f]);
+            hi = std::max<uint64_t>(hi, D.frame_off[f] + D.frame_len[f]);
+        }
+        if (lo == UINT64_MAX) lo = hi = 0;
+        if (hi > lo && !D.bytes) { set_error("stream %d: bytes is NULL", s); return -1; }
+        S.h_lo = lo; S.h_hi = hi;
+        // keep the host address modulo 16 so that 16-byte aligned frames stay aligned in HBM
+        const size_t mis = (size_t)(reinterpret_cast<uintptr_t>(D.bytes + lo) & 15u);
+        if (s > 0 && b->streams.back().h_hi > b->streams.back().h_lo) {
+            // adjacent in host memory => adjacent in HBM (lets uploads merge into large copies)
+            const StreamRec &Pv = b->streams.back();
+            const uint8_t *pend = Pv.h_bytes + Pv.h_hi;
+            const uint8_t *cur = D.bytes + lo;
+            if (hi > lo && cur >= pend && (size_t)(cur - pend) < 4096) bytes_cur = Pv.d_base + (size_t)(cur - (Pv.h_bytes + Pv.h_lo));
+            else bytes_cur = ((bytes_cur + 255) & ~(size_t)255) + mis;
+        } else bytes_cur = ((bytes_cur + 255) & ~(size_t)255) + mis;
+        S.d_base = bytes_cur;
+        bytes_cur += (size_t)(hi - lo);
+        const size_t npix = (size_t)D.width * D.height;
+        const size_t npix_pad = (npix + 63) & ~(size_t)63;
+        for (int f = 0; f < D.n_frames; f++) {
+            FrameRec R{};
+            R.stream = s; R.len = D.frame_len[f]; R.key = D.frame_key[f] ? 1 : 0;
+            R.d_src = S.d_base + (size_t)(D.frame_len[f] ? D.frame_off[f] - lo : 0);
+            R.out_off = out_cur; out_cur += npix_pad;
+            R.prev = f > 0 ? nf + f - 1 : -1;
+            R.kind = classify(S, D.bytes ? D.bytes + D.frame_off[f] : nullptr, R.len);
+            R.level = 0;   // assigned by plan_and_upload()
+            R.n_tiles = (R.kind == FK_MSV16 || R.kind == FK_MSV8)
+                            ? std::max<uint32_t>(1u, (uint32_t)(((size_t)((R.len + 1) >> 1) + MSV1_TILE_WORDS - 1) / MSV1_TILE_WORDS)) : 0u;
+            b->frames.push_back(R);
+            b->stat_pixels += npix;
+            b->stat_alg_bytes += npix * 4 + R.len + (R.kind == FK_COPY ? npix * 4 : 0);
+            b->stat_in_bytes += R.len;
+            b->stat_out_bytes += npix * 4;
+        }
+        nf += D.n_frames;
+        b->streams.push_back(S);
+    }
+    if (nf == 0) { set_error("no frames"); return -1; }
+    const size_t out_old = b->out_cap;
+    if (!grow(b->d_bytes, b->bytes_cap, bytes_cur + 64)) return -1;
+    if (!grow(b->d_out, b->out_cap, out_cur, true)) return -1;
+    if (remainder && out_old == b->out_cap && !JSP_CUDA(cudaMemset(b->d_out, 0, b->out_cap * 4))) return -1;
+    if (!grow(b->d_pal, b->pal_cap, pal_cur + 1)) return -1;
+    if (!grow(b->d_status, b->status_cap, (size_t)nf)) return -1;
+    b->bytes_used = bytes_cur; b->out_used = out_cur;
+    if ((size_t)nf > b->h_status_cap) {
+        if (b->h_status) cudaFreeHost(b->h_status);
+        b->h_status = nullptr; b->h_status_cap = 0;
+        if (!JSP_CUDA(cudaHostAlloc((void **)&b->h_status, (size_t)nf * 4, cudaHostAllocDefault))) return -1;
+        b->h_status_cap = (size_t)nf;
+    }
+    // palettes: MSVideo1.hx:281-291 -- up to 256 little-endian B,G,R,x quads, missing entries 0
+    for (int s = 0; s < n_streams; s++) {
+        if (b->streams[s].pal_off == SIZE_MAX) continue;
+        int32_t pal[256]; memset(pal, 0, sizeof pal);
+        const int n = sd[s].palette ? std::min(256, sd[s].palette_bytes / 4) : 0;
+        for (int i = 0; i < n; i++) {
+            const uint8_t *p = sd[s].palette + 4 * i;
+            pal[i] = (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+        }
+        if (!JSP_CUDA(cudaMemcpy(b->d_pal + b->streams[s].pal_off, pal, sizeof pal, cudaMemcpyHostToDevice))) return -1;
+    }
+    if (!plan_and_upload(b)) return -1;
+
+    // status post-pass tables
+    {
+        std::vector<uint32_t> sfirst, scount; std::vector<uint8_t> fcodec(b->frames.size());
+        for (const StreamRec &S : b->streams) { sfirst.push_back((uint32_t)S.first_frame); scount.push_back((uint32_t)S.n_frames); }
+        std::vector<const int32_t *> cur, prev; std::vector<uint32_t *> stp; std::vector<uint32_t> first, npx;
+        for (size_t f = 0; f < b->frames.size(); f++) {
+            const FrameRec &R = b->frames[f]; const StreamRec &S = b->streams[R.stream];
+            fcodec[f] = (uint8_t)S.codec;
+            if (S.codec == JSP_CODEC_MSVC16 && (R.prev >= 0 || b->ext_prev) && R.kind == FK_MSV16) {
+                cur.push_back(b->d_out + R.out_off); prev.push_back(R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev);
+                stp.push_back(b->d_status + f);
+                const size_t np = (size_t)S.w * S.h;
+                first.push_back((uint32_t)std::min<size_t>(np, (size_t)std::max(0, b->insign_lines) * S.w)); npx.push_back((uint32_t)np);
+            }
+        }
+        if (!grow(b->d_stream_first, b->streams_cap, sfirst.size())) return -1;
+        if (!grow(b->d_stream_count, b->streams_cap2, scount.size())) return -1;
+        if (!grow(b->d_frame_codec, b->frame_codec_cap, fcodec.size())) return -1;
+        cudaMemcpy(b->d_stream_first, sfirst.data(), sfirst.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(b->d_stream_count, scount.data(), scount.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(b->d_frame_codec, fcodec.data(), fcodec.size(), cudaMemcpyHostToDevice);
+        b->n_sig = cur.size();
+        if (b->n_sig > b->sig_cap) {
+            void *old[] = {b->d_sig_cur, b->d_sig_prev, b->d_sig_status, b->d_sig_first, b->d_sig_npx};
+            for (void *p : old) if (p) cudaFree(p);
+            const size_t n = b->n_sig + 64;
+            if (!JSP_CUDA(cudaMalloc((void **)&b->d_sig_cur, n * 8)) || !JSP_CUDA(cudaMalloc((void **)&b->d_sig_prev, n * 8)) ||
+                !JSP_CUDA(cudaMalloc((void **)&b->d_sig_status, n * 8)) || !JSP_CUDA(cudaMalloc((void **)&b->d_sig_first, n * 4)) ||
+                !JSP_CUDA(cudaMalloc((void **)&b->d_sig_npx, n * 4))) return -1;
+            b->sig_cap = n;
+        }
+        if (b->n_sig) {
+            cudaMemcpy(b->d_sig_cur, cur.data(), cur.size() * 8, cudaMemcpyHostToDevice);
+            cudaMemcpy(b->d_sig_prev, prev.data(), prev.size() * 8, cudaMemcpyHostToDevice);
+            cudaMemcpy(b->d_sig_status, stp.data(), stp.size() * 8, cudaMemcpyHostToDevice);
+            cudaMemcpy(b->d_sig_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(b->d_sig_npx, npx.data(), npx.size() * 4, cudaMemcpyHostToDevice);
+        }
+    }
+    if (!JSP_CUDA(cudaGetLastError())) return -1;
+    return nf;
+}
+
+int jsp_batch_upload(jsp_batch *b)
+{
+    if (!b) return -1;
+    if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
+    for (const CopyRange &r : b->whole.uploads)
+        if (!JSP_CUDA(cudaMemcpyAsync(b->d_bytes + r.d_off, r.h, r.bytes, cudaMemcpyHostToDevice, b->st_compute))) return -1;
+    return 0;
+}
+
+int jsp_batch_run(jsp_batch *b)
+{
+    if (!b) return -1;
+    if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
+    if (!run_plan(b, b->whole, b->st_compute)) return -1;
+    if (!run_status(b, b->st_compute)) return -1;
+    return 0;
+}
+
+int jsp_batch_sync(jsp_batch *b)
+{
+    if (!b) return -1;
+    if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
+    return JSP_CUDA(cudaStreamSynchronize(b->st_compute)) ? 0 : -1;
+}
+
+static uint8_t public_flags(uint32_t v)
+{
+    uint8_t f = 0;
+    if (v & ST_CHANGED) f |= JSP_FRAME_CHANGED;
+    if (v & ST_SIGNIFICANT) f |= JSP_FRAME_SIGNIFICANT;
+    if (v & (ST_ERROR | ST_NEEDS_PREV)) f |= JSP_FRAME_ERROR;
+    return f;
+}
+
+int jsp_batch_results(jsp_batch *b, uint8_t *flags)
+{
+    if (!b) return -1;
+    if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
+    const size_t n = b->frames.size();
+    if (!JSP_CUDA(cudaMemcpyAsync(b->h_status, b->d_status, n * 4, cudaMemcpyDeviceToHost, b->st_compute))) return -1;
+    if (!JSP_CUDA(cudaStreamSynchronize(b->st_compute))) return -1;
+    // A frame the caller flagged as key (so it was scheduled without waiting for its predecessor) that
+    // nevertheless copies from the previous picture: demote it, re-level, decode again in order.
+    bool demoted = false;
+    for (size_t i = 0; i < n; i++)
+        if ((b->h_status[i] & ST_NEEDS_PREV) && b->frames[i].key) { b->frames[i].key = 0; demoted = true; }
+    if (demoted) {
+        if (!plan_and_upload(b)) return -1;
+        if (jsp_batch_run(b)) return -1;
+        b->rerun_count++;
+        return jsp_batch_results(b, flags);
+    }
+    if (flags) for (size_t i = 0; i < n; i++) flags[i] = public_flags(b->h_status[i]);
+    return 0;
+}
+
+// D2H of pictures [lo, hi) on stream st; adjacent host destinations are merged into one copy
+static bool download_range(jsp_batch *b, int64_t lo, int64_t hi, int32_t *const *out_frames, cudaStream_t st)
+{
+    int64_t i = lo;
+    while (i < hi) {
+        if (!out_frames[i]) { i++; continue; }
+        const FrameRec &R = b->frames[i]; const StreamRec &S = b->streams[R.stream];
+        const size_t npix = (size_t)S.w * S.h;
+        const bool rem = S.codec != JSP_CODEC_SCREENPRESSOR && ((S.w & 3) || (S.h & 3));
+        if (rem) {   // the codec never writes the width/height remainder mod 4: leave the caller's pixels alone
+            const size_t bw = (size_t)(S.w & ~3), bh = (size_t)(S.h & ~3);
+            if (bw && bh && !JSP_CUDA(cudaMemcpy2DAsync(out_frames[i], (size_t)S.w * 4, b->d_out + R.out_off, (size_t)S.w * 4,
+                                                        bw * 4, bh, cudaMemcpyDeviceToHost, st))) return false;
+            i++; continue;
+        }
+        int64_t j = i + 1; size_t bytes = npix * 4;
+        while (j < hi && out_frames[j] && out_frames[j] == out_frames[j - 1] + ((size_t)b->streams[b->frames[j - 1].stream].w * b->streams[b->frames[j - 1].stream].h) &&
+               b->frames[j].out_off == b->frames[j - 1].out_off + ((size_t)b->streams[b->frames[j - 1].stream].w * b->streams[b->frames[j - 1].stream].h) &&
+               !((b->streams[b->frames[j].stream].w & 3) || (b->streams[b->frames[j].stream].h & 3)) && bytes < ((size_t)1 << 30)) {
+            bytes += (size_t)b->streams[b->frames[j].stream].w * b->streams[b->frames[j].stream].h * 4; j++;
+        }
+        if (!JSP_CUDA(cudaMemcpyAsync(out_frames[i], b->d_out + R.out_off, bytes, cudaMemcpyDeviceToHost, st))) return false;
+        i = j;
+    }
+    return true;
+}
+
+int jsp_batch_download(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags)
+{
+    if (!b) return -1;
+    if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
+    if (jsp_batch_results(b, flags)) return -1;
+    if (out_frames && !download_range(b, 0, (int64_t)b->frames.size(), out_frames, b->st_compute)) return -1;
+    return JSP_CUDA(cudaStreamSynchronize(b->st_compute)) ? 0 : -1;
+}
+
+int jsp_batch_decode_host(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags)
+{
+    // round 1: upload, decode and download are issued back to back on one stream; the chunked
+    // three-stream PCIe pipeline replaces this body without changing the contract
+    if (jsp_batch_upload(b)) return -1;
+    if (jsp_batch_run(b)) return -1;
+    return jsp_batch_download(b, out_frames, flags);
+}
+
+uint64_t jsp_batch_device_frame(jsp_batch *b, int64_t i)
+{
+    if (!b || i < 0 || (size_t)i >= b->frames.size()) return 0;
+    return (uint64_t)reinterpret_cast<uintptr_t>(b->d_out + b->frames[i].out_off);
+}
+
+int jsp_batch_stats(jsp_batch *b, uint64_t *pixels, uint64_t *alg_bytes, uint64_t *in_bytes, uint64_t *out_bytes)
+{
+    if (!b) return -1;
+    if (pixels) *pixels = b->stat_pixels;
+    if (alg_bytes) *alg_bytes = b->stat_alg_bytes;
+    if (in_bytes) *in_bytes = b->stat_in_bytes;
+    if (out_bytes) *out_bytes = b->stat_out_bytes;
+    return 0;
+}
+
+int jsp_batch_time_runs(jsp_batch *b, int warmup, int iters, int flush_l2, float *ms_total, float *kernel_ms, int64_t *launches)
+{
+    if (!b || iters <= 0) return -1;
+    if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
+    cudaStream_t st = b->st_compute;
+    if (flush_l2 && !b->d_flush) {
+        b->flush_bytes = (size_t)512 << 20;      // > 126 MB L2
+        if (!JSP_CUDA(cudaMalloc(&b->d_flush, b->flush_bytes))) return -1;
+    }
+    for (int i = 0; i < warmup; i++) if (jsp_batch_run(b)) return -1;
+    if (!JSP_CUDA(cudaStreamSynchronize(st))) return -1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float total = 0.f;
+    for (int i = 0; i < iters; i++) {
+        if (flush_l2) cudaMemsetAsync(b->d_flush, i & 0xFF, b->flush_bytes, st);
+        cudaEventRecord(e0, st);
+        if (jsp_batch_run(b)) return -1;
+        cudaEventRecord(e1, st);
+        if (!JSP_CUDA(cudaEventSynchronize(e1))) return -1;
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        total += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_total) *ms_total = total;
+    if (kernel_ms || launches) {
+        // attribution pass: one extra run with an event in front of every launch
+        const size_t n = b->whole.launches.size();
+        while (b->ev_pool.size() < n + 1) { cudaEvent_t e; cudaEventCreate(&e); b->ev_pool.push_back(e); }
+        float acc[JSP_N_KERNELS] = {0}; int64_t cnt[JSP_N_KERNELS] = {0};
+        for (int i = 0; i < iters; i++) {
+            if (flush_l2) cudaMemsetAsync(b->d_flush, i & 0xFF, b->flush_bytes, st);
+            std::vector<int> cls;
+            if (!run_plan(b, b->whole, st, b->ev_pool.data(), &cls)) return -1;
+            if (!JSP_CUDA(cudaStreamSynchronize(st))) return -1;
+            for (size_t k = 0; k < cls.size(); k++) {
+                float ms = 0.f; cudaEventElapsedTime(&ms, b->ev_pool[k], b->ev_pool[k + 1]);
+                acc[cls[k]] += ms; cnt[cls[k]]++;
+            }
+            if (!run_status(b, st)) return -1;
+        }
+        for (int k = 0; k < JSP_N_KERNELS; k++) { if (kernel_ms) kernel_ms[k] = acc[k]; if (launches) launches[k] = cnt[k]; }
+    }
+    return 0;
+}
+
+int jsp_batch_decode(const jsp_stream_desc *streams, int n_streams, int n_gpus, int32_t *const *out_frames,
+                     uint8_t *out_changed, uint8_t *out_significant, int32_t *out_status)
+{
+    if (!streams || n_streams <= 0) { set_error("jsp_batch_decode: bad arguments"); return -1; }
+    const int ndev = jsp_device_count();
+    if (ndev <= 0) { set_error("no CUDA device: libjsplayer_cuda has no CPU fallback"); return -1; }
+    if (n_gpus <= 0) n_gpus = 1;
+    n_gpus = std::min(std::min(n_gpus, ndev), n_streams);
+    // longest-first round robin of whole streams over the devices: no exchange step exists
+    std::vector<int64_t> first(n_streams + 1, 0);
+    std::vector<uint64_t> weight(n_streams, 0);
+    for (int s = 0; s < n_streams; s++) {
+        first[s + 1] = first[s] + streams[s].n_frames;
+        for (int f = 0; f < streams[s].n_frames; f++) weight[s] += streams[s].frame_len[f] + (uint64_t)streams[s].width * streams[s].height / 8;
+    }
+    std::vector<int> order(n_streams);
+    for (int s = 0; s < n_streams; s++) order[s] = s;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return weight[x] > weight[y]; });
+    std::vector<std::vector<int>> shard(n_gpus);
+    std::vector<uint64_t> load(n_gpus, 0);
+    for (int s : order) {
+        int g = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        shard[g].push_back(s); load[g] += weight[s];
+    }
+    std::vector<int> rc(n_gpus, 0);
+    std::vector<std::string> errs(n_gpus);
+    auto work = [&](int g) {
+        std::sort(shard[g].begin(), shard[g].end());
+        std::vector<jsp_stream_desc> sd; std::vector<int32_t *> outs; std::vector<int64_t> gidx;
+        for (int s : shard[g]) {
+            sd.push_back(streams[s]);
+            for (int f = 0; f < streams[s].n_frames; f++) { outs.push_back(out_frames ? out_frames[first[s] + f] : nullptr); gidx.push_back(first[s] + f); }
+        }
+        if (sd.empty()) return;
+        jsp_batch *b = jsp_batch_create(g, 0, JSP_BATCH_SIGNIFICANCE);
+        std::vector<uint8_t> fl(outs.size());
+        if (!b || jsp_batch_configure(b, sd.data(), (int)sd.size()) < 0 || jsp_batch_decode_host(b, outs.data(), fl.data())) {
+            rc[g] = -1; errs[g] = jsp_last_error();
+        } else {
+            for (size_t i = 0; i < gidx.size(); i++) {
+                if (out_changed) out_changed[gidx[i]] = (fl[i] & JSP_FRAME_CHANGED) ? 1 : 0;
+                if (out_significant) out_significant[gidx[i]] = (fl[i] & JSP_FRAME_SIGNIFICANT) ? 1 : 0;
+                if (out_status) out_status[gidx[i]] = (fl[i] & JSP_FRAME_ERROR) ? JSP_ERROR_OCCURED : JSP_ZERO_STATE;
+            }
+        }
+        jsp_batch_destroy(b);
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < n_gpus; g++) th.emplace_back(work, g);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int g = 0; g < n_gpus; g++) if (rc[g]) { set_error("gpu %d: %s", g, errs[g].c_str()); return -1; }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// batch.cuh -- host-side batcher of libjsplayer_cuda: frame / GOP tables, launch plans, device arenas.
+// Plays the role DataLoader's frame table + Manager.worker's frame loop play in the reference
+// (src/DataLoader.hx:31,93-98; src/Manager.hx:454-525), for many streams at once.
+#pragma once
+#include "common.cuh"
+#include "../../include/jsplayer_cuda.h"
+#include <string>
+#include <vector>
+
+namespace jsp {
+
+void set_error(const char *fmt, ...);
+bool cuda_ok(cudaError_t e, const char *what);
+bool msv16_unchanged(int w, int h, const uint8_t *src, uint32_t len);
+#define JSP_CUDA(call) ::jsp::cuda_ok((call), #call)
+
+enum FrameKind : int { FK_MSV16 = 0, FK_MSV8 = 1, FK_COPY = 2, FK_SP = 3 };
+
+struct StreamRec {
+    int codec, w, h, bpp;
+    int n_frames;
+    int64_t first_frame;            // global index of frame 0
+    const uint8_t *h_bytes;         // host base pointer
+    uint64_t h_lo, h_hi;            // byte range [lo, hi) of h_bytes that holds frames
+    size_t d_base;                  // device offset of h_bytes + h_lo
+    size_t pal_off;                 // palette slot (int32 index into d_pal) or SIZE_MAX
+};
+
+struct FrameRec {
+    int stream;
+    uint32_t len;
+    size_t d_src;                   // offset into d_bytes
+    size_t out_off;                 // int32 offset into d_out
+    int64_t prev;                   // global index of the previous frame of the stream, -1 if none
+    int level;
+    int kind;
+    uint8_t key;
+    uint32_t n_tiles, state_base;
+};
+
+struct Launch {
+    int kclass;                     // JSP_K_*
+    int kind;                       // FrameKind
+    size_t first;                   // offset into the plan's tile table / job table
+    uint32_t count;                 // CTAs / jobs
+    uint32_t max_vec4;              // copy jobs: largest job
+    uint32_t ticket;                // ticket counter slot
+};
+
+struct CopyRange { const uint8_t *h; size_t d_off; size_t bytes; };
+
+// One schedulable unit: a set of streams with everything needed to upload, decode and download them.
+struct Plan {
+    int64_t frame_lo = 0, frame_hi = 0;        // global frame range covered (streams are contiguous)
+    std::vector<Launch> launches;
+    std::vector<CopyRange> uploads;
+    size_t tile_tab_off = 0, n_tile_entries = 0;   // slice of d_tile_tab
+    size_t job_off = 0, n_jobs = 0;                // slice of d_jobs
+    size_t state_off = 0, n_states = 0;            // slice of the tile-state arrays
+    size_t ticket_off = 0, n_tickets = 0;
+};
+
+}  // namespace jsp
+
+struct jsp_batch {
+    int device = 0;
+    int sm_count = 148;
+    int insign_lines = 0;
+    int flags = 0;
+    cudaStream_t st_compute = nullptr, st_in = nullptr, st_out = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+
+    std::vector<jsp::StreamRec> streams;
+    std::vector<jsp::FrameRec> frames;
+    jsp::Plan whole;
+    std::vector<jsp::Plan> chunks;
+
+    // device arenas (grown on demand, never shrunk)
+    uint8_t *d_bytes = nullptr;   size_t bytes_cap = 0, bytes_used = 0;
+    int32_t *d_out = nullptr;     size_t out_cap = 0, out_used = 0;      // in int32
+    int32_t *d_pal = nullptr;     size_t pal_cap = 0;
+    uint32_t *d_status = nullptr; size_t status_cap = 0;
+    jsp::Msv1Frame *d_mframes = nullptr; size_t mframes_cap = 0;
+    uint2 *d_tile_tab = nullptr;  size_t tile_tab_cap = 0;
+    jsp::CopyJob *d_jobs = nullptr; size_t jobs_cap = 0;
+    unsigned long long *d_tile_map = nullptr, *d_tile_cnt = nullptr; size_t states_cap = 0;
+    unsigned int *d_tickets = nullptr; size_t tickets_cap = 0;
+    // significance post-pass tables
+    const int32_t **d_sig_cur = nullptr; const int32_t **d_sig_prev = nullptr; uint32_t **d_sig_status = nullptr;
+    uint32_t *d_sig_first = nullptr, *d_sig_npx = nullptr; size_t sig_cap = 0, n_sig = 0;
+    uint32_t *d_stream_first = nullptr, *d_stream_count = nullptr; size_t streams_cap = 0, streams_cap2 = 0;
+    uint8_t *d_frame_codec = nullptr; size_t frame_codec_cap = 0;
+    void *d_flush = nullptr; size_t flush_bytes = 0;
+
+    uint32_t *h_status = nullptr; size_t h_status_cap = 0;   // pinned
+
+    const int32_t *ext_prev = nullptr;   // previous picture held outside the batch (per-stream drop-in)
+    int ext_has_prev = 0;                // codec's prevFrame was non-null before the batch's first frame
+    int rerun_count = 0;
+
+    uint64_t stat_pixels = 0, stat_alg_bytes = 0, stat_in_bytes = 0, stat_out_bytes = 0;
+};

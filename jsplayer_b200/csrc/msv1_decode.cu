@@ -1,0 +1,562 @@
+// msv1_decode.cu -- Microsoft Video 1 (CRAM/MSVC) batch decode for sm_100a.
+//
+// Replaces the serial block walk of reference src/MSVideo1.hx:106-209 (RGB555) and :293-393
+// (8-bit palettised) with ONE kernel that reads every compressed byte once and writes every
+// output pixel once (HBM-bound; no tensor-core work exists on this path).
+//
+// The bitstream of every frame of the launch is cut into 4 KiB tiles; one CTA owns one tile:
+//   scan phase  (per tile, in shared memory)
+//     1. every lane walks its 16-word segment BACKWARDS and gets, for each possible entry offset
+//        0..8 (an opcode is at most 9 words), the offset at which the opcode chain leaves the segment
+//        -> a 9-nibble map in one 64-bit register.  Opcode boundaries depend on bytes only.
+//     2. maps are chained lane -> warp -> tile with warp shuffles; opcode chains self-synchronise, so
+//        most maps are constant and the chain resolves in one or two shuffle rounds.
+//     3. tiles of one frame are chained with a single-pass decoupled look-back (one 64-bit state word
+//        per tile); tiles are ticketed tile-major over all frames so predecessors are long finished.
+//     4. lanes walk forward from their now-known entry, count blocks (skip runs weigh n), and a
+//        warp-shuffle prefix sum + a second look-back give every opcode its absolute 4x4-block index;
+//        a per-opcode (position, block) table lands in shared memory.
+//   fill phase: one thread per coded block, consecutive threads = consecutive blocks, four 16-byte
+//     streaming stores per block (a warp writes 4 x 512 contiguous bytes); skip runs are copied from
+//     the previous picture warp-per-run with 16-byte loads/stores.
+//
+// JavaScript semantics of the reference on truncated input are reproduced exactly (see
+// oracle/msvideo1_oracle.c): bytes past the end read as `undefined`.
+#include "common.cuh"
+
+namespace jsp {
+namespace {
+
+typedef unsigned long long u64;
+
+constexpr u64 FLAG_AGG  = 1ull << 62;
+constexpr u64 FLAG_INCL = 2ull << 62;
+constexpr u64 FLAG_MASK = 3ull << 62;
+constexpr u64 MAP_TERM  = 0xFull << 60;           // nibble 15 maps to 15: "chain terminated" is absorbing
+constexpr u64 MAP_IDENT = 0x876543210ull | MAP_TERM;
+constexpr u64 ONES9     = 0x111111111ull;
+constexpr uint32_t TERM = 15;
+
+__device__ __forceinline__ uint32_t nib(u64 m, uint32_t e) { return (uint32_t)(m >> (4 * e)) & 15u; }
+
+template <int NENT>
+__device__ __forceinline__ bool map_const(u64 m, uint32_t &c)
+{
+    constexpr u64 MASK = (1ull << (4 * NENT)) - 1;
+    c = (uint32_t)m & 15u;
+    return (m & MASK) == ((ONES9 & MASK) * c);
+}
+
+// (A then B)(e) = B[A[e]]
+template <int NENT>
+__device__ __forceinline__ u64 compose(u64 A, u64 B)
+{
+    uint32_t c;
+    if (map_const<NENT>(B, c)) return B;
+    u64 r = MAP_TERM;
+#pragma unroll
+    for (int e = 0; e < NENT; e++) r |= (u64)nib(B, nib(A, e)) << (4 * e);
+    return r;
+}
+
+__device__ __forceinline__ u64 ld_state(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(u64 *p, u64 v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 shfl64(u64 v, int src)
+{
+    uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+    uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return ((u64)hi << 32) | lo;
+}
+
+// MSVideo1.hx:211-214
+__device__ __forceinline__ uint32_t rgb15(uint32_t c)
+{
+    return ((c & 0x1Fu) << 3) | ((c & 0x3E0u) << 6) | ((c & 0x7C00u) << 9);
+}
+
+__device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b, uint32_t cap)
+{
+    uint32_t s = a + b;
+    return s < cap ? s : cap;
+}
+
+struct Smem {
+    alignas(16) uint8_t bytes[MSV1_STAGE_BYTES];
+    uint32_t blk[MSV1_TILE_WORDS];     // absolute block index of opcode k
+    uint16_t pos[MSV1_TILE_WORDS];     // word position in the tile | 0x8000 for copy runs
+    uint16_t runs[MSV1_TILE_WORDS];    // opcode indices of the short skip runs
+    int32_t  pal[256];
+    u64      wmap[4];
+    uint32_t wentry[4];
+    uint32_t wops[4];
+    uint32_t wblk[4];
+    uint32_t ticket;
+    uint32_t first_block;
+    uint32_t nruns;
+    uint32_t big_blk0;                 // first block of a "rest of frame" copy, or 0xFFFFFFFF
+    uint32_t flags;
+    uint32_t terminated;
+};
+
+// 16 reconstructed pixels of one coded block from 8 quadrant colours (2-colour and 1-colour blocks are
+// replicated into the same form).  bit i of `flags` = 1 selects the odd colour of the pair.
+__device__ __forceinline__ void store_block(int32_t *out, uint32_t X, uint32_t by, uint32_t bx,
+                                            const uint32_t (&col)[8], uint32_t flags, bool vec_ok)
+{
+    int32_t *p = out + (size_t)by * 4u * X + bx * 4u;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        uint32_t px[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            const int q = ((r & 2) << 1) + (x & 2);
+            px[x] = ((flags >> (4 * r + x)) & 1u) ? col[q + 1] : col[q];
+        }
+        if (vec_ok) {
+            __stcs(reinterpret_cast<uint4 *>(p), make_uint4(px[0], px[1], px[2], px[3]));
+        } else {
+            p[0] = (int32_t)px[0]; p[1] = (int32_t)px[1]; p[2] = (int32_t)px[2]; p[3] = (int32_t)px[3];
+        }
+        p += X;
+    }
+}
+
+__device__ __forceinline__ void copy_block(int32_t *out, const int32_t *prev, uint32_t X, uint32_t by,
+                                           uint32_t bx, bool vec_ok)
+{
+    const size_t off = (size_t)by * 4u * X + bx * 4u;
+    int32_t *d = out + off;
+    if (vec_ok) {
+        uint4 v[4];
+        if (prev) {
+            const int32_t *s = prev + off;
+#pragma unroll
+            for (int r = 0; r < 4; r++) v[r] = __ldcs(reinterpret_cast<const uint4 *>(s + (size_t)r * X));
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; r++) v[r] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) __stcs(reinterpret_cast<uint4 *>(d + (size_t)r * X), v[r]);
+    } else {
+        for (int r = 0; r < 4; r++)
+            for (int x = 0; x < 4; x++) d[(size_t)r * X + x] = prev ? prev[off + (size_t)r * X + x] : 0;
+    }
+}
+
+template <bool IS8>
+__global__ void __launch_bounds__(MSV1_THREADS)
+msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict__ tile_tab,
+                   u64 *__restrict__ tile_map, u64 *__restrict__ tile_cnt, unsigned int *__restrict__ ticket)
+{
+    constexpr int NENT = IS8 ? 5 : 9;      // possible entry offsets into a segment (longest opcode: 5 / 9 words)
+    __shared__ Smem sm;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t FULL = 0xffffffffu;
+
+    // ---- work assignment: tickets hand tiles out in table order, so every tile a CTA may wait for has
+    //      already been started by a CTA that never waits for a later one (forward progress) ----
+    if (tid == 0) {
+        sm.ticket = atomicAdd(ticket, 1u);
+        sm.nruns = 0; sm.big_blk0 = 0xFFFFFFFFu; sm.flags = 0; sm.terminated = 0;
+    }
+    __syncthreads();
+    const uint2 tt = tile_tab[sm.ticket];
+    const Msv1Frame F = frames[tt.x];
+    const uint32_t tile = tt.y;
+    const uint32_t len = F.len, X = F.X, nbx = F.nbx, nblocks = F.nblocks;
+    const uint32_t tile_byte0 = tile * MSV1_TILE_BYTES;
+    const uint32_t n_words = (len + 1u) >> 1;                      // an odd trailing byte is a half word (see below)
+    const uint32_t tile_words = n_words > tile * MSV1_TILE_WORDS
+                                    ? min((uint32_t)MSV1_TILE_WORDS, n_words - tile * MSV1_TILE_WORDS) : 0u;
+    const bool vec_ok = ((X & 3u) == 0) && ((reinterpret_cast<uintptr_t>(F.out) & 15u) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(F.prev) & 15u) == 0);
+
+    // ---- stage the tile (+32 B look-ahead) into shared memory, zero-filled past the end of the frame ----
+    {
+        const uint8_t *g = F.src + tile_byte0;
+        const int avail = (int)min((uint32_t)MSV1_STAGE_BYTES, len > tile_byte0 ? len - tile_byte0 : 0u);
+        const bool aligned = (reinterpret_cast<uintptr_t>(g) & 15u) == 0;
+        uint4 *s4 = reinterpret_cast<uint4 *>(sm.bytes);
+        for (int c = tid; c < MSV1_STAGE_BYTES / 16; c += MSV1_THREADS) {
+            const int b0 = c * 16;
+            uint4 v;
+            if (aligned && b0 + 16 <= avail) {
+                v = __ldcs(reinterpret_cast<const uint4 *>(g + b0));
+            } else if (b0 >= avail) {
+                v = make_uint4(0, 0, 0, 0);
+            } else {
+                // unaligned source or the chunk straddles the end: assemble from aligned 32-bit words
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int o = b0 + 4 * k;
+                    uint32_t val = 0;
+                    if (o < avail) {
+                        const uintptr_t addr = reinterpret_cast<uintptr_t>(g + o);
+                        const uint32_t *ga = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+                        const uint32_t sh = (uint32_t)(addr & 3u) * 8u;
+                        const uint32_t lo = __ldg(ga);
+                        const uint32_t hi = (sh != 0 && o + 4 - (int)(sh >> 3) < avail) ? __ldg(ga + 1) : 0u;
+                        val = __funnelshift_r(lo, hi, sh);
+                        const int rem = avail - o;
+                        if (rem < 4) val &= (1u << (8 * rem)) - 1u;
+                    }
+                    w[k] = val;
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            s4[c] = v;
+        }
+        if (IS8) for (int i = tid; i < 256; i += MSV1_THREADS) sm.pal[i] = F.pal ? F.pal[i] : 0;
+    }
+    __syncthreads();
+    // An odd frame length leaves a half word {a, undefined}.  The reference then takes the 1-colour
+    // branch with (undefined<<8)+a (MSVideo1.hx:171-173) / pal[a] (:353); patching the missing high byte
+    // to 0x80 selects exactly that class with exactly that colour (bit 15 is ignored by fromRGB15).
+    if ((len & 1u) && len >= tile_byte0 && len - tile_byte0 < (uint32_t)MSV1_STAGE_BYTES) {
+        if (tid == 0) sm.bytes[len - tile_byte0] = 0x80;
+        __syncthreads();
+    }
+
+    // ---- scan 1: backward walk of the lane's 16-word segment -> entry->exit map ----
+    u64 M;
+    {
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(sm.bytes) + tid * 8;
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(sw);
+        const uint4 v1 = *reinterpret_cast<const uint4 *>(sw + 4);
+        const uint32_t r[9] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, sw[8]};
+        u64 W = 0;   // nibble k = exit code of position p+1+k (sliding window while p descends)
+#pragma unroll
+        for (int p = MSV1_SEG_WORDS - 1; p >= 0; --p) {
+            uint32_t a, b, h;
+            if (p & 1) { a = (r[p >> 1] >> 16) & 0xFFu; b = r[p >> 1] >> 24; h = (r[(p >> 1) + 1] >> 8) & 0xFFu; }
+            else       { a = r[p >> 1] & 0xFFu; b = (r[p >> 1] >> 8) & 0xFFu; h = r[p >> 1] >> 24; }
+            uint32_t code;
+            bool term = (b == 0x84u) && (a == 0u);                 // skip count 0: rest of the frame is copied (MSVideo1.hx:132,124)
+            if (IS8) {
+                term = term || (a + b == 0u);                      // terminator (MSVideo1.hx:313)
+                if (b < 0x80u)       code = (p + 2 >= 16) ? (uint32_t)(p + 2 - 16) : (uint32_t)(W >> 4) & 15u;
+                else if (b >= 0x90u) code = (p + 5 >= 16) ? (uint32_t)(p + 5 - 16) : (uint32_t)(W >> 16) & 15u;
+                else                 code = (p + 1 >= 16) ? 0u : (uint32_t)W & 15u;
+            } else {
+                (void)a;
+                if (b < 0x80u) {
+                    if (h & 0x80u) code = (p + 9 >= 16) ? (uint32_t)(p + 9 - 16) : (uint32_t)(W >> 32) & 15u;
+                    else           code = (p + 3 >= 16) ? (uint32_t)(p + 3 - 16) : (uint32_t)(W >> 8) & 15u;
+                } else             code = (p + 1 >= 16) ? 0u : (uint32_t)W & 15u;
+            }
+            if (term) code = TERM;
+            W = (W << 4) | code;
+        }
+        M = (W & 0xFFFFFFFFFull) | MAP_TERM;
+    }
+
+    // ---- scan 2: chain the maps.  A lane whose map is constant fixes its successor's entry outright. ----
+    uint32_t myc; const bool myconst = map_const<NENT>(M, myc);
+    bool known; uint32_t entry;
+    {
+        const uint32_t pc = __shfl_up_sync(FULL, myc, 1);
+        const bool pk = __shfl_up_sync(FULL, (int)myconst, 1) != 0;
+        known = lane > 0 && pk; entry = pc;
+    }
+    uint32_t ex; bool exk;
+    for (;;) {
+        exk = known || myconst;
+        ex = known ? nib(M, entry) : myc;
+        const uint32_t pe = __shfl_up_sync(FULL, ex, 1);
+        const bool pk = __shfl_up_sync(FULL, (int)exk, 1) != 0;
+        const bool newly = !known && lane > 0 && pk;
+        if (newly) { known = true; entry = pe; }
+        if (!__any_sync(FULL, newly)) break;
+    }
+    {
+        u64 agg;
+        const bool exit_known = __shfl_sync(FULL, (int)exk, 31) != 0;
+        if (exit_known) {
+            agg = ONES9 * __shfl_sync(FULL, ex, 31) | MAP_TERM;
+        } else {   // no constant map in the whole warp: follow all entries through the 32 segments
+            uint32_t cur = lane < NENT ? lane : 0;
+            for (int i = 0; i < 32; i++) cur = nib(shfl64(M, i), cur);
+            agg = MAP_TERM;
+#pragma unroll
+            for (int e = 0; e < NENT; e++) agg |= (u64)__shfl_sync(FULL, cur, e) << (4 * e);
+        }
+        if (lane == 0) sm.wmap[warp] = agg;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        u64 A = sm.wmap[0];
+        for (int w = 1; w < 4; w++) A = compose<NENT>(A, sm.wmap[w]);
+        u64 *slot = tile_map + F.state_base + tile;
+        uint32_t c; const bool aconst = map_const<NENT>(A, c);
+        if (tile + 1 < F.n_tiles) st_state(slot, aconst ? (FLAG_INCL | c) : (FLAG_AGG | (A & 0xFFFFFFFFFull)));
+        // look back for this tile's entry offset
+        uint32_t e0 = 0;
+        if (tile > 0) {
+            u64 acc = MAP_IDENT;
+            int j = (int)tile - 1;
+            for (;;) {
+                u64 st;
+                do { st = ld_state(tile_map + F.state_base + j); } while ((st & FLAG_MASK) == 0);
+                if ((st & FLAG_MASK) == FLAG_INCL) { e0 = nib(acc, (uint32_t)st & 15u); break; }
+                acc = compose<NENT>((st & 0xFFFFFFFFFull) | MAP_TERM, acc);
+                uint32_t cc;
+                if (map_const<NENT>(acc, cc)) { e0 = cc; break; }
+                if (j == 0) { e0 = nib(acc, 0); break; }
+                --j;
+            }
+        }
+        if (!aconst && tile + 1 < F.n_tiles) st_state(slot, FLAG_INCL | nib(A, e0));
+        uint32_t e = e0;
+        for (int w = 0; w < 4; w++) { sm.wentry[w] = e; e = nib(sm.wmap[w], e); }
+        if (e0 == TERM) sm.terminated = 1;
+    }
+    __syncthreads();
+    if (lane == 0) { known = true; entry = sm.wentry[warp]; }
+    while (!__all_sync(FULL, known)) {
+        const uint32_t e2 = nib(M, entry);
+        const uint32_t pe = __shfl_up_sync(FULL, e2, 1);
+        const bool pk = __shfl_up_sync(FULL, (int)known, 1) != 0;
+        if (!known && lane > 0 && pk) { known = true; entry = pe; }
+    }
+
+    // ---- scan 3: forward walk from the true entry: opcode starts, block counts ----
+    const int seg_lim = (int)min((uint32_t)MSV1_SEG_WORDS,
+                                 tile_words > tid * MSV1_SEG_WORDS ? tile_words - tid * MSV1_SEG_WORDS : 0u);
+    uint32_t starts = 0, nops = 0, blocks = 0;
+    bool lterm = false;
+    if (entry != TERM) {
+        int p = (int)entry;
+        while (p < seg_lim) {
+            const uint8_t *o = sm.bytes + (tid * MSV1_SEG_WORDS + p) * 2;
+            const uint32_t a = o[0], b = o[1];
+            starts |= 1u << p; nops++;
+            if ((IS8 && a + b == 0u) || (b == 0x84u && a == 0u)) { blocks = nblocks; lterm = true; break; }
+            if ((b & 0xFCu) == 0x84u) { blocks = sat_add(blocks, ((b - 0x84u) << 8) | a, nblocks); p += 1; }
+            else {
+                blocks = sat_add(blocks, 1u, nblocks);
+                if (IS8) p += (b < 0x80u) ? 2 : (b >= 0x90u ? 5 : 1);
+                else     p += (b < 0x80u) ? ((o[3] & 0x80u) ? 9 : 3) : 1;
+            }
+        }
+    }
+    // ---- scan 4: block / opcode prefix sums (warp shuffles + look-back) ----
+    uint32_t op_incl = nops, blk_incl = blocks;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o2 = __shfl_up_sync(FULL, op_incl, d);
+        const uint32_t b2 = __shfl_up_sync(FULL, blk_incl, d);
+        if (lane >= (uint32_t)d) { op_incl += o2; blk_incl = sat_add(blk_incl, b2, nblocks); }
+    }
+    if (lane == 31) { sm.wops[warp] = op_incl; sm.wblk[warp] = blk_incl; }
+    if (__any_sync(FULL, lterm) && lane == 0) sm.terminated = 1;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 4; w++) tot = sat_add(tot, sm.wblk[w], nblocks);
+        u64 *slot = tile_cnt + F.state_base + tile;
+        const bool publish = tile + 1 < F.n_tiles;
+        uint32_t first = 0;
+        if (tile > 0) {
+            if (publish) st_state(slot, FLAG_AGG | tot);
+            int j = (int)tile - 1;
+            for (;;) {
+                u64 st;
+                do { st = ld_state(tile_cnt + F.state_base + j); } while ((st & FLAG_MASK) == 0);
+                first = sat_add(first, (uint32_t)st, nblocks);
+                if ((st & FLAG_MASK) == FLAG_INCL || j == 0) break;
+                --j;
+            }
+        }
+        if (publish) st_state(slot, FLAG_INCL | sat_add(first, tot, nblocks));
+        sm.first_block = first;
+    }
+    __syncthreads();
+    const uint32_t first_block = sm.first_block;
+    uint32_t tot_ops = 0, tot_blk = 0, op_base = op_incl - nops, blk_base;
+    {
+        uint32_t wb = 0;
+        for (uint32_t w = 0; w < 4; w++) {
+            if (w == warp) { op_base += tot_ops; wb = tot_blk; }
+            tot_ops += sm.wops[w]; tot_blk = sat_add(tot_blk, sm.wblk[w], nblocks);
+        }
+        // exclusive block prefix of this lane inside the warp (saturating sums are monotone, so recompute)
+        const uint32_t prev_incl = __shfl_up_sync(FULL, blk_incl, 1);
+        blk_base = sat_add(wb, lane ? prev_incl : 0u, nblocks);
+    }
+    const uint32_t incl_block = sat_add(first_block, tot_blk, nblocks);
+    const bool last_tile = tile + 1 == F.n_tiles;
+
+    uint32_t myflags = 0;
+    if (first_block < nblocks) {
+        // ---- per-opcode table ----
+        {
+            uint32_t m = starts, opi = op_base, blk = sat_add(first_block, blk_base, nblocks);
+            while (m) {
+                const int p = __ffs(m) - 1; m &= m - 1;
+                const uint8_t *o = sm.bytes + (tid * MSV1_SEG_WORDS + p) * 2;
+                const uint32_t a = o[0], b = o[1];
+                const bool big = (IS8 && a + b == 0u) || (b == 0x84u && a == 0u);
+                const bool run = big || (b & 0xFCu) == 0x84u;
+                sm.pos[opi] = (uint16_t)((tid * MSV1_SEG_WORDS + p) | (run ? 0x8000u : 0u));
+                sm.blk[opi] = blk;
+                if (big) { sm.big_blk0 = blk; blk = nblocks; }
+                else if (run) {
+                    sm.runs[atomicAdd(&sm.nruns, 1u)] = (uint16_t)opi;
+                    blk = sat_add(blk, ((b - 0x84u) << 8) | a, nblocks);
+                } else blk = sat_add(blk, 1u, nblocks);
+                opi++;
+            }
+        }
+        __syncthreads();
+
+        // ---- fill: one thread per coded block ----
+        for (uint32_t op = tid; op < tot_ops; op += MSV1_THREADS) {
+            const uint32_t pw = sm.pos[op];
+            if (pw & 0x8000u) continue;
+            const uint32_t blk = sm.blk[op];
+            if (blk >= nblocks) continue;                          // opcodes past the last block are never read
+            const uint32_t by = blk / nbx, bx = blk - by * nbx;
+            const uint8_t *o = sm.bytes + pw * 2;
+            const uint32_t abs0 = tile_byte0 + pw * 2;             // byte offset of the opcode in the frame
+            uint32_t col[8], flags;
+            if (abs0 + (IS8 ? 10u : 18u) <= len) {
+                const uint32_t a = o[0], b = o[1];
+                if (IS8) {
+                    if (b < 0x80u) {                               // 2 colours, flags as stored (MSVideo1.hx:319-334)
+                        flags = (b << 8) | a;
+                        const uint32_t c1 = (uint32_t)sm.pal[o[2]], c0 = (uint32_t)sm.pal[o[3]];
+#pragma unroll
+                        for (int k = 0; k < 8; k += 2) { col[k] = c0; col[k + 1] = c1; }
+                    } else if (b >= 0x90u) {                       // 8 colours (:336-352)
+                        flags = ((b << 8) | a) ^ 0xFFFFu;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) col[k] = (uint32_t)sm.pal[o[2 + k]];
+                    } else {                                       // 1 colour (:353-364)
+                        flags = 0;
+                        const uint32_t c = (uint32_t)sm.pal[a];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) col[k] = c;
+                    }
+                } else {
+                    const uint16_t *ow = reinterpret_cast<const uint16_t *>(o);
+                    if (b < 0x80u) {
+                        flags = (((b << 8) | a) ^ 0xFFFFu);
+                        const uint32_t w0 = ow[1];
+                        if (w0 & 0x8000u) {                        // 8 colours (MSVideo1.hx:142-160)
+#pragma unroll
+                            for (int k = 0; k < 8; k++) col[k] = rgb15(ow[1 + k]);
+                        } else {                                   // 2 colours (:160-168)
+                            const uint32_t c0 = rgb15(w0), c1 = rgb15(ow[2]);
+#pragma unroll
+                            for (int k = 0; k < 8; k += 2) { col[k] = c0; col[k + 1] = c1; }
+                        }
+                    } else {                                       // 1 colour (:171-181)
+                        flags = 0;
+                        const uint32_t c = rgb15((b << 8) | a);
+#pragma unroll
+                        for (int k = 0; k < 8; k++) col[k] = c;
+                    }
+                }
+            } else {
+                // the opcode runs past the end of the frame: JavaScript `undefined` reads, byte by byte
+                auto rd = [&](uint32_t i) -> int { return abs0 + i < len ? (int)o[i] : -1; };
+                auto w16 = [&](uint32_t i) -> uint32_t { return abs0 + i + 1 < len ? (uint32_t)o[i] | ((uint32_t)o[i + 1] << 8) : 0u; };
+                const int a = rd(0), b = (len & 1u) && abs0 + 1 == len ? -1 : rd(1);
+                flags = 0;
+                if (IS8) {
+                    auto palu = [&](int ix) -> uint32_t { return ix < 0 ? 0u : (uint32_t)sm.pal[ix]; };
+                    if (b >= 0 && b < 0x80) {
+                        flags = ((uint32_t)b << 8) | (uint32_t)a;
+                        const uint32_t c1 = palu(rd(2)), c0 = palu(rd(3));
+                        for (int k = 0; k < 8; k += 2) { col[k] = c0; col[k + 1] = c1; }
+                    } else if (b >= 0x90) {
+                        flags = (((uint32_t)b << 8) | (uint32_t)a) ^ 0xFFFFu;
+                        for (int k = 0; k < 8; k++) col[k] = palu(rd(2 + k));
+                    } else {
+                        const uint32_t c = palu(a);
+                        for (int k = 0; k < 8; k++) col[k] = c;
+                    }
+                } else {
+                    if (b >= 0 && b < 0x80) {
+                        flags = ((((uint32_t)b << 8) | (uint32_t)a) ^ 0xFFFFu);
+                        const uint32_t w0 = w16(2);
+                        if (w0 & 0x8000u) {
+                            for (int k = 0; k < 8; k++) col[k] = rgb15(w16(2 + 2 * k));
+                        } else {
+                            const uint32_t c0 = rgb15(w0), c1 = rgb15(w16(4));
+                            for (int k = 0; k < 8; k += 2) { col[k] = c0; col[k + 1] = c1; }
+                        }
+                    } else {
+                        const uint32_t c = rgb15(b < 0 ? (a < 0 ? 0u : (uint32_t)a) : (((uint32_t)b << 8) | (uint32_t)a));
+                        for (int k = 0; k < 8; k++) col[k] = c;
+                    }
+                }
+            }
+            store_block(F.out, X, by, bx, col, flags, vec_ok);
+            myflags |= ST_CHANGED | (by >= F.insign_blocks ? ST_SIGNIF_ROWS : 0u);
+        }
+
+        // ---- skip runs: warp per run, 16-byte copies from the previous picture ----
+        const uint32_t nruns = sm.nruns;
+        for (uint32_t r = warp; r < nruns; r += 4) {
+            const uint32_t op = sm.runs[r];
+            const uint32_t blk0 = sm.blk[op];
+            const uint8_t *o = sm.bytes + (sm.pos[op] & 0x7FFFu) * 2;
+            uint32_t n = (((uint32_t)o[1] - 0x84u) << 8) | o[0];
+            n = min(n, nblocks - min(blk0, nblocks));
+            for (uint32_t j = lane; j < n; j += 32) {
+                const uint32_t blk = blk0 + j, by = blk / nbx, bx = blk - by * nbx;
+                copy_block(F.out, F.prev, X, by, bx, vec_ok);
+            }
+            if (n && !F.prev && (F.flags & MSV1_F_HAS_PRED)) myflags |= ST_NEEDS_PREV;
+        }
+        // ---- "rest of the frame is copied" (skip count 0 / 8-bit terminator): whole CTA ----
+        const uint32_t big0 = sm.big_blk0;
+        if (big0 < nblocks) {
+            for (uint32_t blk = big0 + tid; blk < nblocks; blk += MSV1_THREADS) {
+                const uint32_t by = blk / nbx, bx = blk - by * nbx;
+                copy_block(F.out, F.prev, X, by, bx, vec_ok);
+            }
+            if (!F.prev && (F.flags & MSV1_F_HAS_PRED)) myflags |= ST_NEEDS_PREV;
+        }
+    }
+    // ---- the bitstream ended before the last block: the reference keeps "reading" undefined bytes, i.e.
+    //      1-colour blocks of colour 0 that count as changes (MSVideo1.hx:171-181 with NaN -> 0) ----
+    if (last_tile && !sm.terminated && incl_block < nblocks) {
+        const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t blk = incl_block + tid; blk < nblocks; blk += MSV1_THREADS) {
+            const uint32_t by = blk / nbx, bx = blk - by * nbx;
+            store_block(F.out, X, by, bx, zero, 0u, vec_ok);
+            myflags |= ST_CHANGED | (by >= F.insign_blocks ? ST_SIGNIF_ROWS : 0u);
+        }
+    }
+    myflags = __reduce_or_sync(FULL, myflags);
+    if (lane == 0 && myflags) atomicOr(&sm.flags, myflags);
+    __syncthreads();
+    if (tid == 0 && sm.flags) atomicOr(F.status, sm.flags);
+}
+
+}  // namespace
+
+void launch_msv1_decode(bool is8, const Msv1Frame *d_frames, const uint2 *d_tile_tab, uint32_t n_ctas,
+                        unsigned long long *d_tile_map, unsigned long long *d_tile_cnt,
+                        unsigned int *d_ticket, cudaStream_t st)
+{
+    if (n_ctas == 0) return;
+    if (is8)
+        msv1_decode_kernel<true><<<n_ctas, MSV1_THREADS, 0, st>>>(d_frames, d_tile_tab, d_tile_map, d_tile_cnt, d_ticket);
+    else
+        msv1_decode_kernel<false><<<n_ctas, MSV1_THREADS, 0, st>>>(d_frames, d_tile_tab, d_tile_map, d_tile_cnt, d_ticket);
+}
+
+}  // namespace jsp

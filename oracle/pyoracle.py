@@ -1,0 +1,131 @@
+"""ctypes binding of oracle/liboracle.so -- the CPU restatement of the reference decoders.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  Nothing in jsplayer_b200/ imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+_lib = None
+
+ZERO_STATE, IN_PROGRESS, ERROR_OCCURED = 0, 1, 2
+CODEC_SCREENPRESSOR, CODEC_MSVC16, CODEC_MSVC8 = 0, 1, 2
+
+
+class StreamDesc(C.Structure):
+    _fields_ = [("codec", C.c_int), ("width", C.c_int), ("height", C.c_int), ("bpp", C.c_int),
+                ("palette", C.c_void_p), ("palette_bytes", C.c_int), ("n_frames", C.c_int),
+                ("bytes", C.c_void_p), ("frame_off", C.c_void_p), ("frame_len", C.c_void_p),
+                ("frame_key", C.c_void_p), ("out", C.c_void_p)]
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
+        subprocess.run(["make", "-C", HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        lib = C.CDLL(LIB_PATH)
+        lib.ora_create.restype = C.c_void_p
+        lib.ora_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        lib.ora_destroy.argtypes = [C.c_void_p]
+        lib.ora_preinit.argtypes = [C.c_void_p, C.c_int]
+        lib.ora_is_key_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.ora_needs_index.argtypes = [C.c_void_p]
+        lib.ora_previous_frame.restype = C.c_void_p
+        lib.ora_previous_frame.argtypes = [C.c_void_p]
+        lib.ora_decompress_i.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.ora_decompress_p.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        lib.ora_stop_and_clean.argtypes = [C.c_void_p]
+        lib.ora_decode_stream.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]
+        lib.ora_decode_streams_mt.restype = C.c_double
+        lib.ora_decode_streams_mt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        _lib = lib
+    return _lib
+
+
+def _u8(b):
+    a = np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else b
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+class OracleCodec:
+    """IVideoCodec-shaped wrapper (same member names as the reference interface)."""
+
+    def __init__(self, codec, width, height, bpp, palette=None):
+        self.lib = load()
+        self.X, self.Y = width, height
+        pal = _u8(palette) if palette else None
+        self._pal = pal
+        self.h = self.lib.ora_create(codec, width, height, bpp, pal.ctypes.data if pal is not None else None,
+                                     pal.size if pal is not None else 0)
+        self._bufs = {}
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ora_destroy(self.h)
+            self.h = None
+
+    def Preinit(self, n):
+        self.lib.ora_preinit(self.h, n)
+
+    def IsKeyFrame(self, data):
+        a = _u8(data)
+        return bool(self.lib.ora_is_key_frame(self.h, a.ctypes.data if a.size else None, a.size))
+
+    def NeedsIndex(self):
+        return bool(self.lib.ora_needs_index(self.h))
+
+    def PreviousFrame(self):
+        return self._bufs.get(self.lib.ora_previous_frame(self.h))
+
+    def DecompressI(self, src, dst):
+        a = _u8(src)
+        self._bufs[dst.ctypes.data] = dst
+        return self.lib.ora_decompress_i(self.h, a.ctypes.data if a.size else None, a.size, dst.ctypes.data)
+
+    def DecompressP(self, src, dst):
+        a = _u8(src)
+        self._bufs[dst.ctypes.data] = dst
+        pnt, sig = C.c_void_p(0), C.c_int(0)
+        self.lib.ora_decompress_p(self.h, a.ctypes.data if a.size else None, a.size, dst.ctypes.data, C.byref(pnt), C.byref(sig))
+        return self._bufs.get(pnt.value), bool(sig.value)
+
+
+def decode_stream(codec, width, height, bpp, frames, keys=None, palette=None, insignificant_lines=0):
+    """Decodes `frames` (list of bytes) in order; returns (out[n,h,w] int32, changed, significant, status)."""
+    lib = load()
+    n = len(frames)
+    ln = np.array([len(f) for f in frames], dtype=np.uint32)
+    off = np.zeros(n, dtype=np.uint64)
+    if n:
+        off[1:] = np.cumsum(ln.astype(np.uint64))[:-1]
+    blob = np.frombuffer(b"".join(bytes(f) for f in frames) + b"\0", dtype=np.uint8).copy()
+    k = np.zeros(n, dtype=np.uint8)
+    if keys is None:
+        if n:
+            k[0] = 1
+    else:
+        k[:] = np.asarray(keys, dtype=np.uint8)
+    pal = _u8(palette) if palette else None
+    out = np.zeros((n, height, width), dtype=np.int32)
+    changed = np.zeros(n, dtype=np.uint8)
+    signif = np.zeros(n, dtype=np.uint8)
+    status = np.zeros(n, dtype=np.int32)
+    lib.ora_decode_stream(codec, width, height, bpp, pal.ctypes.data if pal is not None else None,
+                          pal.size if pal is not None else 0, insignificant_lines, n, blob.ctypes.data,
+                          off.ctypes.data, ln.ctypes.data, k.ctypes.data, out.ctypes.data, changed.ctypes.data,
+                          signif.ctypes.data, status.ctypes.data)
+    return out, changed, signif, status
