@@ -182,6 +182,7 @@ static void fill_mframes(jsp_batch *b, HostTables &T)
         M.state_base = R.state_base;
         M.insign_blocks = (uint32_t)std::max(0, (b->insign_lines + 3) >> 2);
         M.flags = R.prev >= 0 ? MSV1_F_HAS_PRED : 0u;
+        M.inv_nbx = M.nbx > 1 ? (uint32_t)(0x100000000ull / M.nbx) : 0xFFFFFFFFu;
     }
 }
 

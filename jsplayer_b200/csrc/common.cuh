@@ -36,6 +36,7 @@ struct Msv1Frame {
     uint32_t state_base;     // first slot of this frame in the tile-state arrays
     uint32_t insign_blocks;  // (insignificant_lines+3)>>2
     uint32_t flags;          // MSV1_F_*
+    uint32_t inv_nbx;        // floor(2^32 / nbx): block row = umulhi(block, inv_nbx) (+1 fix-up)
 };
 
 // whole-picture copy / fill jobs (unchanged frames, flat frames, P-frame pre-copies)

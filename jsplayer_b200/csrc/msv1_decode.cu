@@ -76,10 +76,14 @@ __device__ __forceinline__ u64 shfl64(u64 v, int src)
     return ((u64)hi << 32) | lo;
 }
 
-// MSVideo1.hx:211-214
+// MSVideo1.hx:211-214 fromRGB15, for a colour in the low / high half of a 32-bit word (no extraction needed)
 __device__ __forceinline__ uint32_t rgb15(uint32_t c)
 {
-    return ((c & 0x1Fu) << 3) | ((c & 0x3E0u) << 6) | ((c & 0x7C00u) << 9);
+    return ((c << 3) & 0xF8u) | ((c << 6) & 0xF800u) | ((c << 9) & 0xF80000u);
+}
+__device__ __forceinline__ uint32_t rgb15_hi(uint32_t x)
+{
+    return ((x >> 13) & 0xF8u) | ((x >> 10) & 0xF800u) | ((x >> 7) & 0xF80000u);
 }
 
 __device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b, uint32_t cap)
@@ -104,6 +108,7 @@ struct Smem {
     uint32_t big_blk0;                 // first block of a "rest of frame" copy, or 0xFFFFFFFF
     uint32_t flags;
     uint32_t terminated;
+    uint32_t any_runs;
 };
 
 // 16 reconstructed pixels of one coded block from 8 quadrant colours (2-colour and 1-colour blocks are
@@ -111,7 +116,7 @@ struct Smem {
 __device__ __forceinline__ void store_block(int32_t *out, uint32_t X, uint32_t by, uint32_t bx,
                                             const uint32_t (&col)[8], uint32_t flags, bool vec_ok)
 {
-    int32_t *p = out + (size_t)by * 4u * X + bx * 4u;
+    int32_t *p = out + (by * 4u * X + bx * 4u);      // pictures stay below 2^32 pixels
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         uint32_t px[4];
@@ -166,7 +171,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
     //      already been started by a CTA that never waits for a later one (forward progress) ----
     if (tid == 0) {
         sm.ticket = atomicAdd(ticket, 1u);
-        sm.nruns = 0; sm.big_blk0 = 0xFFFFFFFFu; sm.flags = 0; sm.terminated = 0;
+        sm.nruns = 0; sm.big_blk0 = 0xFFFFFFFFu; sm.flags = 0; sm.terminated = 0; sm.any_runs = 0;
     }
     __syncthreads();
     const uint2 tt = tile_tab[sm.ticket];
@@ -227,37 +232,43 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
         __syncthreads();
     }
 
-    // ---- scan 1: backward walk of the lane's 16-word segment -> entry->exit map ----
+    // ---- scan 1: backward walk of the lane's 16-word segment.  R[p] describes the opcode chain that starts at
+    //      word p: bits 0-15 = the words where its opcodes start, bits 16-19 = where it leaves the segment
+    //      (offset into the next one, or 15 = terminated).  All indexing is static after unrolling. ----
+    uint32_t R[MSV1_SEG_WORDS];
+    uint32_t skipmask = 0, termmask = 0;      // per word: "is a copy run" / "ends the frame" if an opcode starts there
     u64 M;
     {
         const uint32_t *sw = reinterpret_cast<const uint32_t *>(sm.bytes) + tid * 8;
         const uint4 v0 = *reinterpret_cast<const uint4 *>(sw);
         const uint4 v1 = *reinterpret_cast<const uint4 *>(sw + 4);
         const uint32_t r[9] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, sw[8]};
-        u64 W = 0;   // nibble k = exit code of position p+1+k (sliding window while p descends)
+#define JSP_NEXT(L) ((p + (L) < MSV1_SEG_WORDS) ? R[(p + (L)) & (MSV1_SEG_WORDS - 1)] : (uint32_t)((p + (L) - MSV1_SEG_WORDS) << 16))
 #pragma unroll
         for (int p = MSV1_SEG_WORDS - 1; p >= 0; --p) {
             uint32_t a, b, h;
-            if (p & 1) { a = (r[p >> 1] >> 16) & 0xFFu; b = r[p >> 1] >> 24; h = (r[(p >> 1) + 1] >> 8) & 0xFFu; }
-            else       { a = r[p >> 1] & 0xFFu; b = (r[p >> 1] >> 8) & 0xFFu; h = r[p >> 1] >> 24; }
-            uint32_t code;
-            bool term = (b == 0x84u) && (a == 0u);                 // skip count 0: rest of the frame is copied (MSVideo1.hx:132,124)
+            if (p & 1) { a = (r[p >> 1] >> 16) & 0xFFu; b = r[p >> 1] >> 24; h = r[(p >> 1) + 1] & 0x8000u; }
+            else       { a = r[p >> 1] & 0xFFu; b = (r[p >> 1] >> 8) & 0xFFu; h = r[p >> 1] & 0x80000000u; }
+            bool isrun = (b & 0xFCu) == 0x84u;                     // skip run (MSVideo1.hx:131 / :315)
+            bool term = (b == 0x84u) && (a == 0u);                 // skip count 0: rest of the frame is copied (:132,124)
+            uint32_t nxt;
             if (IS8) {
-                term = term || (a + b == 0u);                      // terminator (MSVideo1.hx:313)
-                if (b < 0x80u)       code = (p + 2 >= 16) ? (uint32_t)(p + 2 - 16) : (uint32_t)(W >> 4) & 15u;
-                else if (b >= 0x90u) code = (p + 5 >= 16) ? (uint32_t)(p + 5 - 16) : (uint32_t)(W >> 16) & 15u;
-                else                 code = (p + 1 >= 16) ? 0u : (uint32_t)W & 15u;
+                const bool t8 = (a + b == 0u);                     // terminator (MSVideo1.hx:313)
+                term = term || t8; isrun = isrun || t8;
+                nxt = (b < 0x80u) ? JSP_NEXT(2) : (b >= 0x90u ? JSP_NEXT(5) : JSP_NEXT(1));
             } else {
-                (void)a;
-                if (b < 0x80u) {
-                    if (h & 0x80u) code = (p + 9 >= 16) ? (uint32_t)(p + 9 - 16) : (uint32_t)(W >> 32) & 15u;
-                    else           code = (p + 3 >= 16) ? (uint32_t)(p + 3 - 16) : (uint32_t)(W >> 8) & 15u;
-                } else             code = (p + 1 >= 16) ? 0u : (uint32_t)W & 15u;
+                nxt = (b < 0x80u) ? (h ? JSP_NEXT(9) : JSP_NEXT(3)) : JSP_NEXT(1);
             }
-            if (term) code = TERM;
-            W = (W << 4) | code;
+            if (term) nxt = TERM << 16;
+            R[p] = nxt | (1u << p);
+            if (isrun) skipmask |= 1u << p;
+            if (term) termmask |= 1u << p;
         }
-        M = (W & 0xFFFFFFFFFull) | MAP_TERM;
+#undef JSP_NEXT
+        uint32_t lo = 0;
+#pragma unroll
+        for (int e = 0; e < 8; e++) lo |= (R[e] >> 16) << (4 * e);
+        M = ((u64)(R[8] >> 16) << 32) | lo | MAP_TERM;
     }
 
     // ---- scan 2: chain the maps.  A lane whose map is constant fixes its successor's entry outright. ----
@@ -329,25 +340,26 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
         if (!known && lane > 0 && pk) { known = true; entry = pe; }
     }
 
-    // ---- scan 3: forward walk from the true entry: opcode starts, block counts ----
+    // ---- scan 3: the chain of the true entry gives this lane's opcode starts; count its blocks ----
     const int seg_lim = (int)min((uint32_t)MSV1_SEG_WORDS,
                                  tile_words > tid * MSV1_SEG_WORDS ? tile_words - tid * MSV1_SEG_WORDS : 0u);
-    uint32_t starts = 0, nops = 0, blocks = 0;
-    bool lterm = false;
-    if (entry != TERM) {
-        int p = (int)entry;
-        while (p < seg_lim) {
+    uint32_t starts = 0;
+#pragma unroll
+    for (int e = 0; e < NENT; e++) if (entry == (uint32_t)e) starts = R[e];
+    starts &= (1u << seg_lim) - 1u;                                // words past the end of the frame hold no opcodes
+    const uint32_t runs = starts & skipmask;
+    const bool lterm = (starts & termmask) != 0;
+    const uint32_t nops = __popc(starts);
+    uint32_t blocks = nops - __popc(runs);
+    if (runs) {
+        uint32_t m = runs & ~termmask;
+        while (m) {
+            const int p = __ffs(m) - 1; m &= m - 1;
             const uint8_t *o = sm.bytes + (tid * MSV1_SEG_WORDS + p) * 2;
-            const uint32_t a = o[0], b = o[1];
-            starts |= 1u << p; nops++;
-            if ((IS8 && a + b == 0u) || (b == 0x84u && a == 0u)) { blocks = nblocks; lterm = true; break; }
-            if ((b & 0xFCu) == 0x84u) { blocks = sat_add(blocks, ((b - 0x84u) << 8) | a, nblocks); p += 1; }
-            else {
-                blocks = sat_add(blocks, 1u, nblocks);
-                if (IS8) p += (b < 0x80u) ? 2 : (b >= 0x90u ? 5 : 1);
-                else     p += (b < 0x80u) ? ((o[3] & 0x80u) ? 9 : 3) : 1;
-            }
+            blocks += (((uint32_t)o[1] - 0x84u) << 8) | o[0];
         }
+        if (lterm) blocks = nblocks;
+        blocks = min(blocks, nblocks);
     }
     // ---- scan 4: block / opcode prefix sums (warp shuffles + look-back) ----
     uint32_t op_incl = nops, blk_incl = blocks;
@@ -358,7 +370,10 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
         if (lane >= (uint32_t)d) { op_incl += o2; blk_incl = sat_add(blk_incl, b2, nblocks); }
     }
     if (lane == 31) { sm.wops[warp] = op_incl; sm.wblk[warp] = blk_incl; }
-    if (__any_sync(FULL, lterm) && lane == 0) sm.terminated = 1;
+    {
+        const bool anyterm = __any_sync(FULL, lterm), anyrun = __any_sync(FULL, runs != 0);
+        if (lane == 0) { if (anyterm) sm.terminated = 1; if (anyrun) sm.any_runs = 1; }
+    }
     __syncthreads();
     if (tid == 0) {
         uint32_t tot = 0;
@@ -382,6 +397,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
     }
     __syncthreads();
     const uint32_t first_block = sm.first_block;
+    const bool any_runs = sm.any_runs != 0;
     uint32_t tot_ops = 0, tot_blk = 0, op_base = op_incl - nops, blk_base;
     {
         uint32_t wb = 0;
@@ -389,7 +405,6 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
             if (w == warp) { op_base += tot_ops; wb = tot_blk; }
             tot_ops += sm.wops[w]; tot_blk = sat_add(tot_blk, sm.wblk[w], nblocks);
         }
-        // exclusive block prefix of this lane inside the warp (saturating sums are monotone, so recompute)
         const uint32_t prev_incl = __shfl_up_sync(FULL, blk_incl, 1);
         blk_base = sat_add(wb, lane ? prev_incl : 0u, nblocks);
     }
@@ -398,80 +413,85 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
 
     uint32_t myflags = 0;
     if (first_block < nblocks) {
-        // ---- per-opcode table ----
-        {
+        // ---- per-opcode table: word position (and, only when the tile has copy runs, the block index;
+        //      otherwise opcode k of the tile is simply block first_block + k) ----
+        if (!any_runs) {
+            uint32_t m = starts, opi = op_base;
+            while (m) {
+                const int p = __ffs(m) - 1; m &= m - 1;
+                sm.pos[opi++] = (uint16_t)(tid * MSV1_SEG_WORDS + p);
+            }
+        } else {
             uint32_t m = starts, opi = op_base, blk = sat_add(first_block, blk_base, nblocks);
             while (m) {
                 const int p = __ffs(m) - 1; m &= m - 1;
-                const uint8_t *o = sm.bytes + (tid * MSV1_SEG_WORDS + p) * 2;
-                const uint32_t a = o[0], b = o[1];
-                const bool big = (IS8 && a + b == 0u) || (b == 0x84u && a == 0u);
-                const bool run = big || (b & 0xFCu) == 0x84u;
+                const bool run = (skipmask >> p) & 1u, big = (termmask >> p) & 1u;
                 sm.pos[opi] = (uint16_t)((tid * MSV1_SEG_WORDS + p) | (run ? 0x8000u : 0u));
                 sm.blk[opi] = blk;
                 if (big) { sm.big_blk0 = blk; blk = nblocks; }
                 else if (run) {
+                    const uint8_t *o = sm.bytes + (tid * MSV1_SEG_WORDS + p) * 2;
                     sm.runs[atomicAdd(&sm.nruns, 1u)] = (uint16_t)opi;
-                    blk = sat_add(blk, ((b - 0x84u) << 8) | a, nblocks);
+                    blk = sat_add(blk, (((uint32_t)o[1] - 0x84u) << 8) | o[0], nblocks);
                 } else blk = sat_add(blk, 1u, nblocks);
                 opi++;
             }
         }
         __syncthreads();
 
-        // ---- fill: one thread per coded block ----
+        // ---- fill: one thread per coded block, branch-free over the three block classes ----
+        const uint32_t inv_nbx = F.inv_nbx;
         for (uint32_t op = tid; op < tot_ops; op += MSV1_THREADS) {
             const uint32_t pw = sm.pos[op];
             if (pw & 0x8000u) continue;
-            const uint32_t blk = sm.blk[op];
+            const uint32_t blk = any_runs ? sm.blk[op] : first_block + op;
             if (blk >= nblocks) continue;                          // opcodes past the last block are never read
-            const uint32_t by = blk / nbx, bx = blk - by * nbx;
-            const uint8_t *o = sm.bytes + pw * 2;
+            uint32_t by = __umulhi(blk, inv_nbx), bx = blk - by * nbx;
+            if (bx >= nbx) { by++; bx -= nbx; }
             const uint32_t abs0 = tile_byte0 + pw * 2;             // byte offset of the opcode in the frame
             uint32_t col[8], flags;
             if (abs0 + (IS8 ? 10u : 18u) <= len) {
-                const uint32_t a = o[0], b = o[1];
+                // the opcode as aligned 32-bit words, shifted down by 16 bits when it starts on an odd word
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(sm.bytes) + (pw >> 1);
+                const uint32_t sh = (pw & 1u) * 16u;
                 if (IS8) {
-                    if (b < 0x80u) {                               // 2 colours, flags as stored (MSVideo1.hx:319-334)
-                        flags = (b << 8) | a;
-                        const uint32_t c1 = (uint32_t)sm.pal[o[2]], c0 = (uint32_t)sm.pal[o[3]];
+                    const uint32_t v0 = __funnelshift_r(q[0], q[1], sh), v1 = __funnelshift_r(q[1], q[2], sh),
+                                   v2 = __funnelshift_r(q[2], q[3], sh);
+                    const uint32_t a = v0 & 0xFFu, b = (v0 >> 8) & 0xFFu;
+                    const bool two = b < 0x80u, eight = b >= 0x90u;
+                    flags = two ? (v0 & 0xFFFFu) : (eight ? ((v0 & 0xFFFFu) ^ 0xFFFFu) : 0u);   // MSVideo1.hx:320,337
+                    // 2 colours: bit 1 -> pal[first byte], 0 -> pal[second] (:322-323); 1 colour: pal[a] (:353)
+                    const uint32_t podd = (uint32_t)sm.pal[two || eight ? ((v0 >> 16) & 0xFFu) : a];
+                    const uint32_t peven = (uint32_t)sm.pal[two ? (v0 >> 24) : (eight ? ((v0 >> 16) & 0xFFu) : a)];
+                    // (for 8 colours podd/peven are placeholders; the real pairs follow)
 #pragma unroll
-                        for (int k = 0; k < 8; k += 2) { col[k] = c0; col[k + 1] = c1; }
-                    } else if (b >= 0x90u) {                       // 8 colours (:336-352)
-                        flags = ((b << 8) | a) ^ 0xFFFFu;
-#pragma unroll
-                        for (int k = 0; k < 8; k++) col[k] = (uint32_t)sm.pal[o[2 + k]];
-                    } else {                                       // 1 colour (:353-364)
-                        flags = 0;
-                        const uint32_t c = (uint32_t)sm.pal[a];
-#pragma unroll
-                        for (int k = 0; k < 8; k++) col[k] = c;
+                    for (int k = 0; k < 8; k += 2) { col[k] = peven; col[k + 1] = podd; }
+                    if (eight) {                                   // colours in stream order (:338-340)
+                        col[0] = (uint32_t)sm.pal[(v0 >> 16) & 0xFFu]; col[1] = (uint32_t)sm.pal[v0 >> 24];
+                        col[2] = (uint32_t)sm.pal[v1 & 0xFFu];         col[3] = (uint32_t)sm.pal[(v1 >> 8) & 0xFFu];
+                        col[4] = (uint32_t)sm.pal[(v1 >> 16) & 0xFFu]; col[5] = (uint32_t)sm.pal[v1 >> 24];
+                        col[6] = (uint32_t)sm.pal[v2 & 0xFFu];         col[7] = (uint32_t)sm.pal[(v2 >> 8) & 0xFFu];
                     }
                 } else {
-                    const uint16_t *ow = reinterpret_cast<const uint16_t *>(o);
-                    if (b < 0x80u) {
-                        flags = (((b << 8) | a) ^ 0xFFFFu);
-                        const uint32_t w0 = ow[1];
-                        if (w0 & 0x8000u) {                        // 8 colours (MSVideo1.hx:142-160)
-#pragma unroll
-                            for (int k = 0; k < 8; k++) col[k] = rgb15(ow[1 + k]);
-                        } else {                                   // 2 colours (:160-168)
-                            const uint32_t c0 = rgb15(w0), c1 = rgb15(ow[2]);
-#pragma unroll
-                            for (int k = 0; k < 8; k += 2) { col[k] = c0; col[k + 1] = c1; }
-                        }
-                    } else {                                       // 1 colour (:171-181)
-                        flags = 0;
-                        const uint32_t c = rgb15((b << 8) | a);
-#pragma unroll
-                        for (int k = 0; k < 8; k++) col[k] = c;
-                    }
+                    const uint32_t v0 = __funnelshift_r(q[0], q[1], sh), v1 = __funnelshift_r(q[1], q[2], sh),
+                                   v2 = __funnelshift_r(q[2], q[3], sh), v3 = __funnelshift_r(q[3], q[4], sh),
+                                   v4 = __funnelshift_r(q[4], q[5], sh);
+                    const bool one = (v0 & 0x8000u) != 0;          // b >= 0x80: 1 colour = the opcode word (:171-181)
+                    const bool eight = !one && (v0 & 0x80000000u); // colour0 bit 15 (:142)
+                    flags = one ? 0u : ((v0 & 0xFFFFu) ^ 0xFFFFu); // :136
+                    const uint32_t c0 = one ? rgb15(v0) : rgb15_hi(v0);
+                    const uint32_t c1 = one ? c0 : rgb15(v1);
+                    col[0] = c0; col[1] = c1;
+                    col[2] = eight ? rgb15_hi(v1) : c0; col[3] = eight ? rgb15(v2) : c1;
+                    col[4] = eight ? rgb15_hi(v2) : c0; col[5] = eight ? rgb15(v3) : c1;
+                    col[6] = eight ? rgb15_hi(v3) : c0; col[7] = eight ? rgb15(v4) : c1;
                 }
             } else {
                 // the opcode runs past the end of the frame: JavaScript `undefined` reads, byte by byte
+                const uint8_t *o = sm.bytes + pw * 2;
                 auto rd = [&](uint32_t i) -> int { return abs0 + i < len ? (int)o[i] : -1; };
                 auto w16 = [&](uint32_t i) -> uint32_t { return abs0 + i + 1 < len ? (uint32_t)o[i] | ((uint32_t)o[i + 1] << 8) : 0u; };
-                const int a = rd(0), b = (len & 1u) && abs0 + 1 == len ? -1 : rd(1);
+                const int a = rd(0), b = rd(1);
                 flags = 0;
                 if (IS8) {
                     auto palu = [&](int ix) -> uint32_t { return ix < 0 ? 0u : (uint32_t)sm.pal[ix]; };

@@ -194,7 +194,7 @@ def test_full_size_properties_1080p_batch():
     outs, flags = gpu_streams(specs)
     for i in range(n):
         o = outs[i]
-        assert ((o & 0xFF070707) == 0).all()                   # RGB555 -> 0x00RRGGBB with low 3 bits clear
+        assert ((o.view(np.uint32) & np.uint32(0xFF070707)) == 0).all()                   # RGB555 -> 0x00RRGGBB with low 3 bits clear
         assert flags[i] & _lib.JSP_FRAME_CHANGED
     # identical input -> identical output (idempotence), and one oracle spot check
     outs2, _ = gpu_streams(specs[:2])
