@@ -77,19 +77,40 @@ __device__ __forceinline__ u64 shfl64(u64 v, int src)
 }
 
 // MSVideo1.hx:211-214 fromRGB15, for a colour in the low / high half of a 32-bit word (no extraction needed)
+// The three fields are masked on the ALU pipe and positioned with integer multiply-adds on the otherwise idle
+// FMA pipe (the kernel is ALU-pipe bound, profiles/r01_msv1_ncu.md); the fields never overlap, so + is |.
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ uint32_t rgb15(uint32_t c)
 {
-    return ((c << 3) & 0xF8u) | ((c << 6) & 0xF800u) | ((c << 9) & 0xF80000u);
+    return mad_u32(c & 0x7C00u, 512u, mad_u32(c & 0x3E0u, 64u, (c & 0x1Fu) * 8u));
 }
 __device__ __forceinline__ uint32_t rgb15_hi(uint32_t x)
 {
-    return ((x >> 13) & 0xF8u) | ((x >> 10) & 0xF800u) | ((x >> 7) & 0xF80000u);
+    return rgb15(x >> 16);
 }
 
 __device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b, uint32_t cap)
 {
     uint32_t s = a + b;
     return s < cap ? s : cap;
+}
+
+// explicit global-space streaming accesses (the pointers come out of a descriptor, so the compiler would
+// otherwise emit generic-space ST/LD)
+__device__ __forceinline__ void st_global_cs(void *p, const uint4 &v)
+{
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_global_cs(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.cs.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(__cvta_generic_to_global(p)));
+    return v;
 }
 
 struct Smem {
@@ -126,7 +147,7 @@ __device__ __forceinline__ void store_block(int32_t *out, uint32_t X, uint32_t b
             px[x] = ((flags >> (4 * r + x)) & 1u) ? col[q + 1] : col[q];
         }
         if (vec_ok) {
-            __stcs(reinterpret_cast<uint4 *>(p), make_uint4(px[0], px[1], px[2], px[3]));
+            st_global_cs(p, make_uint4(px[0], px[1], px[2], px[3]));
         } else {
             p[0] = (int32_t)px[0]; p[1] = (int32_t)px[1]; p[2] = (int32_t)px[2]; p[3] = (int32_t)px[3];
         }
@@ -144,13 +165,13 @@ __device__ __forceinline__ void copy_block(int32_t *out, const int32_t *prev, ui
         if (prev) {
             const int32_t *s = prev + off;
 #pragma unroll
-            for (int r = 0; r < 4; r++) v[r] = __ldcs(reinterpret_cast<const uint4 *>(s + (size_t)r * X));
+            for (int r = 0; r < 4; r++) v[r] = ld_global_cs(s + (size_t)r * X);
         } else {
 #pragma unroll
             for (int r = 0; r < 4; r++) v[r] = make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int r = 0; r < 4; r++) __stcs(reinterpret_cast<uint4 *>(d + (size_t)r * X), v[r]);
+        for (int r = 0; r < 4; r++) st_global_cs(d + (size_t)r * X, v[r]);
     } else {
         for (int r = 0; r < 4; r++)
             for (int x = 0; x < 4; x++) d[(size_t)r * X + x] = prev ? prev[off + (size_t)r * X + x] : 0;
@@ -195,7 +216,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
             const int b0 = c * 16;
             uint4 v;
             if (aligned && b0 + 16 <= avail) {
-                v = __ldcs(reinterpret_cast<const uint4 *>(g + b0));
+                v = ld_global_cs(g + b0);
             } else if (b0 >= avail) {
                 v = make_uint4(0, 0, 0, 0);
             } else {
