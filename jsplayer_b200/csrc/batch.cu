@@ -72,13 +72,52 @@ static int classify(const StreamRec &S, const uint8_t *src, uint32_t len)
         if ((S.w >> 2) == 0 || (S.h >> 2) == 0) return FK_COPY;
         return FK_MSV8;
     }
-    return FK_SP;
+    return FK_COPY;   // ScreenPressor frames are classified by classify_sp() with the stream's state
+}
+
+// What Manager.worker + ScreenPressor.DecompressI/P decide before any entropy decoding happens
+// (Manager.hx:505-512, ScreenPressor.hx:129-164, :306-313), replayed on the host for one frame.
+static void classify_sp(const StreamRec &S, SpHost &H, FrameRec &R, const uint8_t *src)
+{
+    R.kind = FK_COPY; R.forced = 0; R.sp_flags = 0; R.fill_value = 0;
+    const uint32_t len = R.len;
+    if (R.key) {                                              // DecompressI
+        if (len == 0) { H.last_flat = false; R.forced = ST_ERROR; return; }   // head undefined -> "unknown version of the codec"
+        const int head = src[0], version = (head >> 4) + 1;
+        if ((head & 0xF) == 1) {                              // flat (:132-155)
+            if (H.version == 0) { R.forced = ST_ERROR; return; }             // ec == null (Appendix E)
+            uint32_t c;
+            auto rd = [&](uint32_t i) -> uint32_t { return i < len ? src[i] : 0u; };
+            if (S.bpp == 16) {
+                const uint32_t c16 = rd(0) + rd(1) * 256;
+                c = (((c16 >> 10) & 0x1F) << 19) | (((c16 >> 5) & 0x1F) << 11) | ((c16 & 0x1F) << 3);
+            } else c = (rd(3) << 16) | (rd(2) << 8) | rd(1);
+            R.kind = FK_SP_FLAT; R.fill_value = c; R.forced = ST_CHANGED;
+            R.sp_flags = H.last_flat ? 0u : SPJ_RENEW;        // RenewI skips ec.renewI() after a flat frame (:113)
+            H.last_flat = true; H.decodedI = true;
+            return;
+        }
+        H.last_flat = false;
+        if ((head & 0xF) != 2) { R.forced = ST_ERROR; return; }              // :157-159
+        if (H.version == 0) {
+            if (version != 2) { R.forced = ST_ERROR; return; }               // v3/v4 (rANS): not in this build yet
+            H.version = version;
+        }
+        R.kind = FK_SP_I; R.sp_flags = SPJ_IFRAME;
+        H.decodedI = true;
+    } else {                                                  // DecompressP
+        H.last_flat = false;
+        if (len == 0 || !H.decodedI || src[0] == 0) return;   // :308-313 -> previous buffer
+        R.kind = FK_SP_P;
+    }
+    if (H.version == 2 && S.bpp == 16) R.sp_flags |= SPJ_DIFF16 | SPJ_CXSHIFT0;   // :59, :200-202 (v3/v4 force shift 2, :71-73)
 }
 
 struct HostTables {
     std::vector<Msv1Frame> mframes;
     std::vector<uint2> tile_tab;
     std::vector<CopyJob> jobs;
+    std::vector<SpJob> spjobs;
 };
 
 // Builds the launch list of `plan` for streams [s_lo, s_hi).
@@ -89,6 +128,7 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
     plan.frame_hi = b->streams[s_hi - 1].first_frame + b->streams[s_hi - 1].n_frames;
     plan.tile_tab_off = T.tile_tab.size();
     plan.job_off = T.jobs.size();
+    plan.spjob_off = T.spjobs.size();
     plan.state_off = state_cursor;
     plan.ticket_off = ticket_cursor;
 
@@ -103,12 +143,13 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             const size_t first = T.jobs.size(); uint32_t maxv = 0;
             for (int64_t f : by_level[lv]) {
                 FrameRec &R = b->frames[f];
-                if (R.kind != FK_COPY) continue;
+                if (R.kind != FK_COPY && R.kind != FK_SP_P && R.kind != FK_SP_FLAT) continue;
                 const StreamRec &S = b->streams[R.stream];
                 CopyJob J;
                 J.dst = b->d_out + R.out_off;
                 J.src = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
                 J.value = 0;
+                if (R.kind == FK_SP_FLAT) { J.src = nullptr; J.value = R.fill_value; }
                 J.n_vec4 = (uint32_t)(((size_t)S.w * S.h * 4 + 15) / 16);
                 maxv = std::max(maxv, J.n_vec4);
                 T.jobs.push_back(J);
@@ -136,7 +177,30 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             plan.launches.push_back({JSP_K_MSV1_DECODE, kind, first, (uint32_t)(T.tile_tab.size() - first), 0, (uint32_t)ticket_cursor});
             ticket_cursor++;
         }
+        // ScreenPressor: one warp per frame of this level (after the copies that prepared the pictures)
+        {
+            const size_t first = T.spjobs.size();
+            for (int64_t f : by_level[lv]) {
+                FrameRec &R = b->frames[f];
+                if (R.kind != FK_SP_I && R.kind != FK_SP_P && !(R.kind == FK_SP_FLAT && (R.sp_flags & SPJ_RENEW))) continue;
+                const StreamRec &S = b->streams[R.stream];
+                const SpHost &H = b->sp_hosts[R.stream];
+                SpJob J{};
+                J.src = b->d_bytes + R.d_src; J.len = R.len;
+                J.dst = b->d_out + R.out_off;
+                J.prev = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
+                J.status = b->d_status + f;
+                J.state = b->d_sp_state + H.state_off;
+                J.bts = b->d_sp_bts + H.bts_off;
+                J.X = (uint32_t)S.w; J.Y = (uint32_t)S.h; J.flags = R.sp_flags;
+                J.insign_blocks = (uint32_t)(((S.w + 15) / 16) * ((std::max(0, b->insign_lines) + 15) / 16));
+                T.spjobs.push_back(J);
+            }
+            if (T.spjobs.size() > first)
+                plan.launches.push_back({JSP_K_SP_ENTROPY_RC, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), 0, 0});
+        }
     }
+    plan.n_spjobs = T.spjobs.size() - plan.spjob_off;
     plan.n_tile_entries = T.tile_tab.size() - plan.tile_tab_off;
     plan.n_jobs = T.jobs.size() - plan.job_off;
     plan.n_states = state_cursor - plan.state_off;
@@ -204,6 +268,8 @@ static bool upload_tables(jsp_batch *b, HostTables &T, size_t n_states, size_t n
     if (!T.mframes.empty() && !JSP_CUDA(cudaMemcpy(b->d_mframes, T.mframes.data(), T.mframes.size() * sizeof(Msv1Frame), cudaMemcpyHostToDevice))) return false;
     if (!T.tile_tab.empty() && !JSP_CUDA(cudaMemcpy(b->d_tile_tab, T.tile_tab.data(), T.tile_tab.size() * sizeof(uint2), cudaMemcpyHostToDevice))) return false;
     if (!T.jobs.empty() && !JSP_CUDA(cudaMemcpy(b->d_jobs, T.jobs.data(), T.jobs.size() * sizeof(CopyJob), cudaMemcpyHostToDevice))) return false;
+    if (!grow(b->d_spjobs, b->spjobs_cap, T.spjobs.size() + 1)) return false;
+    if (!T.spjobs.empty() && !JSP_CUDA(cudaMemcpy(b->d_spjobs, T.spjobs.data(), T.spjobs.size() * sizeof(SpJob), cudaMemcpyHostToDevice))) return false;
     return true;
 }
 
@@ -227,6 +293,9 @@ static bool run_plan(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *
             launch_msv1_decode(L.kind == FK_MSV8, b->d_mframes, b->d_tile_tab + L.first, L.count,
                                b->d_tile_map, b->d_tile_cnt, b->d_tickets + L.ticket, st);
             break;
+        case JSP_K_SP_ENTROPY_RC:
+            launch_sp_rc(b->d_spjobs + L.first, L.count, st);
+            break;
         default: break;
         }
     }
@@ -243,7 +312,8 @@ static bool plan_and_upload(jsp_batch *b)
         for (int f = 0; f < S.n_frames; f++) {
             FrameRec &R = b->frames[S.first_frame + f];
             // key frames do not depend on the previous picture; everything else runs one level later
-            const bool independent = R.key && R.kind != FK_COPY;
+            // (ScreenPressor frames of one stream share the stream's model state: always in order)
+            const bool independent = R.key && (R.kind == FK_MSV16 || R.kind == FK_MSV8);
             level = (independent || f == 0) ? 0 : level + 1;
             R.level = level;
         }
@@ -313,7 +383,8 @@ void jsp_batch_destroy(jsp_batch *b)
     for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
     void *ptrs[] = {b->d_bytes, b->d_out, b->d_pal, b->d_status, b->d_mframes, b->d_tile_tab, b->d_jobs, b->d_tile_map,
                     b->d_tile_cnt, b->d_tickets, b->d_sig_cur, b->d_sig_prev, b->d_sig_status, b->d_sig_first, b->d_sig_npx,
-                    b->d_stream_first, b->d_stream_count, b->d_frame_codec, b->d_flush};
+                    b->d_stream_first, b->d_stream_count, b->d_frame_codec, b->d_flush, b->d_spjobs, b->d_sp_state,
+                    b->d_sp_rows, b->d_sp_bts};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (b->h_status) cudaFreeHost(b->h_status);
     if (b->st_compute) cudaStreamDestroy(b->st_compute);
@@ -326,6 +397,12 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
 {
     if (!b || !sd || n_streams <= 0) { set_error("jsp_batch_configure: bad arguments"); return -1; }
     if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
+    // per-stream codec state survives a re-configure only for the per-stream drop-in (same single stream)
+    bool keep = b->persist_streams && (int)b->streams.size() == n_streams;
+    for (int s = 0; keep && s < n_streams; s++)
+        keep = b->streams[s].codec == sd[s].codec && b->streams[s].w == sd[s].width && b->streams[s].h == sd[s].height &&
+               b->streams[s].bpp == sd[s].bpp;
+    if (!keep) b->sp_hosts.assign((size_t)n_streams, SpHost{});
     b->streams.clear(); b->frames.clear(); b->chunks.clear();
     size_t bytes_cur = 0, out_cur = 0, pal_cur = 0;
     int64_t nf = 0;
@@ -373,13 +450,16 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
             R.d_src = S.d_base + (size_t)(D.frame_len[f] ? D.frame_off[f] - lo : 0);
             R.out_off = out_cur; out_cur += npix_pad;
             R.prev = f > 0 ? nf + f - 1 : -1;
-            R.kind = classify(S, D.bytes ? D.bytes + D.frame_off[f] : nullptr, R.len);
+            const uint8_t *fsrc = D.bytes ? D.bytes + D.frame_off[f] : nullptr;
+            R.forced = 0; R.fill_value = 0; R.sp_flags = 0;
+            if (S.codec == JSP_CODEC_SCREENPRESSOR) classify_sp(S, b->sp_hosts[s], R, fsrc);
+            else R.kind = classify(S, fsrc, R.len);
             R.level = 0;   // assigned by plan_and_upload()
             R.n_tiles = (R.kind == FK_MSV16 || R.kind == FK_MSV8)
                             ? std::max<uint32_t>(1u, (uint32_t)(((size_t)((R.len + 1) >> 1) + MSV1_TILE_WORDS - 1) / MSV1_TILE_WORDS)) : 0u;
             b->frames.push_back(R);
             b->stat_pixels += npix;
-            b->stat_alg_bytes += npix * 4 + R.len + (R.kind == FK_COPY ? npix * 4 : 0);
+            b->stat_alg_bytes += npix * 4 + R.len + ((R.kind == FK_COPY || R.kind == FK_SP_P) ? npix * 4 : 0);
             b->stat_in_bytes += R.len;
             b->stat_out_bytes += npix * 4;
         }
@@ -410,6 +490,33 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
             pal[i] = (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
         }
         if (!JSP_CUDA(cudaMemcpy(b->d_pal + b->streams[s].pal_off, pal, sizeof pal, cudaMemcpyHostToDevice))) return -1;
+    }
+    // ScreenPressor model state: small tables + 12288 colour rows per stream, block-type scratch
+    {
+        size_t st_cur = 0, rows_cur = 0, bts_cur = 0; bool any = false;
+        for (int s = 0; s < n_streams; s++) {
+            if (b->streams[s].codec != JSP_CODEC_SCREENPRESSOR) continue;
+            any = true;
+            SpHost &H = b->sp_hosts[s];
+            H.state_off = st_cur; st_cur += sp_rc_state_bytes();
+            H.rows_off = rows_cur; rows_cur += sp_rc_rows_bytes();
+            H.bts_off = bts_cur; bts_cur += ((size_t)((b->streams[s].w + 15) / 16) * ((b->streams[s].h + 15) / 16) + 255) & ~(size_t)255;
+        }
+        if (any) {
+            const bool fresh_alloc = st_cur > b->sp_state_cap || rows_cur > b->sp_rows_cap || !b->d_sp_state;
+            if (!grow(b->d_sp_state, b->sp_state_cap, st_cur)) return -1;
+            if (!grow(b->d_sp_rows, b->sp_rows_cap, rows_cur)) return -1;
+            if (!grow(b->d_sp_bts, b->sp_bts_cap, bts_cur)) return -1;
+            if (!keep || fresh_alloc) {
+                // generation tags of all rows to 0, generations start at 1: every row reads as "all ones"
+                if (!JSP_CUDA(cudaMemsetAsync(b->d_sp_rows, 0, rows_cur, b->st_compute))) return -1;
+                if (!JSP_CUDA(cudaMemsetAsync(b->d_sp_state, 0, st_cur, b->st_compute))) return -1;
+                for (int s = 0; s < n_streams; s++)
+                    if (b->streams[s].codec == JSP_CODEC_SCREENPRESSOR)
+                        sp_rc_state_init(b->d_sp_state + b->sp_hosts[s].state_off, b->d_sp_rows + b->sp_hosts[s].rows_off, 1u, b->st_compute);
+                if (!JSP_CUDA(cudaStreamSynchronize(b->st_compute))) return -1;
+            }
+        }
     }
     if (!plan_and_upload(b)) return -1;
 
@@ -497,6 +604,7 @@ int jsp_batch_results(jsp_batch *b, uint8_t *flags)
     const size_t n = b->frames.size();
     if (!JSP_CUDA(cudaMemcpyAsync(b->h_status, b->d_status, n * 4, cudaMemcpyDeviceToHost, b->st_compute))) return -1;
     if (!JSP_CUDA(cudaStreamSynchronize(b->st_compute))) return -1;
+    for (size_t i = 0; i < n; i++) b->h_status[i] |= b->frames[i].forced;
     // A frame the caller flagged as key (so it was scheduled without waiting for its predecessor) that
     // nevertheless copies from the previous picture: demote it, re-level, decode again in order.
     bool demoted = false;

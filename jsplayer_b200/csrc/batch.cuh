@@ -3,6 +3,7 @@
 // (src/DataLoader.hx:31,93-98; src/Manager.hx:454-525), for many streams at once.
 #pragma once
 #include "common.cuh"
+#include "sp_common.cuh"
 #include "../../include/jsplayer_cuda.h"
 #include <string>
 #include <vector>
@@ -14,7 +15,27 @@ bool cuda_ok(cudaError_t e, const char *what);
 bool msv16_unchanged(int w, int h, const uint8_t *src, uint32_t len);
 #define JSP_CUDA(call) ::jsp::cuda_ok((call), #call)
 
-enum FrameKind : int { FK_MSV16 = 0, FK_MSV8 = 1, FK_COPY = 2, FK_SP = 3 };
+enum FrameKind : int {
+    FK_MSV16 = 0, FK_MSV8 = 1,
+    FK_COPY = 2,        // picture = previous picture (unchanged / skipped / failed frame)
+    FK_SP_I = 3,        // ScreenPressor coded I frame
+    FK_SP_P = 4,        // ScreenPressor P frame (starts from a copy of the previous picture)
+    FK_SP_FLAT = 5,     // ScreenPressor flat I frame: whole-picture fill (+ model reset)
+};
+
+// ScreenPressor per-stream bookkeeping the reference keeps in the codec object (ScreenPressor.hx:26-43)
+struct SpHost {
+    int version = 0;            // 0 = no entropy coder yet (`ec == null`), else 2/3/4 (initEntro, :66-79)
+    bool decodedI = false;
+    bool last_flat = false;     // last_one_was_flat != null
+    size_t state_off = 0, rows_off = 0, bts_off = 0;
+};
+
+// sp_rc.cu
+size_t sp_rc_state_bytes();
+size_t sp_rc_rows_bytes();
+void sp_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t st);
+void launch_sp_rc(const SpJob *d_jobs, uint32_t n_jobs, cudaStream_t st);
 
 struct StreamRec {
     int codec, w, h, bpp;
@@ -36,6 +57,9 @@ struct FrameRec {
     int kind;
     uint8_t key;
     uint32_t n_tiles, state_base;
+    uint32_t forced;                // status bits decided on the host (ST_ERROR, ST_CHANGED of flat frames)
+    uint32_t fill_value;            // FK_SP_FLAT colour
+    uint32_t sp_flags;              // SPJ_* for ScreenPressor jobs
 };
 
 struct Launch {
@@ -58,6 +82,7 @@ struct Plan {
     size_t job_off = 0, n_jobs = 0;                // slice of d_jobs
     size_t state_off = 0, n_states = 0;            // slice of the tile-state arrays
     size_t ticket_off = 0, n_tickets = 0;
+    size_t spjob_off = 0, n_spjobs = 0;            // slice of d_spjobs
 };
 
 }  // namespace jsp
@@ -85,6 +110,13 @@ struct jsp_batch {
     jsp::CopyJob *d_jobs = nullptr; size_t jobs_cap = 0;
     unsigned long long *d_tile_map = nullptr, *d_tile_cnt = nullptr; size_t states_cap = 0;
     unsigned int *d_tickets = nullptr; size_t tickets_cap = 0;
+    // ScreenPressor: per-stream model state in HBM
+    std::vector<jsp::SpHost> sp_hosts;             // one per stream (unused entries for MSVideo1 streams)
+    jsp::SpJob *d_spjobs = nullptr; size_t spjobs_cap = 0;
+    uint8_t *d_sp_state = nullptr; size_t sp_state_cap = 0;
+    uint8_t *d_sp_rows = nullptr;  size_t sp_rows_cap = 0;
+    uint8_t *d_sp_bts = nullptr;   size_t sp_bts_cap = 0;
+    int persist_streams = 0;                       // per-stream drop-in: keep codec state across configure calls
     // significance post-pass tables
     const int32_t **d_sig_cur = nullptr; const int32_t **d_sig_prev = nullptr; uint32_t **d_sig_status = nullptr;
     uint32_t *d_sig_first = nullptr, *d_sig_npx = nullptr; size_t sig_cap = 0, n_sig = 0;

@@ -59,6 +59,7 @@ bool ensure_batch(jsp_dec *d)
     if (d->b) return true;
     d->b = jsp_batch_create(d->device, d->insign_lines, JSP_BATCH_SIGNIFICANCE);
     if (!d->b) return false;
+    d->b->persist_streams = 1;
     const size_t npix = ((size_t)d->w * d->h + 63) & ~(size_t)63;
     if (!JSP_CUDA(cudaMalloc((void **)&d->d_prev, npix * 4))) return false;
     return JSP_CUDA(cudaMemset(d->d_prev, 0, npix * 4));

@@ -1,0 +1,253 @@
+// sp_common.cuh -- ScreenPressor frame decode for sm_100a, shared by the range-coder (v2) and rANS (v3/v4)
+// entropy kernels.  Replaces reference src/ScreenPressor.hx:117-295 (DecompressI) and :302-484 (DecompressP).
+//
+// One warp decodes one frame of one stream: the entropy decode is a strictly serial chain through the coder
+// state and the adaptive models (every symbol depends on the previous one, and the context of the next colour
+// depends on reconstructed pixels -- ScreenPressor.hx:274-275,462-463), so the parallelism is (a) across
+// streams: one warp-sized CTA per stream, hundreds per launch, and (b) inside a symbol: the 32 lanes search the
+// cumulative-frequency table together and write / predict a run of pixels together.  Whole-picture work
+// (P-frame "start from the previous picture", unchanged frames, flat frames) is done by the wide frame_copy
+// kernel before this one (frame_ops.cu).
+#pragma once
+#include "common.cuh"
+
+namespace jsp {
+
+enum : uint32_t {
+    SPJ_IFRAME   = 1u << 0,   // coded I frame (head & 15 == 2)
+    SPJ_RENEW    = 1u << 1,   // flat I frame: only reset the models (RenewI, ScreenPressor.hx:108-115)
+    SPJ_DIFF16   = 1u << 2,   // 16 bpp stream on the range coder: other context constants (:200-202, :316-318)
+    SPJ_CXSHIFT0 = 1u << 3,   // SC_CXSHIFT == 0 (:59)
+};
+
+struct SpJob {
+    const uint8_t *src;       // compressed frame (device)
+    int32_t       *dst;       // output picture; for P frames it already holds a copy of the previous picture
+    const int32_t *prev;      // previous picture (P frames)
+    uint32_t      *status;
+    void          *state;     // per-stream model state (RcState / AnsState)
+    uint8_t       *bts;       // per-stream block-type scratch, nbx*nby bytes
+    uint32_t len, X, Y, flags;
+    uint32_t insign_blocks;   // nbx * ceil(insignificant_lines / 16) (ScreenPressor.hx:86-89)
+    uint32_t pad;
+};
+
+constexpr uint32_t FULLMASK = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// per-byte add / subtract without carries between bytes (the predictor works per channel, mod 256)
+__device__ __forceinline__ uint32_t vadd4(uint32_t a, uint32_t b) { return ((a & 0x7F7F7F7Fu) + (b & 0x7F7F7F7Fu)) ^ ((a ^ b) & 0x80808080u); }
+__device__ __forceinline__ uint32_t vsub4(uint32_t a, uint32_t b) { return ((a | 0x80808080u) - (b & 0x7F7F7F7Fu)) ^ ((a ^ ~b) & 0x80808080u); }
+
+__device__ __forceinline__ uint32_t px_load(const int32_t *p, long i, long end)
+{
+    return (p && i >= 0 && i < end) ? (uint32_t)p[i] : 0u;      // out-of-frame reads yield 0 (JavaScript undefined -> 0)
+}
+
+// One segment of m <= 32 consecutive pixels starting at index i, all produced by predictor `ptype`
+// (ScreenPressor.hx:242-273 / :439-450).  `left` = the pixel at i-1.  Returns the segment's last pixel.
+__device__ __forceinline__ uint32_t sp_segment(int32_t *dst, const int32_t *prev, long i, int m, int ptype,
+                                               uint32_t clr, uint32_t left, long X, long end)
+{
+    const int lane = (int)lane_id();
+    const long idx = i + lane;
+    uint32_t v = clr;
+    switch (ptype) {
+    case 1: v = left; break;
+    case 2: v = px_load(dst, idx - X, end); break;
+    case 3: v = px_load(prev, idx, end); break;
+    case 5: v = px_load(dst, idx - X - 1, end); break;
+    case 4: {
+        uint32_t d = lane < m ? vsub4(px_load(dst, idx - X, end), px_load(dst, idx - X - 1, end)) : 0u;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULLMASK, d, s);
+            if (lane >= s) d = vadd4(d, o);
+        }
+        v = vadd4(left, d) & 0x00FFFFFFu;
+        break;
+    }
+    default: break;
+    }
+    if (lane < m && idx >= 0 && idx < end) dst[idx] = (int32_t)v;
+    const uint32_t last = __shfl_sync(FULLMASK, v, (m - 1) & 31);
+    __syncwarp();
+    return last;
+}
+
+// ---- the frame loops, generic over the entropy coder (EntroCoder interface, EntroCoders.hx:8-24) ----
+template <class Coder>
+__device__ void sp_decode_iframe(Coder &ec, const SpJob &J)
+{
+    const long X = J.X, end = (long)J.X * J.Y;
+    int32_t *dst = J.dst;
+    const int cxshift = (J.flags & SPJ_CXSHIFT0) ? 0 : 2;
+    int maskcx1 = 0xFC00, shiftcx1 = 4, shiftcx = 18;
+    if (J.flags & SPJ_DIFF16) { maskcx1 = 0xFF00; shiftcx1 = 2; shiftcx = 16; }
+    const int lane = (int)lane_id();
+    const int chunk = X < 32 ? (int)X : 32;       // a chunk never reads pixels it writes itself (row above is X away)
+    ec.renewI();
+    ec.decodeBegin(J.src, J.len, 1);
+    int cx = 0, cx1 = 0;
+    long di = 0, k = 0;
+    uint32_t clr = 0, lastval = 0;
+    auto decode_rgb = [&]() -> uint32_t {       // ScreenPressor.hx:173-183
+        const int r = ec.decodeClr(cx + cx1);
+        cx1 = (cx << 6) & 0xFC0; cx = r >> cxshift;
+        const int g = ec.decodeClr(4096 + cx + cx1);
+        cx1 = (cx << 6) & 0xFC0; cx = g >> cxshift;
+        const int b = ec.decodeClr(2 * 4096 + cx + cx1);
+        cx1 = (cx << 6) & 0xFC0; cx = b >> cxshift;
+        return ((uint32_t)b << 16) + ((uint32_t)g << 8) + (uint32_t)r;
+    };
+    while (k < X + 1) {                            // first X+1 pixels: (colour, run) pairs, :170-197
+        clr = decode_rgb();
+        const int n = ec.decodeN(0);
+        if (ec.failed()) return;
+        k += n;
+        for (int o = 0; o < n; o += 32) {
+            const long idx = di + o + lane;
+            if (o + lane < n && idx < end) dst[idx] = (int32_t)clr;
+        }
+        if (n > 0) lastval = clr;
+        di += n;
+    }
+    __syncwarp();
+    int ptype = 0;
+    while (di < end) {                             // :218-286
+        ptype = ec.decodeP(ptype);
+        if (ptype == 0) clr = decode_rgb();
+        int n = ec.decodeN(ptype);
+        if (ec.failed()) return;
+        if (ptype == 3 || ptype > 5) n = 0;        // no such predictor in an I frame: nothing is written
+        if (ptype == 1) clr = lastval;             // `clr = dst[lasti]` even for an empty run (:252)
+        for (int o = 0; o < n; o += chunk) {
+            const int m = n - o < chunk ? n - o : chunk;
+            lastval = sp_segment(dst, nullptr, di + o, m, ptype, clr, lastval, X, end);
+        }
+        if (n > 0 && ptype != 0) clr = lastval;
+        di += n;
+        cx1 = ((int)clr & maskcx1) >> shiftcx1;    // :274-275
+        cx = (int)clr >> shiftcx;
+    }
+}
+
+template <class Coder>
+__device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bits)
+{
+    const long X = J.X, Y = J.Y, end = X * Y;
+    const int nbx = (int)((J.X + 15) / 16), nby = (int)((J.Y + 15) / 16), nb = nbx * nby;
+    int32_t *dst = J.dst;
+    const int32_t *prev = J.prev;
+    uint8_t *bts = J.bts;
+    const int lane = (int)lane_id();
+    const int cxshift = (J.flags & SPJ_CXSHIFT0) ? 0 : 2;
+    int maskcx1 = 0xFC00, shiftcx1 = 4, shiftcx = 18;
+    if (J.flags & SPJ_DIFF16) { maskcx1 = 0xFF00; shiftcx1 = 2; shiftcx = 16; }
+    ec.decodeBegin(J.src, J.len, 1);
+    int t = ec.decodeX();
+    int xx1 = ec.decodeX(); xx1 = (xx1 << 8) + t;
+    t = ec.decodeX();
+    int xx2 = ec.decodeX(); xx2 = (xx2 << 8) + t;
+    for (int i = lane; i < nb; i += 32) bts[i] = 0;
+    __syncwarp();
+    bool signif = false;
+    long x = xx1;
+    while (x <= xx2) {                             // block types, run-length coded (:336-344)
+        const int bt = ec.decodeBT();
+        const int n = ec.decodeBN();
+        if (ec.failed()) return;
+        for (int o = lane; o < n; o += 32) { const long p = x + o; if (p >= 0 && p < nb) bts[p] = (uint8_t)bt; }
+        if (bt > 0 && n > 0) {                     // significant changes? (:347-352)
+            const long lo = x > (long)J.insign_blocks ? x : (long)J.insign_blocks;
+            const long hi = x + n - 1 < nb - 1 ? x + n - 1 : nb - 1;
+            if (lo <= hi) signif = true;
+        }
+        x += n;
+    }
+    __syncwarp();
+    if (signif) status_bits |= ST_SIGNIFICANT;
+    status_bits |= ST_CHANGED;
+    int cx = 0, cx1 = 0;
+    uint32_t clr = 0;
+    int lastmx = 0, lastmy = 0;
+    auto decode_rgb = [&]() -> uint32_t {
+        const int r = ec.decodeClr(cx + cx1);
+        cx1 = (cx << 6) & 0xFC0; cx = r >> cxshift;
+        const int g = ec.decodeClr(4096 + cx + cx1);
+        cx1 = (cx << 6) & 0xFC0; cx = g >> cxshift;
+        const int b = ec.decodeClr(2 * 4096 + cx + cx1);
+        cx1 = (cx << 6) & 0xFC0; cx = b >> cxshift;
+        return ((uint32_t)b << 16) + ((uint32_t)g << 8) + (uint32_t)r;
+    };
+    for (int bi = 0; bi < nb; bi++) {
+        // skip unchanged blocks 32 at a time: they already hold the previous picture
+        if ((bi & 31) == 0) {
+            const int probe = bi + lane < nb ? bts[bi + lane] : 0;
+            const uint32_t any = __ballot_sync(FULLMASK, probe != 0);
+            if (!any) { bi += 31; continue; }
+        }
+        const int bt = bts[bi];
+        if (bt == 0) continue;
+        const int by = bi / nbx, bx = bi - by * nbx;
+        const int y16 = by * 16, x16 = bx * 16;
+        int x1 = x16, x2 = x16 + 16, y1 = y16, y2 = y16 + 16;
+        if (x2 > X) x2 = (int)X;
+        if (y2 > Y) y2 = (int)Y;
+        if (((bt - 1) & 1) > 0) {                  // sub-rectangle (:375-386); the block itself is already copied
+            x1 = ec.decodeSXY(0) + x16;
+            y1 = ec.decodeSXY(1) + y16;
+            x2 = ec.decodeSXY(2) + x16 + 1;
+            y2 = ec.decodeSXY(3) + y16 + 1;
+        }
+        if (((bt - 1) & 2) > 0) {                  // motion vector (:388-405)
+            int mx, my;
+            if (Coder::kCanDecodeBool && ec.decodeBool()) { mx = lastmx; my = lastmy; }
+            else { mx = ec.decodeMX() - 256; my = ec.decodeMY() - 256; }
+            if (ec.failed()) return;
+            lastmx = mx; lastmy = my;
+            const int w = x2 - x1;                 // <= 16: the rectangle lies inside one block
+            for (int y = y1; y < y2; y += 2) {     // two rows of up to 16 pixels per pass
+                const int ry = y + (lane >> 4), rx = lane & 15;
+                if (ry < y2 && rx < w) {
+                    const long i = (long)ry * X + x1 + rx, j = (long)(ry + my) * X + (x1 + mx) + rx;
+                    if (i >= 0 && i < end) dst[i] = (int32_t)px_load(prev, j, end);
+                }
+            }
+            __syncwarp();
+        } else {                                   // data (:406-467): runs in raster order inside the rectangle
+            int xq = x1, y = y1, ptype = 0;
+            while (y < y2) {
+                ptype = ec.decodeP(ptype);
+                if (ptype == 0) clr = decode_rgb();
+                int n = ec.decodeN(ptype);
+                if (ec.failed()) return;
+                while (n > 0) {                    // one row piece at a time: later rows may read this one
+                    int m = x2 - xq; if (m > n) m = n; if (m > 32) m = 32;
+                    if (m <= 0) {                  // degenerate rectangle (x2 <= x1): the reference steps one pixel per row
+                        const long i = (long)y * X + xq;
+                        uint32_t v = clr;
+                        if (ptype == 1) v = px_load(dst, i - 1, end); else if (ptype == 2) v = px_load(dst, i - X, end);
+                        else if (ptype == 3) v = px_load(prev, i, end); else if (ptype == 5) v = px_load(dst, i - X - 1, end);
+                        else if (ptype == 4) v = vadd4(px_load(dst, i - 1, end), vsub4(px_load(dst, i - X, end), px_load(dst, i - X - 1, end))) & 0xFFFFFFu;
+                        if (lane == 0 && i >= 0 && i < end) dst[i] = (int32_t)v;
+                        __syncwarp();
+                        clr = v; n--; xq = x1; y++;
+                        continue;
+                    }
+                    const long i = (long)y * X + xq;
+                    const uint32_t left = (ptype == 1 || ptype == 4) ? px_load(dst, i - 1, end) : 0u;
+                    const uint32_t last = sp_segment(dst, prev, i, m, ptype, clr, left, X, end);
+                    if (ptype != 0) clr = last;
+                    n -= m; xq += m;
+                    if (xq >= x2) { xq = x1; y++; }
+                }
+                cx1 = ((int)clr & maskcx1) >> shiftcx1;    // :462-463
+                cx = (int)clr >> shiftcx;
+            }
+        }
+    }
+}
+
+}  // namespace jsp

@@ -191,3 +191,18 @@ entro *entro_rc_new(void)
     r->base.differentConstantsFor16bpp = erc_diff16; r->base.failed = erc_failed;
     return &r->base;
 }
+
+/* Test hook for the model-level known-answer vector G5: a fresh colour context decodes
+ * `value` to the symbol of the same number and then holds cnt[17+v]=401, cnt[v>>4]=416, cnt[16]=656. */
+int ora_kat_rc_fresh_row(const uint8_t *src, int len, int cxi, uint32_t out[3])
+{
+    entro *e = entro_rc_new();
+    entro_rc *r = (entro_rc *)e;
+    e->preinit(e); e->renewI(e);
+    e->decodeBegin(e, src, len, 1);
+    int c = e->decodeClr(e, cxi);
+    const uint32_t *row = r->cntab + (size_t)cxi * CNTABSZ;
+    out[0] = row[17 + c]; out[1] = row[c >> 4]; out[2] = row[16];
+    e->destroy(e);
+    return c;
+}

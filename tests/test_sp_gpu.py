@@ -1,0 +1,131 @@
+"""GPU parity: ScreenPressor decoded by the CUDA path through the C ABI must be bit-exact against the CPU oracle --
+pictures, `changed`, `significant_changes` and error status."""
+import numpy as np
+import pytest
+
+from jsplayer_b200 import synth, BatchDecoder, StreamSpec, ScreenPressor, CodecType, DecoderState, _lib
+from oracle import pyoracle as O
+
+pytestmark = pytest.mark.gpu
+SP = CodecType.codec_screenpressor
+
+
+def gpu_decode(specs, insign=0):
+    bd = BatchDecoder(insignificant_lines=insign, significance=True)
+    bd.configure(specs)
+    outs, flags = bd.decode_host()
+    bd.close()
+    return outs, flags
+
+
+def check(w, h, bpp, frames, keys, insign=0):
+    exp, ch, sg, st = O.decode_stream(O.CODEC_SCREENPRESSOR, w, h, bpp, frames, keys=keys, insignificant_lines=insign)
+    outs, flags = gpu_decode([StreamSpec(SP, w, h, bpp, frames=frames, keys=keys)], insign)
+    for i in range(len(frames)):
+        err = bool(flags[i] & _lib.JSP_FRAME_ERROR)
+        assert err == (st[i] != 0), "error status of frame %d" % i
+        if err and i > 0 and keys[i] == 0:
+            continue                                   # a failed P frame leaves a partial picture
+        if not err:
+            assert (outs[i] == exp[i]).all(), "frame %d differs" % i
+            assert bool(flags[i] & _lib.JSP_FRAME_CHANGED) == bool(ch[i]), "changed flag of frame %d" % i
+            assert bool(flags[i] & _lib.JSP_FRAME_SIGNIFICANT) == bool(sg[i]), "significant flag of frame %d" % i
+
+
+@pytest.mark.parametrize("size", [(64, 48), (33, 17), (16, 16), (20, 9), (320, 240), (250, 130), (1280, 720)])
+def test_v2_iframes_and_pframes(size):
+    w, h = size
+    n = 4 if w >= 1280 else 8
+    frames, keys, pics = synth.sp_stream(w, h, n, seed=w * 31 + h, version=2, change_permille=40)
+    check(w, h, 24, frames, keys)
+    check(w, h, 24, frames, keys, insign=36)
+
+
+def test_v2_gop_16bpp_and_long_stream():
+    w, h = 160, 96
+    frames, keys, pics = synth.sp_stream(w, h, 24, seed=3, version=2, gop=6, change_permille=60)
+    check(w, h, 24, frames, keys, insign=16)
+    frames, keys, pics = synth.sp_stream(w, h, 6, seed=4, version=2, bpp=16)
+    check(w, h, 16, frames, keys)
+
+
+def test_flat_unchanged_and_error_frames():
+    w, h = 64, 32
+    enc = synth.SPEncoder(w, h, 24, 2)
+    p0 = synth.screen(w, h, 1)
+    p1, mv = synth.screen_next(p0, 2, 100)
+    f_i = enc.iframe(p0)
+    f_p = enc.pframe(p1, p0, mv)
+    f_flat = enc.flat(0x123456)
+    flat_pic = np.full((h, w), 0x123456, dtype=np.int32)
+    p2, mv2 = synth.screen_next(flat_pic, 3, 100)
+    f_p2 = enc.pframe(p2, flat_pic, mv2)
+    frames = [f_p, f_flat, f_i, f_p, b"", b"\0", f_flat, f_flat, f_p2, b"\x13abc", b""]
+    keys = [0, 1, 1, 0, 0, 0, 1, 1, 0, 1, 1]
+    check(w, h, 24, frames, keys)
+
+
+def test_truncated_and_garbage_streams():
+    w, h = 96, 64
+    frames, keys, pics = synth.sp_stream(w, h, 3, seed=9, version=2, change_permille=80)
+    rng = np.random.default_rng(4)
+    for cut in (len(frames[0]) // 2, 7, 2):
+        check(w, h, 24, [frames[0][:cut]], [1])
+    check(w, h, 24, [frames[0], frames[1][: len(frames[1]) // 2], frames[2]], [1, 0, 0])
+    garbage = bytes([0x12]) + rng.integers(0, 256, 3000, dtype=np.uint8).tobytes()
+    check(w, h, 24, [garbage], [1])
+    check(w, h, 24, [frames[0], bytes([1]) + rng.integers(0, 256, 500, dtype=np.uint8).tobytes()], [1, 0])
+
+
+def test_many_streams():
+    specs, exp = [], []
+    for s in range(20):
+        w, h = [(64, 48), (320, 240), (100, 60), (640, 360)][s % 4]
+        frames, keys, pics = synth.sp_stream(w, h, 2 + s % 4, seed=100 + s, version=2, change_permille=30)
+        specs.append(StreamSpec(SP, w, h, 24, frames=frames, keys=keys))
+        exp += pics
+    outs, flags = gpu_decode(specs)
+    for i, e in enumerate(exp):
+        assert (outs[i] == e).all(), i
+        assert not (flags[i] & _lib.JSP_FRAME_ERROR)
+
+
+def test_repeated_runs_are_idempotent():
+    w, h = 320, 240
+    frames, keys, pics = synth.sp_stream(w, h, 5, seed=77, version=2)
+    bd = BatchDecoder()
+    bd.configure([StreamSpec(SP, w, h, 24, frames=frames, keys=keys)])
+    bd.upload()
+    for _ in range(3):
+        bd.run()
+    outs, flags = bd.download()
+    bd.close()
+    for i in range(5):
+        assert (outs[i] == pics[i]).all()
+
+
+def test_per_stream_dropin_matches_oracle():
+    w, h = 200, 120
+    frames, keys, pics = synth.sp_stream(w, h, 10, seed=5, version=2, gop=5, change_permille=50)
+    frames.insert(3, b"\0"); keys.insert(3, 0)
+    mine = ScreenPressor(w, h, 24)
+    ora = O.OracleCodec(O.CODEC_SCREENPRESSOR, w, h, 24)
+    mine.Preinit(36); ora.Preinit(36)
+    assert not mine.NeedsIndex()
+    bufs_m = [np.zeros(w * h, dtype=np.int32) for _ in range(3)]
+    bufs_o = [np.zeros(w * h, dtype=np.int32) for _ in range(3)]
+    for i, f in enumerate(frames):
+        assert mine.IsKeyFrame(f) == ora.IsKeyFrame(f) == bool(keys[i])
+        dm = next(b for b in bufs_m if b is not mine.PreviousFrame())
+        do = next(b for b in bufs_o if b is not ora.PreviousFrame())
+        if keys[i]:
+            assert mine.DecompressI(f, dm) == DecoderState.zero_state
+            assert ora.DecompressI(f, do) == 0
+            pm, po, sm, so = mine.PreviousFrame(), ora.PreviousFrame(), False, False
+        else:
+            r = mine.DecompressP(f, dm)
+            po, so = ora.DecompressP(f, do)
+            pm, sm = r.data_pnt, r.significant_changes
+        assert (pm is dm) == (po is do), "frame %d: data_pnt identity" % i
+        assert sm == so, "frame %d: significant_changes" % i
+        assert (pm == po).all(), "frame %d: picture" % i
