@@ -41,6 +41,8 @@ def load():
         lib.jsp_synth_screen.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_void_p]
         lib.jsp_synth_screen_next.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                               C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.jsp_synth_noise.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        lib.jsp_ans_transitions.argtypes = [C.c_void_p, C.c_int]
         _lib = lib
     return _lib
 
@@ -148,3 +150,21 @@ def sp_stream(width, height, n_frames, seed, version=2, gop=0, change_permille=2
             cur = nxt
         pics.append(cur.copy())
     return frames, keys, pics
+
+
+def noise(width, height, seed, ncolors=(2, 4, 12, 40, 100, 256), bits=8):
+    """Noisy picture in vertical bands of ncolors[k]-colour palettes (drives the rANS contexts through all kinds)."""
+    px = np.empty((height, width), dtype=np.int32)
+    nc = np.asarray(ncolors, dtype=np.int32)
+    load().jsp_synth_noise(width, height, int(seed), bits, nc.ctypes.data, int(nc.size), px.ctypes.data)
+    return px
+
+
+ANS_TRANSITIONS = ("4from1", "5from1", "5from4", "6from5", "6from2", "7from3", "7from6", "6grow")
+
+
+def ans_transitions(reset=False):
+    """How often the encoder's rANS colour contexts took each kind transition (coverage of synthetic content)."""
+    out = np.zeros(8, dtype=np.int64)
+    load().jsp_ans_transitions(out.ctypes.data, int(reset))
+    return dict(zip(ANS_TRANSITIONS, (int(v) for v in out)))

@@ -23,18 +23,21 @@ typedef struct {
     uint8_t *bts;
 } sp_enc;
 
-sp_enc *jsp_sp_enc_new(int w, int h, int bpp, int version)
+/* ext: an entropy coder supplied by the caller (the test suite passes its rANS coder for v3/v4), or NULL */
+sp_enc *jsp_sp_enc_new_ext(int w, int h, int bpp, int version, sp_coder *ext)
 {
     sp_enc *e = (sp_enc *)calloc(1, sizeof *e);
     e->X = w; e->Y = h; e->bpp = bpp; e->version = version;
     e->cxshift = (bpp == 16 && version == 2) ? 0 : 2;
     e->maskcx1 = 0xFC00; e->shiftcx1 = 4; e->shiftcx = 18;
     if (bpp == 16 && version == 2) { e->maskcx1 = 0xFF00; e->shiftcx1 = 2; e->shiftcx = 16; }
-    e->ec = version == 2 ? sp_rc_coder_new() : sp_ans_coder_new(version == 3 ? 64 : 32);
+    e->ec = ext ? ext : (version == 2 ? sp_rc_coder_new() : sp_ans_coder_new(version == 3 ? 64 : 32));
     e->bts = (uint8_t *)calloc((size_t)((w + 15) / 16) * ((h + 15) / 16) + 1, 1);
     if (!e->ec) { free(e->bts); free(e); return NULL; }
     return e;
 }
+
+sp_enc *jsp_sp_enc_new(int w, int h, int bpp, int version) { return jsp_sp_enc_new_ext(w, h, bpp, version, NULL); }
 
 void jsp_sp_enc_free(sp_enc *e) { if (!e) return; e->ec->destroy(e->ec); free(e->bts); free(e); }
 
@@ -311,5 +314,20 @@ void jsp_synth_screen_next(int X, int Y, uint64_t seed, int bits, const int32_t 
         if (kind == 0) fill_rect(px, X, Y, x, y, 1 + (int)rng_below(&r, 24), 1 + (int)rng_below(&r, 24), rng_colour(&r, bits));
         else if (kind == 1) text_rect(px, X, Y, x, y, 4 + (int)rng_below(&r, 28), 4 + (int)rng_below(&r, 12), rng_colour(&r, bits), rng_colour(&r, bits), &r);
         else px[(long)y * X + x] = rng_colour(&r, bits);
+    }
+}
+
+/* Pictures that push the rANS colour contexts through all their kinds: vertical bands, band k drawn with random
+ * pixels from a palette of ncolors[k] random colours (few colours -> small contexts, many -> 256-symbol tables). */
+void jsp_synth_noise(int X, int Y, uint64_t seed, int bits, const int *ncolors, int nbands, int32_t *px)
+{
+    rng_t r = { seed * 0x9E3779B97F4A7C15ull + 0x1234567 };
+    int32_t pal[256];
+    for (int k = 0; k < nbands; k++) {
+        int nc = ncolors[k] < 1 ? 1 : (ncolors[k] > 256 ? 256 : ncolors[k]);
+        for (int i = 0; i < nc; i++) pal[i] = rng_colour(&r, bits);
+        const int x0 = (int)((long)X * k / nbands), x1 = (int)((long)X * (k + 1) / nbands);
+        for (int y = 0; y < Y; y++)
+            for (int x = x0; x < x1; x++) px[(long)y * X + x] = pal[rng_below(&r, (uint32_t)nc)];
     }
 }

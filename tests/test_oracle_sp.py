@@ -75,3 +75,65 @@ def test_truncated_stream_reports_error():
     cut = frames[0][: len(frames[0]) // 2]
     out, ch, sg, st = O.decode_stream(O.CODEC_SCREENPRESSOR, w, h, 24, [cut], keys=[1])
     assert st[0] == O.ERROR_OCCURED
+
+
+# ---------------------------------------------------------------- rANS streams (v3 / v4) ----
+def test_kat_g6_fresh_ans_models():
+    """ANS.hx:226-238,831-835 (second equal symbol -> Cx4, freqs [100], d 1) and
+    FixedSizeRansCtx(256).renew() (:128-144): freq 16, cum 16 i, count 8, cntsum 2048, decTable[k] = 8 k."""
+    lib = O.load()
+    out = (C.c_int * 10)()
+    lib.ora_kat_ans(77, out)
+    assert list(out) == [0, 1, 4, 1, 100, 16, 48, 8, 2048, 40]
+
+
+@pytest.mark.parametrize("version", [3, 4])
+@pytest.mark.parametrize("size", [(64, 48), (33, 17), (320, 240)])
+def test_roundtrip_ans(version, size):
+    w, h = size
+    frames, keys, pics = synth.sp_stream(w, h, 8, seed=w * 31 + h, version=version, change_permille=40)
+    assert frames[0][0] == ((version - 1) << 4 | 2)
+    out, ch, sg, st = O.decode_stream(O.CODEC_SCREENPRESSOR, w, h, 24, frames, keys=keys)
+    assert (st == 0).all()
+    for i in range(len(frames)):
+        assert (out[i] == pics[i]).all(), "frame %d" % i
+
+
+def many_symbol_picture(w, h, seed):
+    """Noise bands plus a first band whose red channel walks through 100 distinct values before repeating while
+    green = blue = 0: one colour context meets > 64 distinct symbols before its first repeat (Cx3 -> Cx7)."""
+    px = synth.noise(w, h, seed)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    perm = rng.permutation(256)[:100]
+    seq = np.concatenate([perm, perm, perm])
+    n = min(w * 4, seq.size)
+    px.reshape(-1)[:n] = seq[:n]
+    return px
+
+
+@pytest.mark.parametrize("version", [3, 4])
+def test_roundtrip_ans_all_context_kinds(version):
+    """Content that drives the colour contexts through every kind transition of ANS.hx:785-860."""
+    w, h = 384, 256
+    synth.ans_transitions(reset=True)
+    enc = synth.SPEncoder(w, h, 24, version)
+    px = many_symbol_picture(w, h, 5)
+    f0 = enc.iframe(px)
+    nxt = synth.noise(w, h, 6)
+    nxt[: h // 2] = px[: h // 2]
+    f1 = enc.pframe(nxt, px)
+    tr = synth.ans_transitions()
+    assert all(tr[k] > 0 for k in synth.ANS_TRANSITIONS), tr
+    out, ch, sg, st = O.decode_stream(O.CODEC_SCREENPRESSOR, w, h, 24, [f0, f1], keys=[1, 0])
+    assert (st == 0).all()
+    assert (out[0] == px).all() and (out[1] == nxt).all()
+
+
+def test_ans_state_reload_every_131072_symbols():
+    """EntroCoders.hx:249-253: the decoder re-reads the rANS state every Rans.B symbols."""
+    w, h = 512, 300                                        # > 131072 symbols in one noisy I frame
+    enc = synth.SPEncoder(w, h, 24, 4)
+    px = synth.noise(w, h, 11, ncolors=(3, 9, 30))
+    f0 = enc.iframe(px)
+    out, ch, sg, st = O.decode_stream(O.CODEC_SCREENPRESSOR, w, h, 24, [f0], keys=[1])
+    assert st[0] == 0 and (out[0] == px).all()
