@@ -1,15 +1,18 @@
 #!/usr/bin/env python
-"""bench.py -- BASELINE.json's metric on BASELINE.json's config: decoded Mpixel/s.
+"""bench.py -- BASELINE.json's metric on BASELINE.json's configs: decoded Mpixel/s.
 
-Workload at every N: configs[1] "MSVideo1 16-bit RGB555 1920x1080, 1024-frame batch on 1 B200" per GPU
+Headline workload (every N): configs[1] "MSVideo1 16-bit RGB555 1920x1080, 1024-frame batch on 1 B200" per GPU
 (weak scaling: every rank decodes its own 1024 independent key frames; the path shards by stream with no
 collective).  A step = one decode pass over the whole batch.
 
   value        whole-job Mpixel/s with bitstreams and pictures resident in HBM (CUDA events, max over ranks)
   e2e          the same through jsp_batch_decode_host with pinned HOST buffers (H2D + decode + D2H timed)
-  roofline     msv1_decode kernel: algorithmic bytes / event-timed launch duration vs measured HBM copy peak
+  roofline     dominant kernel: algorithmic bytes / event-timed launch duration vs measured HBM copy peak
   cpu_baseline the CPU oracle (port of the reference decoder) on this box's host cores, bounded sample
+  codecs       (rank 0, N = 1 only, --no-codecs to skip) the same measurement for the ScreenPressor configs:
+               configs[2] "RGB24 1280x720 keyframe-only, 256 streams" and a bounded slice of configs[3]
 
+`--workload c3|c4` makes a ScreenPressor config the timed workload instead (same JSON contract).
 `--impl reference` times the reference's CPU algorithm (the oracle port; the Haxe/JS original cannot run
 here) on all host cores on a bounded sample of the same workload and prints the same JSON line.
 """
@@ -28,22 +31,98 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H = 1920, 1080
-MIX = (25, 50, 25)          # % 1-/2-/8-colour blocks -> 8 B per block on average
-SEED = 0xC0DEC2
-WORKLOAD = "MSVideo1 RGB555 1920x1080 key frames, 25/50/25% 1/2/8-colour blocks, independent streams"
+INSIGN = 36                                       # Manager.hx:61 insignificant_lines
 
 
-def gen_frames(n, rank, threads=16):
-    from jsplayer_b200 import synth
-    synth.load()
+# ------------------------------------------------------------------------------------------ workloads ----
+class Workload:
+    """A list of independent streams (StreamSpec) per rank + how to describe and sample it."""
+    name = ""
+    metric = ""
+    desc = ""
+    dominant = 0                                  # JSP_K_* class whose launches the roofline is quoted on
+    dominant_name = ""
 
-    def one(i):
-        return synth.msv1_frame(False, W, H, SEED + rank * 1000003 + i, mix=MIX)
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        return list(ex.map(one, range(n)))
+    def specs(self, rank, scale):                 # -> list of StreamSpec
+        raise NotImplementedError
 
 
+class C2(Workload):
+    name = "c2"
+    metric = "decoded Mpixel/s (MSVideo1 RGB555 1080p batch)"
+    W, H = 1920, 1080
+    MIX = (25, 50, 25)                            # % 1-/2-/8-colour blocks -> 8 B per block (SURVEY.md 8d, C2)
+    SEED = 0xC0DEC2
+    desc = "MSVideo1 RGB555 1920x1080 key frames, 25/50/25% 1/2/8-colour blocks, independent streams"
+    dominant, dominant_name = 0, "msv1_decode_kernel<false>"
+
+    def __init__(self, frames=1024):
+        self.n = frames
+
+    def frames(self, rank, n=None, threads=16):
+        from jsplayer_b200 import synth
+        synth.load()
+        n = self.n if n is None else n
+
+        def one(i):
+            return synth.msv1_frame(False, self.W, self.H, self.SEED + rank * 1000003 + i, mix=self.MIX)
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            return list(ex.map(one, range(n)))
+
+    def specs(self, rank, n=None):
+        from jsplayer_b200 import StreamSpec, CodecType
+        return [StreamSpec(CodecType.codec_msvc16, self.W, self.H, 16, frames=[f]) for f in self.frames(rank, n)]
+
+    def config(self):
+        return {"workload": self.desc, "frames_per_gpu": self.n, "width": self.W, "height": self.H}
+
+
+class SPWorkload(Workload):
+    """ScreenPressor streams from the screen-content generator.  `distinct` different streams are encoded and
+    repeated round-robin up to `streams` (every copy is decoded independently with its own model state)."""
+    dominant, dominant_name = 2, "sp_rc_decode_kernel"
+
+    def __init__(self, streams, frames_per_stream, width, height, gop, versions, distinct, seed, change_permille, name, metric, desc):
+        self.n, self.fps, self.W, self.H, self.gop = streams, frames_per_stream, width, height, gop
+        self.versions, self.distinct, self.seed, self.change = versions, distinct, seed, change_permille
+        self.name, self.metric, self.desc = name, metric, desc
+
+    def specs(self, rank, n=None):
+        from jsplayer_b200 import StreamSpec, CodecType, synth
+        synth.load()
+        n = self.n if n is None else n
+        k = min(self.distinct, n)
+
+        def one(i):
+            ver = self.versions[i % len(self.versions)]
+            return synth.sp_stream(self.W, self.H, self.fps, seed=self.seed + rank * 7919 + i, version=ver,
+                                   gop=self.gop, change_permille=self.change)[:2]
+        with ThreadPoolExecutor(max_workers=16) as ex:
+            base = list(ex.map(one, range(k)))
+        return [StreamSpec(CodecType.codec_screenpressor, self.W, self.H, 24, frames=base[i % k][0], keys=base[i % k][1])
+                for i in range(n)]
+
+    def config(self):
+        return {"workload": self.desc, "streams_per_gpu": self.n, "frames_per_stream": self.fps, "width": self.W,
+                "height": self.H, "distinct_streams": min(self.distinct, self.n),
+                "stream_versions": ["v%d" % v for v in self.versions]}
+
+
+def make_workload(name, args):
+    if name == "c2":
+        return C2(args.frames)
+    if name == "c3":
+        return SPWorkload(args.streams or 256, 4, 1280, 720, 1, args.sp_versions, 32, 0xC0DEC3, 40, "c3",
+                          "decoded Mpixel/s (ScreenPressor RGB24 720p key frames)",
+                          "ScreenPressor RGB24 1280x720 keyframe-only, 4 I frames per stream, independent synthetic screen-content streams")
+    if name == "c4":
+        return SPWorkload(args.streams or 128, 32, 1920, 1080, 0, args.sp_versions, 16, 0xC0DEC4, 20, "c4",
+                          "decoded Mpixel/s (ScreenPressor 1080p inter-frame streams)",
+                          "ScreenPressor 1920x1080 inter-frame streams (1 I + 31 P, skip/copy-heavy screen content), per-stream entropy decode + wide copy")
+    raise SystemExit("unknown workload " + name)
+
+
+# ------------------------------------------------------------------------------------------ helpers ----
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -104,42 +183,193 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
+def ncu_traffic(kernel_key):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("msv1_decode_bytes_per_launch")
+            return json.load(open(p)).get(kernel_key)
         except Exception:
             return None
     return None
 
 
-def cpu_baseline(frames, threads, budget_s=12.0):
-    """The oracle (CPU port of reference src/MSVideo1.hx) on `threads` host threads, bounded sample."""
+def oracle_descs(specs):
+    """StreamSpec list -> (ctypes array of the oracle's stream descriptors, keep-alive list)."""
+    from oracle import pyoracle as O
+    keep = []
+    descs = (O.StreamDesc * len(specs))()
+    cache = {}
+    for i, sp in enumerate(specs):
+        key = id(sp.frames)
+        if key not in cache:
+            ln = np.array([len(f) for f in sp.frames], dtype=np.uint32)
+            off = np.zeros(len(ln), dtype=np.uint64)
+            if len(ln):
+                off[1:] = np.cumsum(ln.astype(np.uint64))[:-1]
+            blob = np.frombuffer(b"".join(bytes(f) for f in sp.frames) + b"\0", dtype=np.uint8).copy()
+            keys = np.zeros(len(ln), dtype=np.uint8)
+            if sp.keys is None:
+                keys[:1] = 1
+            else:
+                keys[:] = np.asarray(sp.keys, dtype=np.uint8)
+            cache[key] = (blob, off, ln, keys)
+            keep.append(cache[key])
+        blob, off, ln, keys = cache[key]
+        d = descs[i]
+        d.codec, d.width, d.height, d.bpp = int(sp.codec), sp.width, sp.height, sp.bpp
+        d.palette, d.palette_bytes, d.n_frames = None, 0, len(ln)
+        d.bytes, d.frame_off, d.frame_len, d.frame_key, d.out = blob.ctypes.data, off.ctypes.data, ln.ctypes.data, keys.ctypes.data, None
+    return descs, keep
+
+
+def cpu_baseline(specs, threads, budget_s=12.0, min_reps=3):
+    """The oracle (CPU port of the reference decoders) on `threads` host threads over `specs`, bounded sample.
+    Returns (Mpixel/s, seconds per pass, passes)."""
     import ctypes as C
     from oracle import pyoracle as O
     lib = O.load()
-    n = len(frames)
-    ln = np.array([len(f) for f in frames], dtype=np.uint32)
-    blob = np.frombuffer(b"".join(frames), dtype=np.uint8)
-    offs = np.concatenate([[0], np.cumsum(ln.astype(np.uint64))[:-1]]).astype(np.uint64)
-    zero = np.zeros(1, dtype=np.uint64)
-    key = np.ones(1, dtype=np.uint8)
-    descs = (O.StreamDesc * n)()
-    for i in range(n):
-        d = descs[i]
-        d.codec, d.width, d.height, d.bpp = O.CODEC_MSVC16, W, H, 16
-        d.palette, d.palette_bytes, d.n_frames = None, 0, 1
-        d.bytes = blob.ctypes.data + int(offs[i])
-        d.frame_off, d.frame_len, d.frame_key, d.out = zero.ctypes.data, ln[i:].ctypes.data, key.ctypes.data, None
+    descs, keep = oracle_descs(specs)
     px = C.c_uint64(0)
-    lib.ora_decode_streams_mt(descs, n, threads, 36, C.byref(px))       # warm-up
+    lib.ora_decode_streams_mt(descs, len(specs), threads, INSIGN, C.byref(px))       # warm-up
     times, t_start = [], time.perf_counter()
-    while len(times) < 3 or (time.perf_counter() - t_start < budget_s and len(times) < 50):
-        times.append(lib.ora_decode_streams_mt(descs, n, threads, 36, C.byref(px)))
+    while len(times) < min_reps or (time.perf_counter() - t_start < budget_s and len(times) < 50):
+        times.append(lib.ora_decode_streams_mt(descs, len(specs), threads, INSIGN, C.byref(px)))
     t = statistics.median(times)
     return px.value / t / 1e6, t, len(times)
+
+
+def check_against_oracle(bd, specs, outs, which):
+    """Parity gate: pictures of the streams in `which` (all frames) against the CPU oracle."""
+    from oracle import pyoracle as O
+    first = 0
+    firsts = []
+    for sp in specs:
+        firsts.append(first)
+        first += sp.n_frames
+    for s in which:
+        sp = specs[s]
+        exp = O.decode_stream(int(sp.codec), sp.width, sp.height, sp.bpp, list(sp.frames), keys=sp.keys,
+                              insignificant_lines=INSIGN)[0]
+        for f in range(sp.n_frames):
+            if not (outs[firsts[s] + f].reshape(sp.height, sp.width) == exp[f]).all():
+                raise SystemExit("bench: GPU output differs from the oracle (stream %d frame %d)" % (s, f))
+
+
+def sample_size(wl, cores, n_specs):
+    if wl.name == "c2":
+        return max(16, min(n_specs, 2 * cores))
+    return max(8, min(n_specs, cores))
+
+
+def measure(wl, args, rank, local_rank, world, dist, torch, with_e2e=True, with_cpu=True):
+    """Times `wl` on this rank; returns the JSON line (dict) on rank 0, else None."""
+    from jsplayer_b200 import BatchDecoder
+    warmup = max(3, args.warmup)
+    cores = os.cpu_count() or 1
+    specs = wl.specs(rank)
+    bd = BatchDecoder(device=local_rank, insignificant_lines=INSIGN)
+    bd.configure(specs, pinned=True)
+    st = bd.stats()
+    kbytes = bd.kernel_bytes()
+    bd.upload()
+    bd.sync()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity gate on this rank's data before anything is timed ----
+    bd.run(); bd.sync()
+    first_of = np.cumsum([0] + [sp.n_frames for sp in specs])
+    chk = sorted({0, len(specs) - 1})
+    outs = [None] * bd.n_frames
+    for s in chk:
+        for f in range(specs[s].n_frames):
+            outs[first_of[s] + f] = np.empty((specs[s].height, specs[s].width), dtype=np.int32)
+    _, flags = bd.download(outs)
+    if (flags & 4).any():
+        raise SystemExit("bench: %d frames reported a decode error" % int((flags & 4).astype(bool).sum()))
+    check_against_oracle(bd, specs, outs, chk)
+
+    # ---- device-resident timing ----
+    flush = st["in_bytes"] + st["out_bytes"] < (512 << 20)          # small working sets: flush the 126 MB L2 between steps
+    sampler = ClockSampler(local_rank)
+    barrier()
+    bd.time_runs(warmup=warmup, iters=1, flush_l2=flush)
+    barrier()
+    sampler.start()
+    ms_total, kms, kcnt = bd.time_runs(warmup=0, iters=args.steps, flush_l2=flush)
+    barrier()
+    clocks = sampler.stop()
+    t_local = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_local.item()) / args.steps
+    value = st["pixels"] * world / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end: pinned host bitstreams -> H2D -> decode -> D2H pinned host pictures ----
+    e2e = None
+    if with_e2e:
+        outs_p = bd.alloc_outputs(pinned=True)
+        bd.decode_host(outs_p)                       # warm-up (page-touches the pinned output once)
+        barrier()
+        e2e_t = []
+        for _ in range(max(1, args.e2e_steps)):
+            t0 = time.perf_counter()
+            bd.decode_host(outs_p)
+            e2e_t.append(time.perf_counter() - t0)
+        barrier()
+        e_local = torch.tensor([statistics.mean(e2e_t)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e_local, op=dist.ReduceOp.MAX)
+        e2e_s = float(e_local.item())
+        check_against_oracle(bd, specs, outs_p, chk[-1:])
+        e2e = {"value": st["pixels"] * world / e2e_s / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": st["in_bytes"],
+               "d2h_bytes_per_step": st["out_bytes"], "ms_per_step": e2e_s * 1e3, "steps": len(e2e_t)}
+
+    line = None
+    if rank == 0:
+        from jsplayer_b200 import _lib
+        peak, peak_src = hbm_peak()
+        k = wl.dominant
+        if kcnt[k] == 0:                              # e.g. a rANS-only ScreenPressor run
+            k = max(range(len(kcnt)), key=lambda i: kms[i])
+        n_launch = max(1, kcnt[k])
+        k_ms = kms[k] / n_launch                      # average launch duration of the dominant kernel
+        share = kms[k] / max(1e-9, sum(kms))
+        # algorithmic bytes of ONE (average) launch of the dominant kernel (DESIGN.md "Algorithmic bytes")
+        alg_launch = kbytes[k] * args.steps / n_launch
+        achieved = alg_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        cfg = wl.config()
+        cfg.update({"bytes_in_per_gpu": st["in_bytes"], "bytes_out_per_gpu": st["out_bytes"],
+                    "l2": ("inputs+outputs (%.1f GB) far exceed the 126 MB L2; no flush between steps" % ((st["in_bytes"] + st["out_bytes"]) / 1e9))
+                    if not flush else "512 MB memset between steps flushes the 126 MB L2",
+                    "parallelism": "stream-sharded x%d, no collective" % world})
+        line = {
+            "metric": wl.metric, "value": value, "unit": "Mpixel/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": cfg,
+            "gpu_launches": int(sum(kcnt) + 2 * args.steps),
+            "kernels": {_lib.KERNEL_NAMES[i]: {"launches": int(kcnt[i]), "ms": round(kms[i], 4)} for i in range(len(kcnt)) if kcnt[i]},
+            "roofline": {"bound": "hbm", "kernel": _lib.KERNEL_NAMES[k] if wl.name != "c2" else wl.dominant_name,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(_lib.KERNEL_NAMES[k] + "_bytes_per_launch"),
+                         "peak_source": peak_src, "alg_bytes_per_launch": alg_launch, "launch_ms": k_ms,
+                         "share_of_step": share},
+            "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if with_cpu and not args.no_cpu_baseline:
+            n_s = sample_size(wl, cores, len(specs))
+            v, t, reps = cpu_baseline(specs[:n_s], cores)
+            line["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", "cores": cores, "kind": "port",
+                                    "sample": "%d of the %d streams, one stream per thread at a time, median of %d passes (%.2f s each)" % (n_s, len(specs), reps, t)}
+    bd.close()
+    return line
 
 
 def main():
@@ -148,9 +378,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=1024, help="frames (= independent streams) per GPU")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--frames", type=int, default=1024, help="c2: frames (= independent streams) per GPU")
+    ap.add_argument("--streams", type=int, default=0, help="c3/c4: streams per GPU (default 256 / 128)")
+    ap.add_argument("--sp-versions", type=lambda s: [int(x) for x in s.split(",")], default=[2],
+                    help="ScreenPressor stream versions to mix (2 = range coder, 3/4 = rANS)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-codecs", action="store_true", help="skip the per-codec ScreenPressor legs")
     args = ap.parse_args()
     warmup = max(3, args.warmup)
 
@@ -158,26 +393,27 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
+    wl = make_workload(args.workload, args)
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        n_s = max(16, min(args.frames, 2 * cores))
-        frames = gen_frames(n_s, 0)
-        from oracle import pyoracle as O  # noqa: F401
+        n_s = sample_size(wl, cores, 1 << 30)
+        specs = wl.specs(0, n_s)
         per_step = []
         for i in range(warmup + args.steps):
-            v, t, reps = cpu_baseline(frames, cores, budget_s=0.0)
+            v, t, reps = cpu_baseline(specs, cores, budget_s=0.0, min_reps=1)
             if i >= warmup:
                 per_step.append((v, t))
         v = statistics.median([x[0] for x in per_step])
         t = statistics.median([x[1] for x in per_step])
-        line = {"impl": "reference", "metric": "decoded Mpixel/s (MSVideo1 RGB555 1080p batch)", "value": v, "unit": "Mpixel/s",
+        cfg = wl.config()
+        cfg["streams_per_step"] = n_s
+        line = {"impl": "reference", "metric": wl.metric, "value": v, "unit": "Mpixel/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_step": n_s, "width": W, "height": H},
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": v, "unit": "Mpixel/s", "cores": cores, "kind": "port",
-                                 "sample": "%d of the workload's frames per step, one frame per thread at a time, median of %d steps" % (n_s, args.steps)},
+                                 "sample": "%d of the workload's streams per step, one stream per thread at a time, median of %d steps" % (n_s, args.steps)},
                 "e2e": {"value": v, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -189,99 +425,25 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from jsplayer_b200 import BatchDecoder, StreamSpec, CodecType, _lib
+    line = measure(wl, args, rank, local_rank, world, dist, torch)
 
-    frames = gen_frames(args.frames, rank)
-    specs = [StreamSpec(CodecType.codec_msvc16, W, H, 16, frames=[f]) for f in frames]
-    bd = BatchDecoder(device=local_rank, insignificant_lines=36)
-    bd.configure(specs, pinned=True)
-    st = bd.stats()
-    bd.upload()
-    bd.sync()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- parity gate on this rank's data before anything is timed: two frames against the oracle ----
-    from oracle import pyoracle as O
-    bd.run(); bd.sync()
-    outs = [None] * bd.n_frames
-    chk = [0, bd.n_frames - 1]
-    for i in chk:
-        outs[i] = np.empty((H, W), dtype=np.int32)
-    bd.download(outs)
-    for i in chk:
-        exp = O.decode_stream(O.CODEC_MSVC16, W, H, 16, [frames[i]])[0][0]
-        if not (outs[i] == exp).all():
-            raise SystemExit("bench: GPU output differs from the oracle on frame %d" % i)
-
-    # ---- device-resident timing ----
-    sampler = ClockSampler(local_rank)
-    barrier()
-    bd.time_runs(warmup=warmup, iters=1, flush_l2=False)
-    barrier()
-    sampler.start()
-    ms_total, kms, kcnt = bd.time_runs(warmup=0, iters=args.steps, flush_l2=False)
-    barrier()
-    clocks = sampler.stop()
-    t_local = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t_local.item())
-    ms_per_step = ms_total_max / args.steps
-    value = st["pixels"] * world / (ms_per_step * 1e-3) / 1e6
-
-    # ---- end to end: pinned host bitstreams -> H2D -> decode -> D2H pinned host pictures ----
-    outs_p = bd.alloc_outputs(pinned=True)
-    bd.decode_host(outs_p)                       # warm-up (page-touches the pinned output once)
-    barrier()
-    e2e_t = []
-    for _ in range(max(1, args.e2e_steps)):
-        t0 = time.perf_counter()
-        bd.decode_host(outs_p)
-        e2e_t.append(time.perf_counter() - t0)
-    barrier()
-    e_local = torch.tensor([statistics.mean(e2e_t)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e_local, op=dist.ReduceOp.MAX)
-    e2e_s = float(e_local.item())
-    e2e_value = st["pixels"] * world / e2e_s / 1e6
-    exp = O.decode_stream(O.CODEC_MSVC16, W, H, 16, [frames[1]])[0][0]
-    if not (outs_p[1] == exp).all():
-        raise SystemExit("bench: end-to-end output differs from the oracle")
+    # ---- per-codec legs (BASELINE.json's metric is "per codec"): ScreenPressor, rank 0 of a 1-GPU run only ----
+    if rank == 0 and world == 1 and args.workload == "c2" and not args.no_codecs:
+        codecs = {}
+        for name, streams in (("c3", 256), ("c4", 64)):
+            a2 = argparse.Namespace(**vars(args))
+            a2.streams, a2.steps, a2.e2e_steps = streams, min(args.steps, 5), 1
+            try:
+                l2 = measure(make_workload(name, a2), a2, 0, local_rank, 1, dist, torch)
+                codecs[name] = {k: l2[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "kernels", "roofline", "e2e", "cpu_baseline") if k in l2}
+            except (Exception, SystemExit) as e:       # a failed extra leg must not lose the headline line
+                codecs[name] = {"error": str(e)}
+        line["codecs"] = codecs
 
     if rank == 0:
-        peak, peak_src = hbm_peak()
-        n_launch = max(1, kcnt[0])
-        k_ms = kms[0] / n_launch                                  # avg msv1_decode launch duration
-        achieved = st["alg_bytes"] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-        traffic = ncu_traffic()
-        line = {
-            "metric": "decoded Mpixel/s (MSVideo1 RGB555 1080p batch)", "value": value, "unit": "Mpixel/s",
-            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": args.frames, "width": W, "height": H,
-                       "bytes_in_per_gpu": st["in_bytes"], "bytes_out_per_gpu": st["out_bytes"],
-                       "l2": "inputs+outputs (%.1f GB) far exceed the 126 MB L2; no flush between steps" % ((st["in_bytes"] + st["out_bytes"]) / 1e9),
-                       "parallelism": "stream-sharded x%d, no collective" % world},
-            "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": st["in_bytes"], "d2h_bytes_per_step": st["out_bytes"],
-                    "ms_per_step": e2e_s * 1e3, "steps": len(e2e_t)},
-            "gpu_launches": int((kcnt[0] + kcnt[1]) + 2 * args.steps),
-            "roofline": {"bound": "hbm", "kernel": "msv1_decode_kernel<false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "alg_bytes_per_launch": st["alg_bytes"], "launch_ms": k_ms},
-            "clocks": clocks,
-        }
-        if not args.no_cpu_baseline:
-            n_s = max(16, min(args.frames, 2 * cores))
-            v, t, reps = cpu_baseline(frames[:n_s], cores)
-            line["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", "cores": cores, "kind": "port",
-                                    "sample": "%d of the %d frames, one frame per thread at a time, median of %d passes (%.2f s each)" % (n_s, args.frames, reps, t)}
         print(json.dumps(line))
-    bd.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

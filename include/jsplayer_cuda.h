@@ -114,6 +114,10 @@ JSP_API int        jsp_batch_time_runs(jsp_batch *b, int warmup, int iters, int 
 JSP_API int        jsp_batch_stats(jsp_batch *b, uint64_t *pixels, uint64_t *alg_bytes,
                                    uint64_t *in_bytes, uint64_t *out_bytes);
 
+/* bytes[k] (k < JSP_N_KERNELS) = algorithmic bytes kernel class k moves in one jsp_batch_run(): pictures it
+ * writes (and previous pictures it copies) + compressed bytes it reads; intermediates excluded. */
+JSP_API int        jsp_batch_kernel_bytes(jsp_batch *b, uint64_t *bytes);
+
 /* One-shot convenience with the signature SURVEY.md 8b sketches; shards streams longest-first over
  * n_gpus devices of this process (no collectives: GOPs/streams are independent). */
 JSP_API int jsp_batch_decode(const jsp_stream_desc *streams, int n_streams, int n_gpus,

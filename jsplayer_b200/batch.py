@@ -210,5 +210,11 @@ class BatchDecoder:
         self._lib.jsp_batch_stats(self._h, *[C.byref(x) for x in v])
         return dict(pixels=v[0].value, alg_bytes=v[1].value, in_bytes=v[2].value, out_bytes=v[3].value)
 
+    def kernel_bytes(self):
+        """Algorithmic bytes per run of every kernel class (index = JSP_K_*)."""
+        v = (C.c_uint64 * _lib.JSP_N_KERNELS)()
+        self._check(self._lib.jsp_batch_kernel_bytes(self._h, v), "jsp_batch_kernel_bytes")
+        return [int(x) for x in v]
+
     def device_frame_ptr(self, i):
         return int(self._lib.jsp_batch_device_frame(self._h, int(i)))

@@ -100,7 +100,7 @@ static void classify_sp(const StreamRec &S, SpHost &H, FrameRec &R, const uint8_
         H.last_flat = false;
         if ((head & 0xF) != 2) { R.forced = ST_ERROR; return; }              // :157-159
         if (H.version == 0) {
-            if (version != 2) { R.forced = ST_ERROR; return; }               // v3/v4 (rANS): not in this build yet
+            if (version < 2 || version > 4) { R.forced = ST_ERROR; return; } // initEntro: "unknown version of ScreenPressor!" (:74)
             H.version = version;
         }
         R.kind = FK_SP_I; R.sp_flags = SPJ_IFRAME;
@@ -111,6 +111,7 @@ static void classify_sp(const StreamRec &S, SpHost &H, FrameRec &R, const uint8_
         R.kind = FK_SP_P;
     }
     if (H.version == 2 && S.bpp == 16) R.sp_flags |= SPJ_DIFF16 | SPJ_CXSHIFT0;   // :59, :200-202 (v3/v4 force shift 2, :71-73)
+    if (H.version == 3) R.sp_flags |= SPJ_ANS_V3;
 }
 
 struct HostTables {
@@ -177,14 +178,16 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             plan.launches.push_back({JSP_K_MSV1_DECODE, kind, first, (uint32_t)(T.tile_tab.size() - first), 0, (uint32_t)ticket_cursor});
             ticket_cursor++;
         }
-        // ScreenPressor: one warp per frame of this level (after the copies that prepared the pictures)
-        {
+        // ScreenPressor: one warp per frame of this level (after the copies that prepared the pictures),
+        // one launch per entropy coder (range coder v2 / rANS v3, v4)
+        for (int ans = 0; ans < 2; ans++) {
             const size_t first = T.spjobs.size();
             for (int64_t f : by_level[lv]) {
                 FrameRec &R = b->frames[f];
                 if (R.kind != FK_SP_I && R.kind != FK_SP_P && !(R.kind == FK_SP_FLAT && (R.sp_flags & SPJ_RENEW))) continue;
                 const StreamRec &S = b->streams[R.stream];
                 const SpHost &H = b->sp_hosts[R.stream];
+                if ((H.version > 2) != (ans != 0)) continue;
                 SpJob J{};
                 J.src = b->d_bytes + R.d_src; J.len = R.len;
                 J.dst = b->d_out + R.out_off;
@@ -197,7 +200,7 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
                 T.spjobs.push_back(J);
             }
             if (T.spjobs.size() > first)
-                plan.launches.push_back({JSP_K_SP_ENTROPY_RC, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), 0, 0});
+                plan.launches.push_back({ans ? JSP_K_SP_ENTROPY_ANS : JSP_K_SP_ENTROPY_RC, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), 0, 0});
         }
     }
     plan.n_spjobs = T.spjobs.size() - plan.spjob_off;
@@ -295,6 +298,9 @@ static bool run_plan(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *
             break;
         case JSP_K_SP_ENTROPY_RC:
             launch_sp_rc(b->d_spjobs + L.first, L.count, st);
+            break;
+        case JSP_K_SP_ENTROPY_ANS:
+            launch_sp_ans(b->d_spjobs + L.first, L.count, st);
             break;
         default: break;
         }
@@ -408,6 +414,7 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
     int64_t nf = 0;
     bool remainder = false;
     b->stat_pixels = b->stat_alg_bytes = b->stat_in_bytes = b->stat_out_bytes = 0;
+    memset(b->stat_k_bytes, 0, sizeof b->stat_k_bytes);
     for (int s = 0; s < n_streams; s++) {
         const jsp_stream_desc &D = sd[s];
         if (D.width <= 0 || D.height <= 0 || D.n_frames < 0 || (D.n_frames > 0 && (!D.frame_off || !D.frame_len || !D.frame_key))) {
@@ -462,6 +469,16 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
             b->stat_alg_bytes += npix * 4 + R.len + ((R.kind == FK_COPY || R.kind == FK_SP_P) ? npix * 4 : 0);
             b->stat_in_bytes += R.len;
             b->stat_out_bytes += npix * 4;
+            // per kernel class (DESIGN.md "Algorithmic bytes"): what each kernel must move for this frame
+            const int kent = (S.codec == JSP_CODEC_SCREENPRESSOR && b->sp_hosts[s].version > 2) ? JSP_K_SP_ENTROPY_ANS : JSP_K_SP_ENTROPY_RC;
+            switch (R.kind) {
+            case FK_MSV16: case FK_MSV8: b->stat_k_bytes[JSP_K_MSV1_DECODE] += npix * 4 + R.len; break;
+            case FK_COPY:    b->stat_k_bytes[JSP_K_FRAME_COPY] += npix * 8; break;
+            case FK_SP_FLAT: b->stat_k_bytes[JSP_K_FRAME_COPY] += npix * 4; break;
+            case FK_SP_P:    b->stat_k_bytes[JSP_K_FRAME_COPY] += npix * 8; b->stat_k_bytes[kent] += R.len; break;
+            case FK_SP_I:    b->stat_k_bytes[kent] += npix * 4 + R.len; break;
+            default: break;
+            }
         }
         nf += D.n_frames;
         b->streams.push_back(S);
@@ -498,8 +515,9 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
             if (b->streams[s].codec != JSP_CODEC_SCREENPRESSOR) continue;
             any = true;
             SpHost &H = b->sp_hosts[s];
-            H.state_off = st_cur; st_cur += sp_rc_state_bytes();
-            H.rows_off = rows_cur; rows_cur += sp_rc_rows_bytes();
+            const bool ans = H.version > 2;
+            H.state_off = st_cur; st_cur += ans ? sp_ans_state_bytes() : sp_rc_state_bytes();
+            H.rows_off = rows_cur; rows_cur += ((ans ? sp_ans_ctx_bytes() : sp_rc_rows_bytes()) + 255) & ~(size_t)255;
             H.bts_off = bts_cur; bts_cur += ((size_t)((b->streams[s].w + 15) / 16) * ((b->streams[s].h + 15) / 16) + 255) & ~(size_t)255;
         }
         if (any) {
@@ -512,8 +530,11 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
                 if (!JSP_CUDA(cudaMemsetAsync(b->d_sp_rows, 0, rows_cur, b->st_compute))) return -1;
                 if (!JSP_CUDA(cudaMemsetAsync(b->d_sp_state, 0, st_cur, b->st_compute))) return -1;
                 for (int s = 0; s < n_streams; s++)
-                    if (b->streams[s].codec == JSP_CODEC_SCREENPRESSOR)
-                        sp_rc_state_init(b->d_sp_state + b->sp_hosts[s].state_off, b->d_sp_rows + b->sp_hosts[s].rows_off, 1u, b->st_compute);
+                    if (b->streams[s].codec == JSP_CODEC_SCREENPRESSOR) {
+                        const SpHost &H = b->sp_hosts[s];
+                        if (H.version > 2) sp_ans_state_init(b->d_sp_state + H.state_off, b->d_sp_rows + H.rows_off, 1u, b->st_compute);
+                        else sp_rc_state_init(b->d_sp_state + H.state_off, b->d_sp_rows + H.rows_off, 1u, b->st_compute);
+                    }
                 if (!JSP_CUDA(cudaStreamSynchronize(b->st_compute))) return -1;
             }
         }
@@ -678,6 +699,13 @@ int jsp_batch_stats(jsp_batch *b, uint64_t *pixels, uint64_t *alg_bytes, uint64_
     if (alg_bytes) *alg_bytes = b->stat_alg_bytes;
     if (in_bytes) *in_bytes = b->stat_in_bytes;
     if (out_bytes) *out_bytes = b->stat_out_bytes;
+    return 0;
+}
+
+int jsp_batch_kernel_bytes(jsp_batch *b, uint64_t *bytes)
+{
+    if (!b || !bytes) return -1;
+    for (int k = 0; k < JSP_N_KERNELS; k++) bytes[k] = b->stat_k_bytes[k];
     return 0;
 }
 

@@ -36,6 +36,11 @@ size_t sp_rc_state_bytes();
 size_t sp_rc_rows_bytes();
 void sp_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t st);
 void launch_sp_rc(const SpJob *d_jobs, uint32_t n_jobs, cudaStream_t st);
+// sp_ans.cu
+size_t sp_ans_state_bytes();
+size_t sp_ans_ctx_bytes();
+void sp_ans_state_init(void *d_state, void *d_ctx, uint32_t gen0, cudaStream_t st);
+void launch_sp_ans(const SpJob *d_jobs, uint32_t n_jobs, cudaStream_t st);
 
 struct StreamRec {
     int codec, w, h, bpp;
@@ -131,4 +136,5 @@ struct jsp_batch {
     int rerun_count = 0;
 
     uint64_t stat_pixels = 0, stat_alg_bytes = 0, stat_in_bytes = 0, stat_out_bytes = 0;
+    uint64_t stat_k_bytes[JSP_N_KERNELS] = {0};    // algorithmic bytes per run, per kernel class
 };

@@ -1,0 +1,861 @@
+// sp_ans.cu -- ScreenPressor v3 / v4 entropy decode on sm_100a: byte-wise rANS with adaptive context models.
+// Replaces reference src/ANS.hx (whole file) and EntroCoderANS (src/EntroCoders.hx:182-313), one stream per warp.
+//
+//  * rANS state, read position and symbol counter are replicated in every lane; the bitstream is read through a
+//    128-byte shared-memory window refilled by one coalesced warp load;
+//  * the fixed-size adaptive tables (FixedSizeRansCtx, ANS.hx:54-145: ntab 6x256, ptypetab 6x6, xxtab, ntab2, bttab,
+//    sxytab 4x16, mvtab 2x512 -- 21.5 KB) live in shared memory for the whole frame; a lane owns 8 (16) consecutive
+//    symbols in registers, the symbol search is one __ballot_sync over "cumFreq of the next symbol > f" and the
+//    periodic rebuild (:89-102) is a warp-shuffle prefix sum -- no linear scans;
+//  * a colour context (ANS.hx:785-860) is a fixed 64-byte header + 1536-byte body slab in HBM/L2 (12288 per stream).
+//    The context kinds escalate exactly as in the reference: raw symbol lists (Cx1/2/3) -> small sorted tables with
+//    implicit escapes (Cx4/Cx5) -> Cx6 (<= 40 symbols, move-to-front by count) -> full 256-symbol table (Cx7).
+//    One coalesced warp load brings header + the first 512 body bytes (everything but a Cx7); Cx7 runs on the
+//    register path of the fixed tables; the small, branchy kinds are bookkept by lane 0 on the shared-memory copy
+//    ("one lane does the bookkeeping"), the warp writes the slab back coalesced;
+//  * renewI (EntroCoders.hx:216-227) is O(1) for the 12288 contexts: a generation number in the header.
+//
+// JavaScript typed-array semantics (Uint16Array wrap of freqs / cnts, Uint8Array decTable and symbols) are explicit.
+#include "sp_common.cuh"
+#include <cstddef>
+#include <cstring>
+
+namespace jsp {
+
+constexpr int ANS_SCALE = 4096;                    // Rans.PROB_SCALE
+constexpr uint32_t ANS_L = 1u << 23;               // RANS_BYTE_L, ANS.hx:33
+constexpr int ANS_B = 131072;                      // Rans.B, ANS.hx:10
+constexpr int ANS_NCTX = 3 * 4096;
+constexpr int ANS_HDR_BYTES = 64, ANS_BODY_BYTES = 1536;
+enum { CXK_NONE = 0, CXK_1, CXK_2, CXK_3, CXK_4, CXK_5, CXK_6, CXK_7 };
+
+// ---- fixed-size adaptive table: separate arrays instead of the reference's (freq, cumFreq) pairs ----
+template <int N>
+struct FxTab {
+    static constexpr int NP = N < 32 ? 32 : N;
+    static constexpr int K = NP / 32;
+    alignas(16) uint16_t cum[NP];
+    alignas(16) uint16_t fr[NP];
+    alignas(16) uint16_t cnt[NP];
+    uint8_t dec[32];
+    uint32_t cntsum;
+    uint32_t pad[3];
+};
+
+struct AnsSmall {
+    FxTab<256> ntab[6], xxtab, ntab2;
+    FxTab<512> mvtab[2];
+    FxTab<16> sxytab[4];
+    FxTab<6> ptypetab[6];
+    FxTab<5> bttab;
+};
+
+struct alignas(16) CxHdr {
+    uint32_t gen;          // generation the slab belongs to; any other value reads as "no context yet"
+    uint16_t d;            // symbols met
+    uint8_t kind;
+    uint8_t maxpos;        // SmallContext.maxpos
+    uint8_t fshift;        // Cx6.fshift
+    uint8_t S;             // SmallContext.S (4 / 16) or Cx6 slots (32 / 64)
+    uint16_t pad0;
+    uint32_t cntsum;       // Cx5.cntsum | Cx6 cnts[S] (Uint16) | Cx7 cntsum
+    uint8_t dec[32];       // Cx7 decTable
+    uint8_t pad1[16];
+};
+static_assert(sizeof(CxHdr) == ANS_HDR_BYTES, "CxHdr layout");
+
+// body layouts (byte offsets): kinds 1-3 symb[256] @0 | kinds 4/5 symbols[16] @0, freqs u16[16] @16 |
+// kind 6 symbols[64] @0, freq u16[64] @64, cumFreq u16[64] @192, cnts u16[64] @320 |
+// kind 7 cumFreq u16[256] @0, freq u16[256] @512, cnts u16[256] @1024
+constexpr int B_SC_FR = 16, B6_FR = 64, B6_CUM = 192, B6_CNT = 320, B6_BYTES = 448, B7_FR = 512, B7_CNT = 1024;
+
+struct AnsState {                                  // per stream, in HBM
+    AnsSmall small;
+    uint32_t gen;
+    uint32_t pad[3];
+    uint4 *hdrs;                                   // ANS_NCTX * 4 uint4
+    uint4 *bodies;                                 // ANS_NCTX * 96 uint4
+};
+
+struct AnsShared {
+    AnsSmall small;
+    alignas(16) CxHdr hdr;
+    alignas(16) uint8_t body[512];
+    alignas(16) uint8_t big[ANS_BODY_BYTES];       // Cx7 under construction / Cx6 rescale temporaries
+    alignas(16) uint8_t win[128];                  // bitstream window
+    int res_c, res_freq, res_cum, res_wb;          // lane 0 -> warp
+};
+
+struct CxRes { int c, freq, cum; };
+
+// ---- register-resident table ops -------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void ld_u16(const uint16_t *p, uint32_t (&v)[K])
+{
+    if constexpr (K == 1) { v[0] = *p; }
+    else {
+#pragma unroll
+        for (int q = 0; q < K / 8; q++) {
+            const uint4 w = reinterpret_cast<const uint4 *>(p)[q];
+            v[8 * q + 0] = w.x & 0xFFFFu; v[8 * q + 1] = w.x >> 16; v[8 * q + 2] = w.y & 0xFFFFu; v[8 * q + 3] = w.y >> 16;
+            v[8 * q + 4] = w.z & 0xFFFFu; v[8 * q + 5] = w.z >> 16; v[8 * q + 6] = w.w & 0xFFFFu; v[8 * q + 7] = w.w >> 16;
+        }
+    }
+}
+template <int K>
+__device__ __forceinline__ void st_u16(uint16_t *p, const uint32_t (&v)[K])
+{
+    if constexpr (K == 1) { *p = (uint16_t)v[0]; }
+    else {
+#pragma unroll
+        for (int q = 0; q < K / 8; q++)
+            reinterpret_cast<uint4 *>(p)[q] = make_uint4(v[8 * q] | (v[8 * q + 1] << 16), v[8 * q + 2] | (v[8 * q + 3] << 16),
+                                                         v[8 * q + 4] | (v[8 * q + 5] << 16), v[8 * q + 6] | (v[8 * q + 7] << 16));
+    }
+}
+
+// FixedSizeRansCtx.decode + incrCnt (ANS.hx:85-126) on a table whose lane-owned symbols are in registers.
+// dec = the table's decTable (shared memory).  Returns the symbol; freq / cumf = its interval BEFORE the update.
+template <int N, int K>
+__device__ __forceinline__ int fx_core(uint32_t (&cum)[K], uint32_t (&fr)[K], uint32_t (&cnt)[K], uint8_t *dec,
+                                       uint32_t &cntsum, int f, int &freq, int &cumf, bool &rebuilt, int &owner)
+{
+    const int lane = (int)lane_id(), j0 = lane * K;
+    const int c0 = dec[(f >> 7) & 31];
+    const uint32_t nxt = __shfl_down_sync(FULLMASK, cum[0], 1);
+    uint32_t mask = 0;
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+        const int j = j0 + q;
+        const uint32_t cn = q + 1 < K ? cum[(q + 1) % K] : nxt;
+        if (j >= c0 && j < N - 1 && (int)cn > f) mask |= 1u << q;
+    }
+    const uint32_t ball = __ballot_sync(FULLMASK, mask != 0);
+    int c = N - 1;
+    if (ball) {
+        const int lw = __ffs(ball) - 1;
+        const uint32_t m = __shfl_sync(FULLMASK, mask, lw);
+        c = lw * K + __ffs(m) - 1;
+    }
+    owner = c / K;
+    const int qs = c % K;
+    uint32_t sf = 0, sc = 0;
+#pragma unroll
+    for (int q = 0; q < K; q++) if (q == qs) { sf = fr[q]; sc = cum[q]; }
+    freq = (int)__shfl_sync(FULLMASK, sf, owner);
+    cumf = (int)__shfl_sync(FULLMASK, sc, owner);
+    if (lane == owner) {
+#pragma unroll
+        for (int q = 0; q < K; q++) if (q == qs) cnt[q] = (cnt[q] + 16u) & 0xFFFFu;
+    }
+    cntsum += 16;
+    rebuilt = cntsum + 16 > (uint32_t)ANS_SCALE;
+    if (rebuilt) {                                                   // ANS.hx:89-102
+        uint32_t s = 0;
+#pragma unroll
+        for (int q = 0; q < K; q++) if (j0 + q < N) s += cnt[q];
+        uint32_t incl = s;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(FULLMASK, incl, dd); if (lane >= dd) incl += o; }
+        uint32_t cf = incl - s, ns = 0;
+#pragma unroll
+        for (int q = 0; q < K; q++) {
+            const int j = j0 + q;
+            if (j < N) {
+                const uint32_t frq = cnt[q];
+                fr[q] = frq; cum[q] = cf & 0xFFFFu;
+                const int k0 = (int)((cf + 127u) >> 7), k1 = (((int)(cf + frq) - 1) >> 7) + 1;
+                for (int k = k0; k < k1; k++) if (k < 32) dec[k] = (uint8_t)j;
+                cf += frq;
+                cnt[q] = (cnt[q] - (frq >> 1)) & 0xFFFFu;
+                ns += cnt[q];
+            }
+        }
+        cntsum = __reduce_add_sync(FULLMASK, ns);
+        __syncwarp();
+    }
+    return c;
+}
+
+// ---- lane-0 bookkeeping of the small colour-context kinds on the shared-memory copy (ANS.hx:155-704) ----
+namespace cx {
+
+__device__ __forceinline__ uint16_t *u16p(uint8_t *B, int off) { return reinterpret_cast<uint16_t *>(B + off); }
+__device__ __forceinline__ int scale_shift(int tot, int &scaled)      // `while (tot <= PROB_SCALE/2) { tot <<= 1; shift++; }`
+{
+    int shift = 0;
+    while (tot <= ANS_SCALE / 2 && tot > 0) { tot <<= 1; shift++; }
+    scaled = tot;
+    return shift;
+}
+__device__ void insort(uint8_t *a, int n)                             // Sorter.insort, ANS.hx:862-872
+{
+    for (int i = 1; i < n; i++) {
+        int j = i;
+        while (j > 0 && a[j - 1] > a[j]) { const uint8_t t = a[j]; a[j] = a[j - 1]; a[j - 1] = t; j--; }
+    }
+}
+__device__ void fill_dec(uint8_t *dec, int i, int cf, int fr)
+{
+    const int k0 = (cf + 127) >> 7, k1 = ((cf + fr - 1) >> 7) + 1;
+    for (int k = k0; k < k1; k++) if (k >= 0 && k < 32) dec[k] = (uint8_t)i;
+}
+
+// SmallContext.create, :226-238 -- the Cx1 list is in B[0..d)
+__device__ void sc_create(CxHdr &H, uint8_t *B, int S, int c)
+{
+    const int d = H.d;
+    uint16_t *fq = u16p(B, B_SC_FR);
+    insort(B, d);
+    for (int i = d; i < 16; i++) B[i] = 0;
+    H.S = (uint8_t)S; H.maxpos = 0;
+    for (int i = 0; i < 16; i++) fq[i] = 0;
+    for (int i = 0; i < d; i++) {
+        if (B[i] == c) { fq[i] = 100; H.maxpos = (uint8_t)i; } else fq[i] = 50;
+    }
+}
+__device__ void sc_rescale(CxHdr &H, uint8_t *B, int &totFr)          // :254-261
+{
+    uint16_t *fq = u16p(B, B_SC_FR);
+    int s = 256 - H.d;
+    for (int i = 0; i < H.d; i++) { fq[i] = (uint16_t)(fq[i] - (fq[i] >> 1)); s += fq[i]; }
+    totFr = s;
+}
+__device__ bool sc_add(CxHdr &H, uint8_t *B, int pos, int c, int &totFr)   // addSymb, :240-252
+{
+    if (H.d == H.S) return false;
+    uint16_t *fq = u16p(B, B_SC_FR);
+    for (int i = H.d - 1; i >= pos; i--) { B[i + 1] = B[i]; fq[i + 1] = fq[i]; }
+    B[pos] = (uint8_t)c; fq[pos] = 50; H.d++;
+    if (H.maxpos >= pos) H.maxpos++;
+    totFr += 50;
+    if (totFr + 50 > ANS_SCALE) sc_rescale(H, B, totFr);
+    return true;
+}
+// SmallContext.decodeSC, :263-309
+__device__ bool sc_decode(CxHdr &H, uint8_t *B, int someFreq, CxRes &r, int totFr0, int &totFr)
+{
+    uint16_t *fq = u16p(B, B_SC_FR);
+    totFr = totFr0;
+    int tot;
+    const int shift = scale_shift(totFr0, tot);
+    someFreq >>= shift;
+    const int bonus = (ANS_SCALE - tot) >> shift;
+    const int mp = H.maxpos, d = H.d;
+    const uint16_t maxFreq = fq[mp];
+    fq[mp] = (uint16_t)(maxFreq + bonus);
+    int cumFr = 0, lastSymb = 0, pos = 0;
+    while (pos < d) {
+        const int s = B[pos];
+        const int startFr = cumFr + s - lastSymb;
+        if (someFreq < startFr) {
+            r.c = someFreq - cumFr + lastSymb;
+            r.cum = someFreq << shift; r.freq = 1 << shift;
+            fq[mp] = maxFreq;
+            return sc_add(H, B, pos, r.c, totFr);
+        }
+        const int frq = fq[pos];
+        if (startFr + frq > someFreq) {
+            r.c = s;
+            cumFr += s - lastSymb;
+            r.cum = cumFr << shift; r.freq = frq << shift;
+            fq[mp] = maxFreq;
+            fq[pos] = (uint16_t)(fq[pos] + 50); totFr += 50;
+            if (pos != H.maxpos && fq[pos] > fq[H.maxpos]) H.maxpos = (uint8_t)pos;
+            if (totFr + 50 > ANS_SCALE) sc_rescale(H, B, totFr);
+            return true;
+        }
+        cumFr += s - lastSymb + frq;
+        lastSymb = s + 1;
+        pos++;
+    }
+    fq[mp] = maxFreq;
+    r.c = lastSymb + someFreq - cumFr;
+    r.cum = someFreq << shift; r.freq = 1 << shift;
+    return sc_add(H, B, pos, r.c, totFr);
+}
+__device__ void c5_calcsum(CxHdr &H, uint8_t *B)                      // :374-378
+{
+    const uint16_t *fq = u16p(B, B_SC_FR);
+    int t = 256 - H.d;
+    for (int i = 0; i < H.d; i++) t += fq[i];
+    H.cntsum = (uint32_t)t;
+}
+// Cx5.createFrom4, :350-372 (in place)
+__device__ void c5_from4(CxHdr &H, uint8_t *B, int c)
+{
+    uint16_t *fq = u16p(B, B_SC_FR);
+    uint8_t os[4]; uint16_t of[4];
+    const int dd = H.d;
+    for (int i = 0; i < 4; i++) { os[i] = B[i]; of[i] = fq[i]; }
+    for (int i = 0; i < 16; i++) { B[i] = 0; fq[i] = 0; }
+    H.S = 16; H.maxpos = 0;                                           // a new Cx5: maxpos starts at 0 (:223)
+    int i = 0, totFr = 0;
+    while (i < dd && os[i] < c) { B[i] = os[i]; fq[i] = of[i]; totFr += of[i]; i++; }
+    int j = i;
+    B[j] = (uint8_t)c; fq[j] = 50; totFr += 50; j++;
+    while (i < dd) { B[j] = os[i]; fq[j] = of[i]; totFr += of[i]; i++; j++; }
+    H.d = (uint16_t)(dd + 1);
+    if (totFr > ANS_SCALE) { int t; sc_rescale(H, B, t); }
+    c5_calcsum(H, B);
+    H.kind = CXK_5;
+}
+
+// ---- Cx6 ----
+__device__ void c6_init(CxHdr &H, uint8_t *B, int S)
+{
+    H.S = (uint8_t)S;
+    uint32_t *w = reinterpret_cast<uint32_t *>(B);
+    for (int i = 0; i < B6_BYTES / 4; i++) w[i] = 0;
+    H.cntsum = 0;
+}
+__device__ void c6_calcsum(CxHdr &H, uint8_t *B)                      // :571-578
+{
+    const uint16_t *cn = u16p(B, B6_CNT);
+    const int shft = H.fshift > 0 ? H.fshift - 1 : 0;
+    int sum = (256 - H.d) << shft;
+    for (int i = 0; i < H.S; i++) sum += cn[i];
+    H.cntsum = (uint32_t)sum & 0xFFFFu;
+}
+__device__ void c6_rescale(CxHdr &H, uint8_t *B, uint8_t *big)        // rescaleDec, :580-604
+{
+    uint16_t *fr = u16p(B, B6_FR), *cm = u16p(B, B6_CUM), *cn = u16p(B, B6_CNT);
+    uint16_t *_cnts = reinterpret_cast<uint16_t *>(big), *_cum = _cnts + 256;
+    const int sh = H.fshift > 0 ? H.fshift - 1 : 0;
+    const int c0 = 1 << sh, d = H.d;
+    for (int i = 0; i < 256; i++) _cnts[i] = (uint16_t)c0;
+    for (int i = 0; i < d; i++) _cnts[B[i]] = cn[i];
+    int cumFr = 0;
+    for (int i = 0; i < 256; i++) { _cum[i] = (uint16_t)cumFr; cumFr += _cnts[i]; }
+    if (H.fshift > 0) H.fshift--;
+    const int shft = H.fshift > 0 ? H.fshift - 1 : 0;
+    int cntsum = (256 - d) << shft;
+    for (int i = 0; i < d; i++) {
+        cn[i] = (uint16_t)(cn[i] - (cn[i] >> 1));
+        cntsum += cn[i];
+        const int idx = B[i];
+        fr[i] = _cnts[idx]; cm[i] = _cum[idx];
+    }
+    H.cntsum = (uint32_t)cntsum & 0xFFFFu;
+}
+__device__ void c6_incr(CxHdr &H, uint8_t *B, uint8_t *big, int pos)  // incrCntDec, :680-696
+{
+    uint16_t *fr = u16p(B, B6_FR), *cm = u16p(B, B6_CUM), *cn = u16p(B, B6_CNT);
+    const int step = 25 << H.fshift;
+    if (pos >= 0) cn[pos] = (uint16_t)(cn[pos] + step);
+    H.cntsum = (H.cntsum + (uint32_t)step) & 0xFFFFu;
+    if (pos > 0 && cn[pos] > cn[pos - 1]) {
+        const uint16_t tc = cn[pos]; cn[pos] = cn[pos - 1]; cn[pos - 1] = tc;
+        const uint16_t tf = fr[pos]; fr[pos] = fr[pos - 1]; fr[pos - 1] = tf;
+        const uint16_t tm = cm[pos]; cm[pos] = cm[pos - 1]; cm[pos - 1] = tm;
+        const uint8_t ts = B[pos]; B[pos] = B[pos - 1]; B[pos - 1] = ts;
+    }
+    if ((int)H.cntsum + step > ANS_SCALE) c6_rescale(H, B, big);
+}
+// Cx6.createFrom5, :431-505 (in place: B holds the Cx5; c did not fit)
+__device__ void c6_from5(CxHdr &H, uint8_t *B, uint8_t *big, int c)
+{
+    uint8_t *os = big + 1024; uint16_t *of = reinterpret_cast<uint16_t *>(big + 1040);
+    const int oldd = H.d;
+    for (int i = 0; i < 16; i++) { os[i] = B[i]; of[i] = u16p(B, B_SC_FR)[i]; }
+    c6_init(H, B, 32);
+    uint16_t *fr = u16p(B, B6_FR), *cm = u16p(B, B6_CUM), *cn = u16p(B, B6_CNT);
+    int totFr = 256 - oldd;
+    for (int i = 0; i < oldd; i++) totFr += of[i];
+    int tot;
+    const int shift = scale_shift(totFr, tot);
+    int cumFr = 0, lastSymb = 0;
+    for (int pos = 0; pos < oldd; pos++) {
+        const int s = os[pos];
+        cumFr += s - lastSymb;
+        const int cfr = of[pos], f = cfr << shift;
+        fr[pos] = (uint16_t)f; cm[pos] = (uint16_t)(cumFr << shift);
+        cn[pos] = (uint16_t)(f - (f >> 1));
+        B[pos] = (uint8_t)s;
+        cumFr += cfr;
+        lastSymb = s + 1;
+    }
+    H.fshift = (uint8_t)shift;
+    const int fr_freq = 1 << shift; int fr_cum = 0;
+    if (c > 0) {
+        int lowerSym = -1, lfreq = 0, lcum = 0;
+        for (int i = 0; i < oldd; i++) {
+            const int s = B[i];
+            if (s > lowerSym && s < c) { lowerSym = s; lfreq = fr[i]; lcum = cm[i]; }
+        }
+        fr_cum = lfreq > 0 ? lcum + lfreq + ((c - lowerSym - 1) << shift) : (c << shift);
+    }
+    fr[oldd] = (uint16_t)fr_freq; cm[oldd] = (uint16_t)fr_cum;
+    cn[oldd] = (uint16_t)(fr_freq - (fr_freq >> 1));
+    B[oldd] = (uint8_t)c;
+    H.d = (uint16_t)(oldd + 1);
+    const int step = 25 << shift;
+    cn[oldd] = (uint16_t)(cn[oldd] + step);
+    H.cntsum = (H.cntsum + (uint32_t)step) & 0xFFFFu;
+    if ((int)H.cntsum + step > ANS_SCALE) c6_rescale(H, B, big);
+    c6_calcsum(H, B);
+    const int d = H.d;
+    for (int i = 0; i < d - 1; i++)                                   // sort by freqs, descending
+        for (int j = i + 1; j < d; j++) {
+            const uint16_t fj = fr[j], fi = fr[i];
+            if (fj > fi) {
+                const uint16_t cfi = cm[i], cfj = cm[j];
+                fr[i] = fj; cm[i] = cfj; fr[j] = fi; cm[j] = cfi;
+                const uint16_t tc = cn[i]; cn[i] = cn[j]; cn[j] = tc;
+                const uint8_t ts = B[i]; B[i] = B[j]; B[j] = ts;
+            }
+        }
+    H.kind = CXK_6;
+}
+// Cx6.createFrom2, :507-555 (B holds the Cx2 list; c was met the second time)
+__device__ void c6_from2(CxHdr &H, uint8_t *B, uint8_t *big, int c, int f0)
+{
+    const int oldd = H.d;
+    uint8_t *ss = big + 1024;
+    for (int i = 0; i < oldd; i++) ss[i] = B[i];
+    insort(ss, oldd);
+    c6_init(H, B, oldd <= 32 ? 32 : 64);
+    uint16_t *fr = u16p(B, B6_FR), *cm = u16p(B, B6_CUM), *cn = u16p(B, B6_CNT);
+    const int totFr = 256 - oldd + oldd * f0 + f0;
+    int tot;
+    const int shift = scale_shift(totFr, tot);
+    int cumFr = 0, lastSymb = 0, newSymbPos = 0;
+    for (int pos = 0; pos < oldd; pos++) {
+        const int s = ss[pos];
+        cumFr += s - lastSymb;
+        int cfr;
+        if (s == c) { newSymbPos = pos; cfr = f0 * 2; } else cfr = f0;
+        const int f = cfr << shift;
+        fr[pos] = (uint16_t)f; cm[pos] = (uint16_t)(cumFr << shift);
+        B[pos] = (uint8_t)s;
+        cn[pos] = (uint16_t)(f - (f >> 1));
+        cumFr += cfr;
+        lastSymb = s + 1;
+    }
+    H.d = (uint16_t)oldd; H.fshift = (uint8_t)shift;
+    c6_calcsum(H, B);
+    if (newSymbPos > 0) {                                             // put that symbol on the 0th position
+        const uint16_t fr0 = fr[0], cf0 = cm[0], frc = fr[newSymbPos], cfc = cm[newSymbPos];
+        fr[0] = frc; cm[0] = cfc; fr[newSymbPos] = fr0; cm[newSymbPos] = cf0;
+        const uint8_t sym0 = B[0]; const uint16_t cnt0 = cn[0], cntc = cn[newSymbPos];
+        cn[0] = cntc; cn[newSymbPos] = cnt0;
+        B[0] = (uint8_t)c; B[newSymbPos] = sym0;
+    }
+    H.kind = CXK_6;
+}
+__device__ int c6_add(CxHdr &H, uint8_t *B, int c, int freq, int cum)     // addDec, :652-661
+{
+    if (H.d >= 40 || H.d >= H.S) return -1;
+    const int pos = H.d;
+    B[pos] = (uint8_t)c; u16p(B, B6_FR)[pos] = (uint16_t)freq; u16p(B, B6_CUM)[pos] = (uint16_t)cum;
+    u16p(B, B6_CNT)[pos] = (uint16_t)(freq - (freq >> 1));
+    H.d++;
+    return pos;
+}
+// Cx6.decode, :606-650; false = the context must be upgraded to Cx7 (r.c is the symbol)
+__device__ bool c6_decode(CxHdr &H, uint8_t *B, uint8_t *big, int someFreq, CxRes &r)
+{
+    const uint16_t *fr = u16p(B, B6_FR), *cm = u16p(B, B6_CUM);
+    int lfreq = 0, lcum = 0, lowerSym = 0;
+    const int d = H.d;
+    for (int i = 0; i < d; i++) {
+        const int cf = cm[i];
+        if (cf <= someFreq) {
+            const int f = fr[i];
+            if (cf + f > someFreq) { r.c = B[i]; r.freq = f; r.cum = cf; c6_incr(H, B, big, i); return true; }
+            if (cf >= lcum) { lfreq = f; lcum = cf; lowerSym = B[i]; }
+        }
+    }
+    const int fr_freq = 1 << H.fshift; int fr_cum, c;
+    if (lfreq > 0) {
+        const int cumFr = lcum + lfreq;
+        const int xx = (someFreq - cumFr) >> H.fshift;
+        c = xx + lowerSym + 1;
+        fr_cum = lcum + lfreq + (xx << H.fshift);
+    } else { c = someFreq >> H.fshift; fr_cum = c << H.fshift; }
+    r.freq = fr_freq; r.cum = fr_cum; r.c = c;
+    int p = c6_add(H, B, c, fr_freq, fr_cum);
+    if (p < 0) {
+        if (H.S == 64) return false;
+        H.S = 64;                                                     // growDec, :663-678 (slots 32..63 are already zero)
+        p = c6_add(H, B, c, fr_freq, fr_cum);
+        if (p < 0) return false;
+    }
+    c6_incr(H, B, big, p);
+    return true;
+}
+
+// ---- Cx7 under construction in `big` (cumFreq @0, freq @512, cnts @1024), decTable in the header ----
+__device__ void c7_from3(CxHdr &H, uint8_t *B, uint8_t *big, int c)   // :711-739
+{
+    uint16_t *cm = reinterpret_cast<uint16_t *>(big), *fr = cm + 256, *cn = cm + 512;
+    for (int i = 0; i < 256; i++) { fr[i] = 1; cn[i] = 1; }
+    const int d = H.d;
+    const int f0 = (ANS_SCALE - (256 - d)) / (d + 1);
+    const int c0 = f0 - (f0 >> 1);
+    for (int i = 0; i < d; i++) { const int s = B[i]; fr[s] = (uint16_t)f0; cn[s] = (uint16_t)c0; }
+    fr[c] = (uint16_t)(fr[c] + f0);
+    cn[c] = (uint16_t)(cn[c] + 16);
+    for (int k = 0; k < 32; k++) H.dec[k] = 0;
+    int cntsum = 0, cf = 0;
+    for (int i = 0; i < 256; i++) {
+        cntsum += cn[i];
+        cm[i] = (uint16_t)cf;
+        const int f = fr[i];
+        fill_dec(H.dec, i, cf, f);
+        cf += f;
+    }
+    H.cntsum = (uint32_t)cntsum;
+    H.kind = CXK_7;
+}
+__device__ void c7_from6(CxHdr &H, uint8_t *B, uint8_t *big)          // :741-771
+{
+    uint16_t *cm = reinterpret_cast<uint16_t *>(big), *fr = cm + 256, *cn = cm + 512;
+    const uint16_t *fr6 = u16p(B, B6_FR), *cm6 = u16p(B, B6_CUM), *cn6 = u16p(B, B6_CNT);
+    for (int i = 0; i < 256; i++) { cm[i] = 0; fr[i] = 0; cn[i] = 0; }
+    for (int k = 0; k < 32; k++) H.dec[k] = 0;
+    const int S = H.S;
+    for (int i = 0; i < S; i++) if (cn6[i] > 0) {
+        const int s = B[i];
+        fr[s] = fr6[i]; cm[s] = cm6[i]; cn[s] = cn6[i];
+    }
+    const int funmet = 1 << H.fshift, cntUnmet = funmet - (funmet >> 1);
+    int cumFr = 0;
+    for (int i = 0; i < 256; i++) {
+        int f;
+        if (fr[i] > 0) f = fr[i];
+        else { fr[i] = (uint16_t)funmet; cm[i] = (uint16_t)cumFr; cn[i] = (uint16_t)cntUnmet; f = funmet; }
+        fill_dec(H.dec, i, cumFr, f);
+        cumFr += f;
+    }
+    // cntsum = c6.cnts[S] is already in the header
+    H.kind = CXK_7;
+}
+
+enum { FOUND, ADDED, NOROOM };
+__device__ int find_or_add(CxHdr &H, uint8_t *B, int c, int cap)      // SymbList.findOrAdd, :163-171
+{
+    const int d = H.d;
+    for (int i = 0; i < d; i++) if (B[i] == c) return FOUND;
+    if (d < cap) { B[d] = (uint8_t)c; H.d++; return ADDED; }
+    return NOROOM;
+}
+
+// Context.decode for kinds 4-6 (ANS.hx:795-810). Returns the number of body bytes to write back, or -1 when a
+// Cx7 was built in `big`.
+__device__ __noinline__ int decode_small(CxHdr &H, uint8_t *B, uint8_t *big, int someFreq, CxRes &r)
+{
+    int tf;
+    switch (H.kind) {
+    case CXK_4: {
+        const uint16_t *fq = u16p(B, B_SC_FR);
+        const int tot = fq[0] + fq[1] + fq[2] + fq[3] + 256 - H.d;    // :320
+        if (!sc_decode(H, B, someFreq, r, tot, tf)) { c5_from4(H, B, r.c); }
+        return 48;
+    }
+    case CXK_5: {
+        const bool ok = sc_decode(H, B, someFreq, r, (int)H.cntsum, tf);
+        H.cntsum = (uint32_t)tf;
+        if (!ok) { c6_from5(H, B, big, r.c); return B6_BYTES; }
+        return 48;
+    }
+    default:                                                          // CXK_6
+        if (!c6_decode(H, B, big, someFreq, r)) { c7_from6(H, B, big); return -1; }
+        return B6_BYTES;
+    }
+}
+
+// Context.update for kinds None-3 after a raw symbol (ANS.hx:812-859). Same return convention.
+__device__ __noinline__ int update_raw(CxHdr &H, uint8_t *B, uint8_t *big, int c, int f0, uint32_t gen)
+{
+    int kind = H.gen == gen ? H.kind : CXK_NONE;
+    switch (kind) {
+    case CXK_NONE:
+        H.gen = gen; H.kind = CXK_1; H.d = 1; H.maxpos = 0; H.fshift = 0; H.S = 0; H.cntsum = 0;
+        B[0] = (uint8_t)c;
+        return 16;
+    case CXK_1:
+        switch (find_or_add(H, B, c, 14)) {
+        case FOUND:
+            if (H.d <= 4) { sc_create(H, B, 4, c); H.kind = CXK_4; }
+            else { sc_create(H, B, 16, c); c5_calcsum(H, B); H.kind = CXK_5; }     // Cx5.fromCx1, :337-342
+            return 48;
+        case NOROOM: B[H.d] = (uint8_t)c; H.d++; H.kind = CXK_2; return 16;          // new Cx2(c1, c), :188-197
+        default: return 16;
+        }
+    case CXK_2:
+        switch (find_or_add(H, B, c, 64)) {
+        case FOUND: c6_from2(H, B, big, c, f0); return B6_BYTES;
+        case NOROOM: B[H.d] = (uint8_t)c; H.d++; H.kind = CXK_3; return 80;          // new Cx3(c2, c), :199-208
+        default: return 64;
+        }
+    default:                                                          // CXK_3
+        if (find_or_add(H, B, c, 256) == FOUND) { c7_from3(H, B, big, c); return -1; }
+        return 256;
+    }
+}
+
+}  // namespace cx
+
+struct AnsCoder {
+    static constexpr bool kCanDecodeBool = true;                      // EntroCoders.hx:257
+    AnsShared *sm;
+    uint4 *hdrs, *bodies;
+    uint32_t gen;
+    int f0;
+    uint32_t x;                                                       // rANS state (low 32 bits; ANS.hx:6)
+    const uint8_t *data;
+    uint32_t len, pos, wbase;
+    int nDec;
+    bool overrun, fail;
+
+    __device__ __forceinline__ bool failed() const { return fail; }
+
+    __device__ __forceinline__ uint32_t rbyte()                       // data[pos++]; out of bounds reads as 0 after `|`
+    {
+        uint32_t b = 0;
+        if (pos < len) {
+            if (pos - wbase >= 128u) {
+                __syncwarp();
+                wbase = pos & ~127u;
+                const int lane = (int)lane_id();
+                uint32_t w = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t p = wbase + 4u * lane + k;
+                    if (p < len) w |= (uint32_t)__ldg(data + p) << (8 * k);
+                }
+                reinterpret_cast<uint32_t *>(sm->win)[lane] = w;
+                __syncwarp();
+            }
+            b = sm->win[pos - wbase];
+        } else overrun = true;
+        pos++;
+        return b;
+    }
+    __device__ void reinit(uint32_t i)                                // Rans.reinitImpl, ANS.hx:22-31
+    {
+        pos = i;
+        uint32_t v = rbyte();
+        v |= rbyte() << 8; v |= rbyte() << 16; v |= rbyte() << 24;
+        x = v;
+    }
+    __device__ void decodeBegin(const uint8_t *src, uint32_t n, uint32_t pos0)   // EntroCoders.hx:229-233
+    {
+        data = src; len = n; overrun = false; wbase = 0x80000000u;
+        reinit(pos0);
+        nDec = 0;
+    }
+    __device__ __forceinline__ int get() { if (overrun) fail = true; return (int)(x & 4095u); }   // decGet, ANS.hx:35
+    __device__ __forceinline__ void advance(int start, int freq)      // decAdvance, ANS.hx:37-44
+    {
+        const int32_t r = (int32_t)x;
+        long long v = (long long)freq * (r >> 12) + (r & 4095) - start;
+        int guard = 0;
+        while (v < (long long)ANS_L) {
+            if (overrun || ++guard > 8) { fail = true; break; }
+            v = (int32_t)(((uint32_t)v << 8) | rbyte());
+        }
+        x = (uint32_t)v;
+    }
+    __device__ __forceinline__ void count()                           // EntroCoders.hx:249-253
+    {
+        nDec++;
+        if (nDec == ANS_B) { reinit(pos); nDec = 0; }
+    }
+
+    template <int N>
+    __device__ void fx_renew(FxTab<N> &t)                             // FixedSizeRansCtx.renew, ANS.hx:128-144
+    {
+        const int lane = (int)lane_id();
+        const int fr = ANS_SCALE / N, c0 = fr - (fr >> 1);
+        for (int i = lane; i < FxTab<N>::NP; i += 32) {
+            t.cum[i] = i < N ? (uint16_t)(i * fr) : 0; t.fr[i] = i < N ? (uint16_t)fr : 0; t.cnt[i] = i < N ? (uint16_t)c0 : 0;
+        }
+        const int i = (lane * 128) / fr;                              // the symbol whose interval holds 128 * lane
+        if (i < N) t.dec[lane] = (uint8_t)i;
+        if (lane == 0) t.cntsum = (uint32_t)(c0 * N);
+    }
+    __device__ void renewI()                                          // EntroCoders.hx:216-227
+    {
+        gen = gen + 1;
+        AnsSmall &s = sm->small;
+        for (int i = 0; i < 6; i++) { fx_renew(s.ntab[i]); fx_renew(s.ptypetab[i]); }
+        fx_renew(s.xxtab); fx_renew(s.ntab2); fx_renew(s.bttab);
+        for (int i = 0; i < 4; i++) fx_renew(s.sxytab[i]);
+        fx_renew(s.mvtab[0]); fx_renew(s.mvtab[1]);
+        __syncwarp();
+    }
+
+    template <int N>
+    __device__ int decodeF(FxTab<N> &t)                               // decodeF, EntroCoders.hx:271-280
+    {
+        constexpr int K = FxTab<N>::K;
+        const int lane = (int)lane_id();
+        uint32_t cum[K], fr[K], cnt[K];
+        ld_u16<K>(t.cum + lane * K, cum); ld_u16<K>(t.fr + lane * K, fr); ld_u16<K>(t.cnt + lane * K, cnt);
+        uint32_t cntsum = t.cntsum;
+        int freq, cumf, owner; bool rebuilt;
+        const int f = get();
+        const int c = fx_core<N, K>(cum, fr, cnt, t.dec, cntsum, f, freq, cumf, rebuilt, owner);
+        if (rebuilt) { st_u16<K>(t.cum + lane * K, cum); st_u16<K>(t.fr + lane * K, fr); st_u16<K>(t.cnt + lane * K, cnt); }
+        else if (lane == owner) st_u16<K>(t.cnt + lane * K, cnt);
+        if (lane == 0) t.cntsum = cntsum;
+        __syncwarp();
+        advance(cumf, freq);
+        count();
+        return c;
+    }
+
+    __device__ int decodeClr(int cxi)                                 // EntroCoders.hx:235-255
+    {
+        const int lane = (int)lane_id();
+        uint4 *gh = hdrs + (size_t)cxi * (ANS_HDR_BYTES / 16);
+        uint4 *gb = bodies + (size_t)cxi * (ANS_BODY_BYTES / 16);
+        const uint4 bv = gb[lane];
+        uint4 hv = make_uint4(0, 0, 0, 0);
+        if (lane < 4) hv = gh[lane];
+        const int f = get();
+        uint4 *sh4 = reinterpret_cast<uint4 *>(&sm->hdr), *sb4 = reinterpret_cast<uint4 *>(sm->body);
+        sb4[lane] = bv;
+        if (lane < 4) sh4[lane] = hv;
+        __syncwarp();
+        CxHdr &H = sm->hdr;
+        const int kind = H.gen == gen ? H.kind : CXK_NONE;
+        int c;
+        if (kind == CXK_7) {                                          // Cx7 = FixedSizeRansCtx(256), register path
+            uint32_t cum[8], fr[8], cnt[8];
+            {
+                uint32_t t[8];
+                const uint4 fv = gb[32 + lane], cv = gb[64 + lane];
+                auto unpack = [&](const uint4 &w, uint32_t (&o)[8]) {
+                    o[0] = w.x & 0xFFFFu; o[1] = w.x >> 16; o[2] = w.y & 0xFFFFu; o[3] = w.y >> 16;
+                    o[4] = w.z & 0xFFFFu; o[5] = w.z >> 16; o[6] = w.w & 0xFFFFu; o[7] = w.w >> 16;
+                };
+                unpack(bv, cum); unpack(fv, fr); unpack(cv, cnt);
+                (void)t;
+            }
+            uint32_t cntsum = H.cntsum;
+            int freq, cumf, owner; bool rebuilt;
+            c = fx_core<256, 8>(cum, fr, cnt, H.dec, cntsum, f, freq, cumf, rebuilt, owner);
+            auto pack = [&](const uint32_t (&v)[8]) {
+                return make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+            };
+            if (rebuilt) { gb[lane] = pack(cum); gb[32 + lane] = pack(fr); gb[64 + lane] = pack(cnt); }
+            else if (lane == owner) gb[64 + lane] = pack(cnt);
+            if (lane == 0) H.cntsum = cntsum;
+            __syncwarp();
+            if (lane < (rebuilt ? 4 : 1)) gh[lane] = sh4[lane];
+            __syncwarp();
+            advance(cumf, freq);
+        } else {
+            int wb;
+            if (kind >= CXK_4) {
+                if (lane == 0) {
+                    CxRes r; r.c = 0; r.freq = 1; r.cum = 0;
+                    sm->res_wb = cx::decode_small(H, sm->body, sm->big, f, r);
+                    sm->res_c = r.c; sm->res_freq = r.freq; sm->res_cum = r.cum;
+                }
+                __syncwarp();
+                c = sm->res_c; wb = sm->res_wb;
+                const int freq = sm->res_freq, cumf = sm->res_cum;
+                advance(cumf, freq);
+                if (c > 255) { fail = true; c &= 255; }               // escape interval past symbol 255: not a valid stream
+            } else {
+                c = (int)rbyte();                                     // Rans.raw, ANS.hx:46-48
+                if (lane == 0) sm->res_wb = cx::update_raw(H, sm->body, sm->big, c, f0, gen);
+                __syncwarp();
+                wb = sm->res_wb;
+            }
+            // write the slab back: header always, the live part of the body (or the freshly built Cx7)
+            if (wb < 0) {
+                const uint4 *big4 = reinterpret_cast<const uint4 *>(sm->big);
+                gb[lane] = big4[lane]; gb[32 + lane] = big4[32 + lane]; gb[64 + lane] = big4[64 + lane];
+            } else if (lane * 16 < wb) gb[lane] = sb4[lane];
+            if (lane < 4) gh[lane] = sh4[lane];
+            __syncwarp();
+        }
+        count();
+        return c;
+    }
+
+    __device__ bool decodeBool()                                      // EntroCoders.hx:259-269
+    {
+        const int f = get();
+        const bool flag = f >= (ANS_SCALE >> 1);
+        advance(flag ? ANS_SCALE >> 1 : 0, ANS_SCALE >> 1);
+        count();
+        return flag;
+    }
+    __device__ int decodeN(int ptype) { return decodeF(sm->small.ntab[ptype]); }
+    __device__ int decodeP(int ptype) { return decodeF(sm->small.ptypetab[ptype]); }
+    __device__ int decodeX() { return decodeF(sm->small.xxtab); }
+    __device__ int decodeBT() { return decodeF(sm->small.bttab); }
+    __device__ int decodeBN() { return decodeF(sm->small.ntab2); }
+    __device__ int decodeSXY(int n) { return decodeF(sm->small.sxytab[n]); }
+    __device__ int decodeMX() { return decodeF(sm->small.mvtab[0]); }
+    __device__ int decodeMY() { return decodeF(sm->small.mvtab[1]); }
+};
+
+namespace {
+
+__global__ void __launch_bounds__(32)
+sp_ans_decode_kernel(const SpJob *__restrict__ jobs)
+{
+    __shared__ AnsShared sm;
+    const SpJob J = jobs[blockIdx.x];
+    AnsState *st = reinterpret_cast<AnsState *>(J.state);
+    const int lane = (int)lane_id();
+    AnsCoder ec;
+    ec.sm = &sm; ec.hdrs = st->hdrs; ec.bodies = st->bodies; ec.gen = st->gen;
+    ec.f0 = (J.flags & SPJ_ANS_V3) ? 64 : 32;                         // Cx6.f0, EntroCoders.hx:210 / ScreenPressor.hx:69-72
+    ec.fail = false; ec.overrun = false; ec.x = 0; ec.data = J.src; ec.len = J.len; ec.pos = 0; ec.wbase = 0x80000000u; ec.nDec = 0;
+    {
+        const uint4 *g = reinterpret_cast<const uint4 *>(&st->small);
+        uint4 *s = reinterpret_cast<uint4 *>(&sm.small);
+        for (int i = lane; i < (int)(sizeof(AnsSmall) / 16); i += 32) s[i] = g[i];
+    }
+    __syncwarp();
+    uint32_t bits = 0;
+    if (J.flags & SPJ_RENEW) {
+        ec.renewI();
+    } else if (J.flags & SPJ_IFRAME) {
+        sp_decode_iframe(ec, J);
+        bits |= ST_CHANGED;
+    } else {
+        sp_decode_pframe(ec, J, bits);
+    }
+    if (ec.failed()) bits |= ST_ERROR;
+    __syncwarp();
+    {
+        uint4 *g = reinterpret_cast<uint4 *>(&st->small);
+        const uint4 *s = reinterpret_cast<const uint4 *>(&sm.small);
+        for (int i = lane; i < (int)(sizeof(AnsSmall) / 16); i += 32) g[i] = s[i];
+    }
+    if (lane == 0) { st->gen = ec.gen; if (bits) atomicOr(J.status, bits); }
+}
+
+}  // namespace
+
+size_t sp_ans_state_bytes() { return (sizeof(AnsState) + 255) & ~(size_t)255; }
+size_t sp_ans_ctx_bytes() { return (size_t)ANS_NCTX * (ANS_HDR_BYTES + ANS_BODY_BYTES); }
+
+// host-side init of one stream's state: generation gen0 (headers are zeroed: generation 0 = "no context")
+void sp_ans_state_init(void *d_state, void *d_ctx, uint32_t gen0, cudaStream_t st)
+{
+    struct { uint32_t gen; uint32_t pad[3]; uint4 *hdrs; uint4 *bodies; } h;
+    memset(&h, 0, sizeof h);
+    h.gen = gen0;
+    h.hdrs = reinterpret_cast<uint4 *>(d_ctx);
+    h.bodies = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(d_ctx) + (size_t)ANS_NCTX * ANS_HDR_BYTES);
+    static_assert(sizeof(h) == sizeof(AnsState) - offsetof(AnsState, gen), "AnsState tail layout");
+    cudaStreamSynchronize(st);
+    cudaMemcpy(reinterpret_cast<char *>(d_state) + offsetof(AnsState, gen), &h, sizeof h, cudaMemcpyHostToDevice);
+}
+
+void launch_sp_ans(const SpJob *d_jobs, uint32_t n_jobs, cudaStream_t st)
+{
+    if (n_jobs) sp_ans_decode_kernel<<<n_jobs, 32, 0, st>>>(d_jobs);
+}
+
+}  // namespace jsp

@@ -77,6 +77,7 @@ static void ea_begin(entro *e, const uint8_t *src, int len, int pos0)   /* :229-
 {
     entro_ans *a = (entro_ans *)e;
     a->rans.data = src; a->rans.len = len; a->rans.overrun = 0;
+    a->rans.failed = 0;                                   /* the failure report is per frame */
     rans_init(&a->rans, pos0);
     a->nDec = 0;
 }
@@ -93,6 +94,9 @@ static int ea_clr(entro *e, int cxi)                       /* :235-255 */
     if (cctx_decode(dcx, rans_get(&a->rans), &rcv, a->f0)) {
         c = rcv.c;
         rans_advance(&a->rans, rcv.cumFreq, rcv.freq);
+        /* defined behaviour: an escape interval past symbol 255 (impossible on a valid stream; the reference would
+         * index cntab[] out of range on the next symbol and throw) is a failure and the symbol wraps to a byte */
+        if (c > 255) { a->rans.failed = 1; c &= 255; }
     } else {
         c = rans_byte(&a->rans);                           /* Rans.raw, ANS.hx:46-48 */
         cctx_update(dcx, c, a->f0);

@@ -35,6 +35,7 @@ static inline void rc_byte(rangecoder *rc)
 static void rc_begin(rangecoder *rc, const uint8_t *src, int len, int pos0)
 {
     rc->code = 0; rc->range = 0xFFFFFFFFu; rc->data = src; rc->len = len; rc->poisoned = 0;
+    rc->failed = 0;                                       /* the failure report is per frame */
     rc->pos = pos0 + 1;
     rc_byte(rc); rc_byte(rc); rc_byte(rc); rc_byte(rc);
     /* pos is now pos0 + 5 */

@@ -32,11 +32,12 @@ def check(w, h, bpp, frames, keys, insign=0):
             assert bool(flags[i] & _lib.JSP_FRAME_SIGNIFICANT) == bool(sg[i]), "significant flag of frame %d" % i
 
 
+@pytest.mark.parametrize("version", [2, 3, 4])
 @pytest.mark.parametrize("size", [(64, 48), (33, 17), (16, 16), (20, 9), (320, 240), (250, 130), (1280, 720)])
-def test_v2_iframes_and_pframes(size):
+def test_iframes_and_pframes(size, version):
     w, h = size
     n = 4 if w >= 1280 else 8
-    frames, keys, pics = synth.sp_stream(w, h, n, seed=w * 31 + h, version=2, change_permille=40)
+    frames, keys, pics = synth.sp_stream(w, h, n, seed=w * 31 + h, version=version, change_permille=40)
     check(w, h, 24, frames, keys)
     check(w, h, 24, frames, keys, insign=36)
 
@@ -65,14 +66,15 @@ def test_flat_unchanged_and_error_frames():
     check(w, h, 24, frames, keys)
 
 
-def test_truncated_and_garbage_streams():
+@pytest.mark.parametrize("version", [2, 4])
+def test_truncated_and_garbage_streams(version):
     w, h = 96, 64
-    frames, keys, pics = synth.sp_stream(w, h, 3, seed=9, version=2, change_permille=80)
+    frames, keys, pics = synth.sp_stream(w, h, 3, seed=9, version=version, change_permille=80)
     rng = np.random.default_rng(4)
     for cut in (len(frames[0]) // 2, 7, 2):
         check(w, h, 24, [frames[0][:cut]], [1])
     check(w, h, 24, [frames[0], frames[1][: len(frames[1]) // 2], frames[2]], [1, 0, 0])
-    garbage = bytes([0x12]) + rng.integers(0, 256, 3000, dtype=np.uint8).tobytes()
+    garbage = bytes([0x02 | (version - 1) << 4]) + rng.integers(0, 256, 3000, dtype=np.uint8).tobytes()
     check(w, h, 24, [garbage], [1])
     check(w, h, 24, [frames[0], bytes([1]) + rng.integers(0, 256, 500, dtype=np.uint8).tobytes()], [1, 0])
 
@@ -81,7 +83,7 @@ def test_many_streams():
     specs, exp = [], []
     for s in range(20):
         w, h = [(64, 48), (320, 240), (100, 60), (640, 360)][s % 4]
-        frames, keys, pics = synth.sp_stream(w, h, 2 + s % 4, seed=100 + s, version=2, change_permille=30)
+        frames, keys, pics = synth.sp_stream(w, h, 2 + s % 4, seed=100 + s, version=2 + s % 3, change_permille=30)
         specs.append(StreamSpec(SP, w, h, 24, frames=frames, keys=keys))
         exp += pics
     outs, flags = gpu_decode(specs)
@@ -90,9 +92,10 @@ def test_many_streams():
         assert not (flags[i] & _lib.JSP_FRAME_ERROR)
 
 
-def test_repeated_runs_are_idempotent():
+@pytest.mark.parametrize("version", [2, 3])
+def test_repeated_runs_are_idempotent(version):
     w, h = 320, 240
-    frames, keys, pics = synth.sp_stream(w, h, 5, seed=77, version=2)
+    frames, keys, pics = synth.sp_stream(w, h, 5, seed=77, version=version)
     bd = BatchDecoder()
     bd.configure([StreamSpec(SP, w, h, 24, frames=frames, keys=keys)])
     bd.upload()
@@ -104,9 +107,10 @@ def test_repeated_runs_are_idempotent():
         assert (outs[i] == pics[i]).all()
 
 
-def test_per_stream_dropin_matches_oracle():
+@pytest.mark.parametrize("version", [2, 4])
+def test_per_stream_dropin_matches_oracle(version):
     w, h = 200, 120
-    frames, keys, pics = synth.sp_stream(w, h, 10, seed=5, version=2, gop=5, change_permille=50)
+    frames, keys, pics = synth.sp_stream(w, h, 10, seed=5, version=version, gop=5, change_permille=50)
     frames.insert(3, b"\0"); keys.insert(3, 0)
     mine = ScreenPressor(w, h, 24)
     ora = O.OracleCodec(O.CODEC_SCREENPRESSOR, w, h, 24)
@@ -129,3 +133,49 @@ def test_per_stream_dropin_matches_oracle():
         assert (pm is dm) == (po is do), "frame %d: data_pnt identity" % i
         assert sm == so, "frame %d: significant_changes" % i
         assert (pm == po).all(), "frame %d: picture" % i
+
+
+
+# ---------------------------------------------------------------- rANS specifics (v3 / v4) ----
+def many_symbol_picture(w, h, seed):
+    """see tests/test_oracle_sp.py: drives one colour context through Cx1 -> Cx2 -> Cx3 -> Cx7"""
+    px = synth.noise(w, h, seed)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    perm = rng.permutation(256)[:100]
+    seq = np.concatenate([perm, perm, perm])
+    n = min(w * 4, seq.size)
+    px.reshape(-1)[:n] = seq[:n]
+    return px
+
+
+@pytest.mark.parametrize("version", [3, 4])
+def test_ans_all_context_kinds(version):
+    """Noisy content drives the colour contexts through every kind transition of ANS.hx:785-860."""
+    w, h = 384, 256
+    synth.ans_transitions(reset=True)
+    enc = synth.SPEncoder(w, h, 24, version)
+    px = many_symbol_picture(w, h, 5)
+    f0 = enc.iframe(px)
+    nxt = synth.noise(w, h, 6)
+    nxt[: h // 2] = px[: h // 2]
+    f1 = enc.pframe(nxt, px)
+    tr = synth.ans_transitions()
+    assert all(tr[k] > 0 for k in synth.ANS_TRANSITIONS), tr
+    check(w, h, 24, [f0, f1], [1, 0])
+
+
+def test_ans_state_reload_every_131072_symbols():
+    w, h = 512, 300
+    enc = synth.SPEncoder(w, h, 24, 4)
+    px = synth.noise(w, h, 11, ncolors=(3, 9, 30))
+    check(w, h, 24, [enc.iframe(px)], [1])
+
+
+def test_ans_noise_many_sizes():
+    for i, (w, h) in enumerate([(64, 64), (130, 70), (257, 33)]):
+        for version in (3, 4):
+            enc = synth.SPEncoder(w, h, 24, version)
+            a = synth.noise(w, h, 20 + i, ncolors=(2, 5, 17, 70, 256))
+            b = synth.noise(w, h, 40 + i, ncolors=(256, 3))
+            b[::2] = a[::2]
+            check(w, h, 24, [enc.iframe(a), enc.pframe(b, a), enc.iframe(b)], [1, 0, 1])
