@@ -825,7 +825,10 @@ sp_ans_decode_kernel(const SpJob *__restrict__ jobs)
     } else {
         sp_decode_pframe(ec, J, bits);
     }
-    if (ec.failed()) bits |= ST_ERROR;
+    if (ec.failed()) {
+        bits = ST_ERROR;
+        if (!(J.flags & SPJ_RENEW)) sp_undo_frame(J, (J.flags & SPJ_IFRAME) != 0);
+    }
     __syncwarp();
     {
         uint4 *g = reinterpret_cast<uint4 *>(&st->small);

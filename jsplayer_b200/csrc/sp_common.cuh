@@ -77,6 +77,18 @@ __device__ __forceinline__ uint32_t sp_segment(int32_t *dst, const int32_t *prev
     return last;
 }
 
+// A frame whose entropy decode failed shows the previous picture (a P frame returns the retained buffer) or
+// nothing (a failed I frame has already dropped prevFrame, ScreenPressor.hx:110): undo the partial writes.
+__device__ __forceinline__ void sp_undo_frame(const SpJob &J, bool iframe)
+{
+    const size_t n = (size_t)J.X * J.Y;
+    const int lane = (int)lane_id();
+    const int32_t *src = iframe ? nullptr : J.prev;
+    __syncwarp();
+    for (size_t i = lane; i < n; i += 32) J.dst[i] = src ? src[i] : 0;
+    __syncwarp();
+}
+
 // ---- the frame loops, generic over the entropy coder (EntroCoder interface, EntroCoders.hx:8-24) ----
 template <class Coder>
 __device__ void sp_decode_iframe(Coder &ec, const SpJob &J)
