@@ -80,6 +80,11 @@ static int classify(const StreamRec &S, const uint8_t *src, uint32_t len)
 static void classify_sp(const StreamRec &S, SpHost &H, FrameRec &R, const uint8_t *src)
 {
     R.kind = FK_COPY; R.forced = 0; R.sp_flags = 0; R.fill_value = 0;
+    struct SegMark { SpHost &H; FrameRec &R; ~SegMark() {
+        // a coded I frame and a model-resetting flat frame start a segment that depends on nothing before it
+        R.sp_seg_start = R.kind == FK_SP_I || (R.kind == FK_SP_FLAT && (R.sp_flags & SPJ_RENEW));
+        if (R.sp_seg_start) H.n_segments++;
+        R.sp_seg = H.n_segments - 1; } } seg_mark{H, R};
     const uint32_t len = R.len;
     if (R.key) {                                              // DecompressI
         if (len == 0) { H.last_flat = false; R.forced = ST_ERROR; return; }   // head undefined -> "unknown version of the codec"
@@ -122,8 +127,10 @@ struct HostTables {
 };
 
 // Builds the launch list of `plan` for streams [s_lo, s_hi).
-static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables &T, size_t &state_cursor, size_t &ticket_cursor)
+static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables &T, size_t &state_cursor, size_t &ticket_cursor,
+                       bool secondary = false)
 {
+    const uint32_t mframe_base = secondary ? (uint32_t)b->frames.size() : 0u;   // chunk plans use their own frame descriptors
     plan.launches.clear(); plan.uploads.clear();
     plan.frame_lo = b->streams[s_lo].first_frame;
     plan.frame_hi = b->streams[s_hi - 1].first_frame + b->streams[s_hi - 1].n_frames;
@@ -169,11 +176,14 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             std::sort(fr.begin(), fr.end(), [&](int64_t x, int64_t y) {
                 return b->frames[x].n_tiles != b->frames[y].n_tiles ? b->frames[x].n_tiles > b->frames[y].n_tiles : x < y; });
             const size_t first = T.tile_tab.size();
-            for (int64_t f : fr) { b->frames[f].state_base = (uint32_t)state_cursor; state_cursor += b->frames[f].n_tiles; }
+            for (int64_t f : fr) {
+                (secondary ? b->frames[f].state_base2 : b->frames[f].state_base) = (uint32_t)state_cursor;
+                state_cursor += b->frames[f].n_tiles;
+            }
             size_t live = fr.size();
             for (uint32_t t = 0; t < max_tiles; t++) {
                 while (live > 0 && b->frames[fr[live - 1]].n_tiles <= t) live--;
-                for (size_t i = 0; i < live; i++) T.tile_tab.push_back(make_uint2((uint32_t)fr[i], t));
+                for (size_t i = 0; i < live; i++) T.tile_tab.push_back(make_uint2((uint32_t)fr[i] + mframe_base, t));
             }
             plan.launches.push_back({JSP_K_MSV1_DECODE, kind, first, (uint32_t)(T.tile_tab.size() - first), 0, (uint32_t)ticket_cursor});
             ticket_cursor++;
@@ -193,8 +203,9 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
                 J.dst = b->d_out + R.out_off;
                 J.prev = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
                 J.status = b->d_status + f;
-                J.state = b->d_sp_state + H.state_off;
-                J.bts = b->d_sp_bts + H.bts_off;
+                const size_t slot = R.sp_seg > 0 ? (size_t)(R.sp_seg % H.n_slots) : 0;
+                J.state = b->d_sp_state + H.state_off + slot * H.state_stride;
+                J.bts = b->d_sp_bts + H.bts_off + slot * H.bts_stride;
                 J.X = (uint32_t)S.w; J.Y = (uint32_t)S.h; J.flags = R.sp_flags;
                 J.insign_blocks = (uint32_t)(((S.w + 15) / 16) * ((std::max(0, b->insign_lines) + 15) / 16));
                 T.spjobs.push_back(J);
@@ -228,8 +239,9 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
 
 static void fill_mframes(jsp_batch *b, HostTables &T)
 {
-    T.mframes.assign(b->frames.size(), Msv1Frame{});
-    for (size_t f = 0; f < b->frames.size(); f++) {
+    const size_t N = b->frames.size();
+    T.mframes.assign(b->chunks.empty() ? N : 2 * N, Msv1Frame{});
+    for (size_t f = 0; f < N; f++) {
         const FrameRec &R = b->frames[f];
         if (R.kind != FK_MSV16 && R.kind != FK_MSV8) continue;
         const StreamRec &S = b->streams[R.stream];
@@ -250,6 +262,7 @@ static void fill_mframes(jsp_batch *b, HostTables &T)
         M.insign_blocks = (uint32_t)std::max(0, (b->insign_lines + 3) >> 2);
         M.flags = R.prev >= 0 ? MSV1_F_HAS_PRED : 0u;
         M.inv_nbx = M.nbx > 1 ? (uint32_t)(0x100000000ull / M.nbx) : 0xFFFFFFFFu;
+        if (!b->chunks.empty()) { T.mframes[N + f] = M; T.mframes[N + f].state_base = R.state_base2; }
     }
 }
 
@@ -313,20 +326,54 @@ static bool run_plan(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *
 // (Re)computes dependency levels from the key flags, rebuilds the launch plan and uploads the tables.
 static bool plan_and_upload(jsp_batch *b)
 {
-    for (const StreamRec &S : b->streams) {
+    for (size_t s = 0; s < b->streams.size(); s++) {
+        const StreamRec &S = b->streams[s];
         int level = -1;
+        std::vector<int> seg_end;                  // last level of every ScreenPressor segment seen so far
         for (int f = 0; f < S.n_frames; f++) {
             FrameRec &R = b->frames[S.first_frame + f];
-            // key frames do not depend on the previous picture; everything else runs one level later
-            // (ScreenPressor frames of one stream share the stream's model state: always in order)
-            const bool independent = R.key && (R.kind == FK_MSV16 || R.kind == FK_MSV8);
-            level = (independent || f == 0) ? 0 : level + 1;
+            // MSVideo1 key frames do not depend on the previous picture; everything else runs one level later.
+            // ScreenPressor: the frames of one segment share model state and run in order; a new segment starts
+            // at level 0, or right after the segment whose state slot it reuses.
+            bool independent = R.key && (R.kind == FK_MSV16 || R.kind == FK_MSV8);
+            int start = 0;
+            if (S.codec == JSP_CODEC_SCREENPRESSOR) {
+                const SpHost &H = b->sp_hosts[s];
+                if (R.sp_seg_start) {
+                    independent = true;
+                    const int reused = R.sp_seg - H.n_slots;           // the segment that used this state slot before
+                    if (reused >= 0 && (size_t)reused < seg_end.size()) start = seg_end[reused] + 1;
+                }
+                if (R.sp_seg >= 0 && seg_end.size() <= (size_t)R.sp_seg) seg_end.resize(R.sp_seg + 1, 0);
+            }
+            level = independent ? start : (f == 0 ? 0 : level + 1);
             R.level = level;
+            if (S.codec == JSP_CODEC_SCREENPRESSOR && R.sp_seg >= 0) seg_end[R.sp_seg] = level;
         }
     }
     HostTables T;
     size_t state_cursor = 0, ticket_cursor = 0;
     build_plan(b, b->whole, 0, (int)b->streams.size(), T, state_cursor, ticket_cursor);
+    // End-to-end path: when the batch is transfer-bound (MSVideo1 only: one wide launch per level, no per-stream
+    // serial chains to keep busy) the streams are also cut into chunks of whole streams so that the upload of
+    // chunk k+1, the decode of chunk k and the download of chunk k-1 overlap on three CUDA streams.
+    b->chunks.clear();
+    {
+        bool sp = false; size_t out_bytes = 0;
+        for (const StreamRec &S : b->streams) { sp = sp || S.codec == JSP_CODEC_SCREENPRESSOR; out_bytes += (size_t)S.w * S.h * 4 * S.n_frames; }
+        const size_t target = std::max<size_t>((size_t)96 << 20, out_bytes / 48);
+        if (!sp && !b->persist_streams && out_bytes > 4 * target) {
+            int s_lo = 0; size_t acc = 0;
+            for (int s = 0; s < (int)b->streams.size(); s++) {
+                acc += (size_t)b->streams[s].w * b->streams[s].h * 4 * b->streams[s].n_frames;
+                if (acc >= target || s + 1 == (int)b->streams.size()) {
+                    b->chunks.emplace_back();
+                    build_plan(b, b->chunks.back(), s_lo, s + 1, T, state_cursor, ticket_cursor, true);
+                    s_lo = s + 1; acc = 0;
+                }
+            }
+        }
+    }
     fill_mframes(b, T);
     return upload_tables(b, T, state_cursor, ticket_cursor);
 }
@@ -511,14 +558,22 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
     // ScreenPressor model state: small tables + 12288 colour rows per stream, block-type scratch
     {
         size_t st_cur = 0, rows_cur = 0, bts_cur = 0; bool any = false;
+        size_t n_sp = 0;
+        for (int s = 0; s < n_streams; s++) if (b->streams[s].codec == JSP_CODEC_SCREENPRESSOR) n_sp++;
+        // at most ~48 GB of model state per device: concurrent segments per stream are capped accordingly
+        const int max_slots = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)48 << 30) / (std::max<size_t>(1, n_sp) * sp_ans_ctx_bytes())));
         for (int s = 0; s < n_streams; s++) {
             if (b->streams[s].codec != JSP_CODEC_SCREENPRESSOR) continue;
             any = true;
             SpHost &H = b->sp_hosts[s];
             const bool ans = H.version > 2;
-            H.state_off = st_cur; st_cur += ans ? sp_ans_state_bytes() : sp_rc_state_bytes();
-            H.rows_off = rows_cur; rows_cur += ((ans ? sp_ans_ctx_bytes() : sp_rc_rows_bytes()) + 255) & ~(size_t)255;
-            H.bts_off = bts_cur; bts_cur += ((size_t)((b->streams[s].w + 15) / 16) * ((b->streams[s].h + 15) / 16) + 255) & ~(size_t)255;
+            H.n_slots = b->persist_streams ? 1 : std::max(1, std::min(H.n_segments, max_slots));
+            H.state_stride = ans ? sp_ans_state_bytes() : sp_rc_state_bytes();
+            H.rows_stride = ((ans ? sp_ans_ctx_bytes() : sp_rc_rows_bytes()) + 255) & ~(size_t)255;
+            H.bts_stride = ((size_t)((b->streams[s].w + 15) / 16) * ((b->streams[s].h + 15) / 16) + 255) & ~(size_t)255;
+            H.state_off = st_cur; st_cur += H.state_stride * H.n_slots;
+            H.rows_off = rows_cur; rows_cur += H.rows_stride * H.n_slots;
+            H.bts_off = bts_cur; bts_cur += H.bts_stride * H.n_slots;
         }
         if (any) {
             const bool fresh_alloc = st_cur > b->sp_state_cap || rows_cur > b->sp_rows_cap || !b->d_sp_state;
@@ -532,8 +587,11 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
                 for (int s = 0; s < n_streams; s++)
                     if (b->streams[s].codec == JSP_CODEC_SCREENPRESSOR) {
                         const SpHost &H = b->sp_hosts[s];
-                        if (H.version > 2) sp_ans_state_init(b->d_sp_state + H.state_off, b->d_sp_rows + H.rows_off, 1u, b->st_compute);
-                        else sp_rc_state_init(b->d_sp_state + H.state_off, b->d_sp_rows + H.rows_off, 1u, b->st_compute);
+                        for (int k = 0; k < H.n_slots; k++) {
+                            uint8_t *stp = b->d_sp_state + H.state_off + k * H.state_stride, *rwp = b->d_sp_rows + H.rows_off + k * H.rows_stride;
+                            if (H.version > 2) sp_ans_state_init(stp, rwp, 1u, b->st_compute);
+                            else sp_rc_state_init(stp, rwp, 1u, b->st_compute);
+                        }
                     }
                 if (!JSP_CUDA(cudaStreamSynchronize(b->st_compute))) return -1;
             }
@@ -679,11 +737,41 @@ int jsp_batch_download(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags)
 
 int jsp_batch_decode_host(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags)
 {
-    // round 1: upload, decode and download are issued back to back on one stream; the chunked
-    // three-stream PCIe pipeline replaces this body without changing the contract
-    if (jsp_batch_upload(b)) return -1;
-    if (jsp_batch_run(b)) return -1;
-    return jsp_batch_download(b, out_frames, flags);
+    if (!b) return -1;
+    if (b->chunks.empty() || !out_frames) {
+        // latency-bound batches (ScreenPressor) and single frames: upload, decode, download back to back
+        if (jsp_batch_upload(b)) return -1;
+        if (jsp_batch_run(b)) return -1;
+        return jsp_batch_download(b, out_frames, flags);
+    }
+    // transfer-bound batches: three-stream pipeline over chunks of whole streams (PCIe is full duplex)
+    if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
+    const size_t nc = b->chunks.size();
+    while (b->ev_pool.size() < 2 * nc + 2) { cudaEvent_t e; if (!JSP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming))) return -1; b->ev_pool.push_back(e); }
+    // the pool may also hold timing events; any event works for ordering
+    cudaEvent_t ev0 = b->ev_pool[2 * nc];
+    if (!JSP_CUDA(cudaEventRecord(ev0, b->st_compute))) return -1;           // order after earlier work on the compute stream
+    if (!JSP_CUDA(cudaStreamWaitEvent(b->st_in, ev0, 0)) || !JSP_CUDA(cudaStreamWaitEvent(b->st_out, ev0, 0))) return -1;
+    const int reruns = b->rerun_count;
+    for (size_t c = 0; c < nc; c++) {
+        const Plan &P = b->chunks[c];
+        for (const CopyRange &r : P.uploads)
+            if (!JSP_CUDA(cudaMemcpyAsync(b->d_bytes + r.d_off, r.h, r.bytes, cudaMemcpyHostToDevice, b->st_in))) return -1;
+        if (!JSP_CUDA(cudaEventRecord(b->ev_pool[2 * c], b->st_in))) return -1;
+        if (!JSP_CUDA(cudaStreamWaitEvent(b->st_compute, b->ev_pool[2 * c], 0))) return -1;
+        if (!run_plan(b, P, b->st_compute)) return -1;
+        if (!JSP_CUDA(cudaEventRecord(b->ev_pool[2 * c + 1], b->st_compute))) return -1;
+        if (!JSP_CUDA(cudaStreamWaitEvent(b->st_out, b->ev_pool[2 * c + 1], 0))) return -1;
+        if (!download_range(b, P.frame_lo, P.frame_hi, out_frames, b->st_out)) return -1;
+    }
+    if (!run_status(b, b->st_compute)) return -1;
+    if (jsp_batch_results(b, flags)) return -1;                              // syncs the compute stream
+    if (!JSP_CUDA(cudaStreamSynchronize(b->st_out))) return -1;
+    if (b->rerun_count != reruns) {                                           // a mis-flagged key frame was demoted and the batch re-decoded
+        if (!download_range(b, 0, (int64_t)b->frames.size(), out_frames, b->st_compute)) return -1;
+        return JSP_CUDA(cudaStreamSynchronize(b->st_compute)) ? 0 : -1;
+    }
+    return 0;
 }
 
 uint64_t jsp_batch_device_frame(jsp_batch *b, int64_t i)

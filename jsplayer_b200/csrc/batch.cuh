@@ -28,7 +28,11 @@ struct SpHost {
     int version = 0;            // 0 = no entropy coder yet (`ec == null`), else 2/3/4 (initEntro, :66-79)
     bool decodedI = false;
     bool last_flat = false;     // last_one_was_flat != null
+    // model state slots: every independent segment (coded I frame / model-resetting flat frame up to the next
+    // one) decodes with its own state, so the segments of one stream run concurrently; slot = segment % n_slots
     size_t state_off = 0, rows_off = 0, bts_off = 0;
+    size_t state_stride = 0, rows_stride = 0, bts_stride = 0;
+    int n_slots = 1, n_segments = 0;
 };
 
 // sp_rc.cu
@@ -62,9 +66,12 @@ struct FrameRec {
     int kind;
     uint8_t key;
     uint32_t n_tiles, state_base;
+    uint32_t state_base2;           // the frame's tile-state slice in the chunked (pipelined) plans
     uint32_t forced;                // status bits decided on the host (ST_ERROR, ST_CHANGED of flat frames)
     uint32_t fill_value;            // FK_SP_FLAT colour
     uint32_t sp_flags;              // SPJ_* for ScreenPressor jobs
+    bool sp_seg_start;              // ScreenPressor: the frame starts an independent segment
+    int sp_seg;                     // ScreenPressor: index of the independent segment the frame belongs to (-1: none yet)
 };
 
 struct Launch {

@@ -81,8 +81,10 @@ static void ea_begin(entro *e, const uint8_t *src, int len, int pos0)   /* :229-
     rans_init(&a->rans, pos0);
     a->nDec = 0;
 }
+extern unsigned long long g_ora_symbols;
 static inline void ea_count(entro_ans *a)
 {
+    g_ora_symbols++;
     a->nDec++;
     if (a->nDec == ANS_B) { rans_init(&a->rans, a->rans.pos); a->nDec = 0; }
 }

@@ -178,3 +178,17 @@ def test_ans_noise_many_sizes():
             b = synth.noise(w, h, 40 + i, ncolors=(256, 3))
             b[::2] = a[::2]
             check(w, h, 24, [enc.iframe(a), enc.pframe(b, a), enc.iframe(b)], [1, 0, 1])
+
+
+@pytest.mark.parametrize("version", [2, 4])
+def test_independent_segments_run_concurrently(version):
+    """Every coded I frame resets all models (ScreenPressor.hx:163, EntroCoders.hx:81-130, 216-227): the batcher decodes
+    the segments of one stream concurrently with one model-state slot each (more segments than slots here)."""
+    w, h = 96, 80
+    frames, keys, pics = synth.sp_stream(w, h, 40, seed=21, version=version, gop=2, change_permille=80)
+    check(w, h, 24, frames, keys)
+    frames, keys, pics = synth.sp_stream(w, h, 21, seed=22, version=version, gop=1)
+    enc = synth.SPEncoder(w, h, 24, version)
+    frames.insert(5, enc.flat(0x0A0B0C)); keys.insert(5, 1)      # a model-resetting flat frame is a segment of its own
+    frames.insert(6, b"\0"); keys.insert(6, 0)
+    check(w, h, 24, frames, keys, insign=16)
