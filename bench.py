@@ -108,7 +108,66 @@ class SPWorkload(Workload):
                 "stream_versions": ["v%d" % v for v in self.versions]}
 
 
+class C5(Workload):
+    """BASELINE.json configs[4]: mixed 4K corpus of real RIFF AVI files (MSVideo1 RGB555 + ScreenPressor v2/v3/v4, key
+    frame every 16), written to disk, read back through the AVI indexer into pinned buffers and decoded as
+    keyframe-delimited segments (GOPs) -- the unit of sharding; 64 files over 8 GPUs = 8 files per GPU."""
+    name = "c5"
+    metric = "decoded Mpixel/s (mixed 4K AVI corpus, GOP-sharded)"
+    W, H, FRAMES, GOP = 3840, 2160, 64, 16
+    desc = "mixed 3840x2160 corpus: MSVideo1 RGB555 + ScreenPressor AVI files, 64 frames, key every 16, via the AVI indexer, GOP-sharded"
+    dominant, dominant_name = 0, "msv1_decode_kernel<false>"
+
+    def __init__(self, files):
+        self.n = files
+        self._keep = []
+
+    def specs(self, rank, n=None):
+        import tempfile
+        from jsplayer_b200 import synth, avi
+        from jsplayer_b200.synth.avi import write_avi
+        synth.load()
+        n = self.n if n is None else n
+        tmp = tempfile.mkdtemp(prefix="jsp_c5_")
+        W, H = self.W, self.H
+
+        def one(i):
+            path = os.path.join(tmp, "r%d_f%d.avi" % (rank, i))
+            seed = 0xC0DEC5 + rank * 7919 + i
+            if i % 2 == 0:
+                frames = [synth.msv1_frame(False, W, H, seed * 64 + f, skip_permille=0 if f % self.GOP == 0 else 850)
+                          for f in range(self.FRAMES)]
+                keys = [1 if f % self.GOP == 0 else 0 for f in range(self.FRAMES)]
+                write_avi(path, W, H, 16, b"CRAM", frames, keys)
+            else:
+                frames, keys, _ = synth.sp_stream(W, H, self.FRAMES, seed=seed, version=2 + (i // 2) % 3, gop=self.GOP, change_permille=20)
+                write_avi(path, W, H, 24, b"SCPR", frames, keys)
+            return path
+        with ThreadPoolExecutor(max_workers=8) as ex:
+            paths = list(ex.map(one, range(n)))
+        streams = [avi.load_avi(p, pinned=True) for p in paths]
+        for p in paths:
+            os.unlink(p)
+        os.rmdir(tmp)
+        self._keep = streams
+        specs, self.where = avi.gop_specs(streams)
+        return specs
+
+    def config(self):
+        return {"workload": self.desc, "files_per_gpu": self.n, "frames_per_file": self.FRAMES, "gop": self.GOP,
+                "width": self.W, "height": self.H}
+
+
+def spec_frames(sp):
+    """The compressed frames of a StreamSpec as a list of bytes."""
+    if sp.bytes_buf is None:
+        return [bytes(f) for f in sp.frames]
+    return [sp.bytes_buf[int(o):int(o) + int(n)].tobytes() for o, n in zip(sp.frame_off, sp.frame_len)]
+
+
 def make_workload(name, args):
+    if name == "c5":
+        return C5(args.files)
     if name == "c2":
         return C2(args.frames)
     if name == "c3":
@@ -201,13 +260,14 @@ def oracle_descs(specs):
     descs = (O.StreamDesc * len(specs))()
     cache = {}
     for i, sp in enumerate(specs):
-        key = id(sp.frames)
+        key = id(sp.frames) if sp.bytes_buf is None else (id(sp.bytes_buf), int(sp.frame_off[0]) if len(sp.frame_off) else 0)
         if key not in cache:
-            ln = np.array([len(f) for f in sp.frames], dtype=np.uint32)
+            frames = spec_frames(sp)
+            ln = np.array([len(f) for f in frames], dtype=np.uint32)
             off = np.zeros(len(ln), dtype=np.uint64)
             if len(ln):
                 off[1:] = np.cumsum(ln.astype(np.uint64))[:-1]
-            blob = np.frombuffer(b"".join(bytes(f) for f in sp.frames) + b"\0", dtype=np.uint8).copy()
+            blob = np.frombuffer(b"".join(frames) + b"\0", dtype=np.uint8).copy()
             keys = np.zeros(len(ln), dtype=np.uint8)
             if sp.keys is None:
                 keys[:1] = 1
@@ -218,7 +278,9 @@ def oracle_descs(specs):
         blob, off, ln, keys = cache[key]
         d = descs[i]
         d.codec, d.width, d.height, d.bpp = int(sp.codec), sp.width, sp.height, sp.bpp
-        d.palette, d.palette_bytes, d.n_frames = None, 0, len(ln)
+        pal = np.frombuffer(sp.palette, dtype=np.uint8).copy() if sp.palette else None
+        keep.append(pal)
+        d.palette, d.palette_bytes, d.n_frames = (pal.ctypes.data if pal is not None else None), (pal.size if pal is not None else 0), len(ln)
         d.bytes, d.frame_off, d.frame_len, d.frame_key, d.out = blob.ctypes.data, off.ctypes.data, ln.ctypes.data, keys.ctypes.data, None
     return descs, keep
 
@@ -249,7 +311,7 @@ def check_against_oracle(bd, specs, outs, which):
         first += sp.n_frames
     for s in which:
         sp = specs[s]
-        exp = O.decode_stream(int(sp.codec), sp.width, sp.height, sp.bpp, list(sp.frames), keys=sp.keys,
+        exp = O.decode_stream(int(sp.codec), sp.width, sp.height, sp.bpp, spec_frames(sp), keys=sp.keys, palette=sp.palette,
                               insignificant_lines=INSIGN)[0]
         for f in range(sp.n_frames):
             if not (outs[firsts[s] + f].reshape(sp.height, sp.width) == exp[f]).all():
@@ -378,7 +440,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--files", type=int, default=8, help="c5: AVI files per GPU")
     ap.add_argument("--frames", type=int, default=1024, help="c2: frames (= independent streams) per GPU")
     ap.add_argument("--streams", type=int, default=0, help="c3/c4: streams per GPU (default 256 / 128)")
     ap.add_argument("--sp-versions", type=lambda s: [int(x) for x in s.split(",")], default=[2],

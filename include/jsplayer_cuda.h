@@ -124,6 +124,30 @@ JSP_API int jsp_batch_decode(const jsp_stream_desc *streams, int n_streams, int 
                              int32_t *const *out_frames, uint8_t *out_changed,
                              uint8_t *out_significant, int32_t *out_status);
 
+/* ---- AVI indexer: a complete RIFF AVI file in memory -> video stream info + frame table ----
+ * Local-file counterpart of AVIParser (AVIParser.hx:42-184) and of the idx1 / OpenDML index handling of the loaders
+ * (DataLoaderAVIIndexed.hx:276-350, DataLoader.hx:321-401).  Frames are NOT copied: offsets point into `file`, so a
+ * jsp_stream_desc built from the table uploads straight from the (ideally pinned) file buffer. */
+typedef struct {
+    int32_t codec;            /* jsp_codec chosen from the fourcc as AVIParser.hx:75-78 does */
+    int32_t width, height, bpp;
+    uint32_t fourcc;
+    int32_t n_frames;         /* video chunks found in movi */
+    int32_t n_frames_header;  /* avih dwTotalFrames */
+    int32_t palette_bytes;    /* strf bytes from offset 40 (8 bpp) */
+    int32_t has_index;        /* idx1 or OpenDML index present: key flags come from it */
+    double  fps;
+} jsp_avi_info;
+typedef struct jsp_avi jsp_avi;
+JSP_API jsp_avi    *jsp_avi_parse(const uint8_t *file, uint64_t size);          /* NULL on failure, see jsp_avi_last_error */
+JSP_API void        jsp_avi_free(jsp_avi *a);
+JSP_API int         jsp_avi_get_info(const jsp_avi *a, jsp_avi_info *out);
+JSP_API int         jsp_avi_get_palette(const jsp_avi *a, uint8_t *out, int cap);  /* returns palette_bytes */
+/* off[i] / len[i]: payload of video frame i inside `file`; key[i]: index key flag; key_known[i] = 0 when no index
+ * entry covers the frame (the caller then asks jsp_is_key_frame, DataLoaderAVIIndexed.hx:182). Returns n_frames. */
+JSP_API int         jsp_avi_frame_table(const jsp_avi *a, uint64_t *off, uint32_t *len, uint8_t *key, uint8_t *key_known);
+JSP_API const char *jsp_avi_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

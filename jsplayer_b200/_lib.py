@@ -15,6 +15,12 @@ class PFrameResultC(C.Structure):
     _fields_ = [("data_pnt", C.c_void_p), ("significant_changes", C.c_int32)]
 
 
+class AviInfoC(C.Structure):
+    _fields_ = [("codec", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("bpp", C.c_int32),
+                ("fourcc", C.c_uint32), ("n_frames", C.c_int32), ("n_frames_header", C.c_int32),
+                ("palette_bytes", C.c_int32), ("has_index", C.c_int32), ("fps", C.c_double)]
+
+
 class StreamDescC(C.Structure):
     _fields_ = [("codec", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("bpp", C.c_int32),
                 ("palette", C.c_void_p), ("palette_bytes", C.c_int32), ("n_frames", C.c_int32),
@@ -53,6 +59,12 @@ PROTOTYPES = {
     "jsp_batch_time_runs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jsp_batch_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jsp_batch_kernel_bytes": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "jsp_avi_parse": (C.c_void_p, [C.c_void_p, C.c_uint64]),
+    "jsp_avi_free": (None, [C.c_void_p]),
+    "jsp_avi_get_info": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "jsp_avi_get_palette": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "jsp_avi_frame_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jsp_avi_last_error": (C.c_char_p, []),
     "jsp_batch_decode": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -8,6 +8,8 @@
 // No CPU decode path exists here: without a CUDA device every entry point fails.
 #include "batch.cuh"
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -27,6 +29,26 @@ bool cuda_ok(cudaError_t e, const char *what)
     if (e == cudaSuccess) return true;
     set_error("CUDA error %s: %s", cudaGetErrorString(e), what);
     return false;
+}
+
+// Pinned allocations handed out by jsp_host_alloc: two bitstream ranges may be merged into one copy only when
+// they lie in the same allocation (neighbouring allocations can be adjacent in the address space).
+static std::mutex g_alloc_mu;
+static std::map<uintptr_t, size_t> g_allocs;
+static uintptr_t alloc_of(const void *p)
+{
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    auto it = g_allocs.upper_bound(a);
+    if (it == g_allocs.begin()) return 0;
+    --it;
+    return a < it->first + it->second ? it->first : 0;
+}
+static bool same_buffer(const uint8_t *base_a, const uint8_t *pa, const uint8_t *base_b, const uint8_t *pb)
+{
+    if (base_a == base_b) return true;                   // the caller described both with one buffer
+    const uintptr_t x = alloc_of(pa);
+    return x != 0 && x == alloc_of(pb);
 }
 
 template <typename T>
@@ -228,7 +250,8 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
         if (!plan.uploads.empty()) {
             CopyRange &p = plan.uploads.back();
             const uint8_t *pend = p.h + p.bytes;
-            if (r.h >= pend && (size_t)(r.h - pend) < 4096 && r.d_off == p.d_off + (size_t)(r.h - p.h)) {
+            if (r.h >= pend && (size_t)(r.h - pend) < 4096 && r.d_off == p.d_off + (size_t)(r.h - p.h) &&
+                same_buffer(b->streams[s - 1].h_bytes, pend - 1, S.h_bytes, r.h)) {
                 p.bytes = (size_t)(r.h - p.h) + r.bytes;
                 continue;
             }
@@ -408,9 +431,15 @@ void *jsp_host_alloc(size_t bytes)
 {
     void *p = nullptr;
     if (!JSP_CUDA(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable))) return nullptr;
+    { std::lock_guard<std::mutex> lk(g_alloc_mu); g_allocs[reinterpret_cast<uintptr_t>(p)] = bytes ? bytes : 1; }
     return p;
 }
-void jsp_host_free(void *p) { if (p) cudaFreeHost(p); }
+void jsp_host_free(void *p)
+{
+    if (!p) return;
+    { std::lock_guard<std::mutex> lk(g_alloc_mu); g_allocs.erase(reinterpret_cast<uintptr_t>(p)); }
+    cudaFreeHost(p);
+}
 
 jsp_batch *jsp_batch_create(int device, int insignificant_lines, int flags)
 {
@@ -491,7 +520,7 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
             const StreamRec &Pv = b->streams.back();
             const uint8_t *pend = Pv.h_bytes + Pv.h_hi;
             const uint8_t *cur = D.bytes + lo;
-            if (hi > lo && cur >= pend && (size_t)(cur - pend) < 4096) bytes_cur = Pv.d_base + (size_t)(cur - (Pv.h_bytes + Pv.h_lo));
+            if (hi > lo && cur >= pend && (size_t)(cur - pend) < 4096 && same_buffer(Pv.h_bytes, pend - 1, D.bytes, cur)) bytes_cur = Pv.d_base + (size_t)(cur - (Pv.h_bytes + Pv.h_lo));
             else bytes_cur = ((bytes_cur + 255) & ~(size_t)255) + mis;
         } else bytes_cur = ((bytes_cur + 255) & ~(size_t)255) + mis;
         S.d_base = bytes_cur;

@@ -1,0 +1,157 @@
+"""AVI indexer (csrc/avi_index.cpp behind jsp_avi_*) and the GOP / shard logic of jsplayer_b200/avi.py: host-side
+tests, no GPU.  Format facts follow reference src/AVIParser.hx:42-184, src/DataLoaderAVIIndexed.hx:276-350 and
+src/DataLoader.hx:321-401."""
+import struct
+
+import numpy as np
+import pytest
+
+from jsplayer_b200 import synth, avi, CodecType
+from jsplayer_b200.synth.avi import avi_bytes, _chunk, _list
+
+
+def parse(b):
+    return avi.parse_avi(np.frombuffer(b, dtype=np.uint8))
+
+
+def sp_frames(n=6, gop=3, version=2):
+    return synth.sp_stream(64, 48, n, seed=1, version=version, gop=gop)[:2]
+
+
+def test_idx1_relative_offsets_and_payload_lengths():
+    fr, k = sp_frames()
+    a = parse(avi_bytes(64, 48, 24, b"SCPR", fr, k, fps=25))
+    assert (a.codec, a.width, a.height, a.bpp, a.n_frames, a.has_index) == (CodecType.codec_screenpressor, 64, 48, 24, 6, True)
+    assert abs(a.fps - 25) < 1e-3
+    assert list(a.keys) == k
+    assert all(bytes(a.frame(i)) == fr[i] for i in range(6))           # odd-sized frames come without the RIFF pad byte
+    assert a.gops() == [(0, 3), (3, 6)]
+
+
+def test_idx1_absolute_offsets():
+    fr, k = sp_frames()
+    b = bytearray(avi_bytes(64, 48, 24, b"SCPR", fr, k))
+    movi = b.find(b"movi")
+    idx = b.find(b"idx1")
+    n = struct.unpack_from("<I", b, idx + 4)[0] // 16
+    for i in range(n):                                                  # rewrite the offsets as absolute file positions
+        o = idx + 8 + 16 * i + 8
+        struct.pack_into("<I", b, o, struct.unpack_from("<I", b, o)[0] + movi)
+    a = parse(bytes(b))
+    assert list(a.keys) == k and all(bytes(a.frame(i)) == fr[i] for i in range(6))
+
+
+def test_codec_choice_and_palette():
+    pal = synth.random_palette(3)
+    fr = [synth.msv1_frame(True, 64, 48, 1)] + [synth.msv1_frame(True, 64, 48, 2 + i, skip_permille=300) for i in range(3)]
+    for four in (b"CRAM", b"MSVC", b"msvc"):
+        a = parse(avi_bytes(64, 48, 8, four, fr, None, palette=pal))
+        assert a.codec == CodecType.codec_msvc8 and a.palette == pal and list(a.keys) == [1, 0, 0, 0]
+    fr16 = [synth.msv1_frame(False, 64, 48, 1)]
+    assert parse(avi_bytes(64, 48, 16, b"CRAM", fr16)).codec == CodecType.codec_msvc16
+    assert parse(avi_bytes(64, 48, 24, b"SCPR", *sp_frames())).codec == CodecType.codec_screenpressor
+
+
+def strip_idx1(b):
+    i = b.find(b"idx1")
+    body = b[8:i]
+    return b"RIFF" + struct.pack("<I", len(body)) + body
+
+
+def test_no_index_falls_back_to_the_codecs_is_key_frame():
+    fr, k = sp_frames(version=4)
+    a = parse(strip_idx1(avi_bytes(64, 48, 24, b"SCPR", fr, k)))
+    assert not a.has_index and list(a.keys) == k                       # ScreenPressor.hx:96-101
+    frm = [synth.msv1_frame(False, 64, 48, 1)] + [synth.msv1_frame(False, 64, 48, 2 + i, skip_permille=300) for i in range(3)]
+    a = parse(strip_idx1(avi_bytes(64, 48, 16, b"CRAM", frm)))
+    assert list(a.keys) == [1, 0, 0, 0]                                  # MSVideo1.hx:226-259: key <=> no skip opcode
+
+
+def test_opendml_ix00_and_list_rec():
+    """ix00 standard index inside movi (key = bit 31 of the size clear, DataLoader.hx:338-347) and frames wrapped in
+    LIST 'rec ' (AVIParser.hx:150)."""
+    fr, k = sp_frames()
+    whole = avi_bytes(64, 48, 24, b"SCPR", fr, k)
+    head = whole[12:whole.find(b"movi") - 8]                             # everything before LIST movi
+    movi_payload = b""
+    positions = []
+    pos0 = 12 + len(head) + 12                                           # file offset of the first byte after 'movi'
+    for i, f in enumerate(fr):
+        c = _chunk(b"00dc", bytes(f))
+        if i % 2 == 0:
+            positions.append(pos0 + len(movi_payload) + 12 + 8)          # LIST size 'rec ' + chunk header
+            c = _list(b"rec ", c)
+        else:
+            positions.append(pos0 + len(movi_payload) + 8)
+        movi_payload += c
+    base = pos0
+    ents = b"".join(struct.pack("<II", p - base, len(f) | (0 if kk else 0x80000000)) for p, f, kk in zip(positions, fr, k))
+    ix = struct.pack("<HBBI4sQI", 2, 0, 1, len(fr), b"00dc", base, 0) + ents
+    movi_payload += _chunk(b"ix00", ix)
+    body = b"AVI " + head + _list(b"movi", movi_payload)
+    a = parse(b"RIFF" + struct.pack("<I", len(body)) + body)
+    assert a.has_index and a.n_frames == 6
+    assert list(a.keys) == k and all(bytes(a.frame(i)) == fr[i] for i in range(6))
+
+
+def test_bad_files():
+    with pytest.raises(ValueError):
+        parse(b"not an avi file at all")
+    with pytest.raises(ValueError):
+        parse(b"RIFF\x04\0\0\0AVI ")
+    fr, k = sp_frames()
+    b = avi_bytes(64, 48, 24, b"SCPR", fr, k)
+    a = parse(b[: len(b) // 2])                                           # truncated: the frames that are there
+    assert 0 < a.n_frames <= 6
+
+
+def test_shard_is_a_balanced_partition():
+    w = [5, 3, 8, 1, 9, 2, 7, 7]
+    for n in (1, 2, 3, 8):
+        parts = avi.shard(w, n)
+        assert sorted(i for p in parts for i in p) == list(range(len(w)))
+        loads = [sum(w[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(w)
+
+
+def _rank_main(rank, world, port, q):
+    """One rank of the stream-sharded job on CPU: same partition on every rank, own shard only, no data exchange --
+    the only collectives are the ones bench.py uses (barrier + MAX of the elapsed time)."""
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    streams = []
+    for s in range(5):
+        fr, k = synth.sp_stream(48, 32, 6, seed=10 + s, version=2 + s % 3, gop=2 + s % 2)[:2]
+        streams.append(avi.parse_avi(np.frombuffer(avi_bytes(48, 32, 24, b"SCPR", fr, k), dtype=np.uint8)))
+    specs, where = avi.gop_specs(streams)
+    weights = [int(sp.frame_len.sum()) + sp.width * sp.height * sp.n_frames // 8 for sp in specs]
+    mine = avi.shard(weights, world)[rank]
+    dist.barrier()
+    t = torch.tensor([float(len(mine))], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    got = [None] * world
+    dist.all_gather_object(got, mine)
+    q.put((rank, mine, got, len(specs), float(t.item())))
+    dist.destroy_process_group()
+
+
+def test_two_ranks_shard_gops_without_exchange():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (np.random.default_rng().integers(0, 2000))
+    ps = [ctx.Process(target=_rank_main, args=(r, 2, int(port), q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = res[0][3]
+    for rank, mine, got, n_specs, tmax in res:
+        assert got[rank] == mine and n_specs == n
+        assert sorted(got[0] + got[1]) == list(range(n))                 # every GOP decoded exactly once
+        assert tmax == max(len(got[0]), len(got[1]))

@@ -1,0 +1,94 @@
+"""GPU parity for the mixed corpus path (BASELINE.json configs[4] in miniature): MSVideo1 + ScreenPressor AVI files
+-> AVI indexer -> keyframe-delimited segments decoded as independent units -> bit-exact against the oracle decoding
+each file as one stream."""
+import numpy as np
+import pytest
+
+from jsplayer_b200 import synth, avi, BatchDecoder, _lib
+from jsplayer_b200.synth.avi import write_avi
+from oracle import pyoracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def make_corpus(tmp_path):
+    files = []
+    w, h = 128, 96
+    for i in range(6):
+        path = str(tmp_path / ("f%d.avi" % i))
+        if i % 3 == 0:
+            frames = []
+            for f in range(12):
+                frames.append(synth.msv1_frame(False, w, h, 100 * i + f, skip_permille=0 if f % 4 == 0 else 400))
+            keys = [1 if f % 4 == 0 else 0 for f in range(12)]
+            write_avi(path, w, h, 16, b"CRAM", frames, keys)
+            files.append((path, O.CODEC_MSVC16, 16, None, frames, keys))
+        elif i % 3 == 1:
+            pal = synth.random_palette(i)
+            frames = [synth.msv1_frame(True, w, h, 100 * i + f, skip_permille=0 if f % 5 == 0 else 300) for f in range(10)]
+            keys = [1 if f % 5 == 0 else 0 for f in range(10)]
+            write_avi(path, w, h, 8, b"MSVC", frames, keys, palette=pal)
+            files.append((path, O.CODEC_MSVC8, 8, pal, frames, keys))
+        else:
+            frames, keys, _ = synth.sp_stream(w, h, 12, seed=i, version=2 + i % 3, gop=4, change_permille=60)
+            write_avi(path, w, h, 24, b"SCPR", frames, keys)
+            files.append((path, O.CODEC_SCREENPRESSOR, 24, None, frames, keys))
+    return files, w, h
+
+
+def test_mixed_corpus_gop_sharded(tmp_path):
+    files, w, h = make_corpus(tmp_path)
+    streams = [avi.load_avi(p, pinned=True) for p, *_ in files]
+    specs, where = avi.gop_specs(streams)
+    assert len(specs) > len(files)                                    # several segments per file
+    bd = BatchDecoder(insignificant_lines=0)
+    bd.configure(specs)
+    outs, flags = bd.decode_host()
+    bd.close()
+    assert not (flags & _lib.JSP_FRAME_ERROR).any()
+    i = 0
+    exp = [O.decode_stream(codec, w, h, bpp, frames, keys=keys, palette=pal)[0] for _, codec, bpp, pal, frames, keys in files]
+    for (fi, lo, hi) in where:
+        for f in range(lo, hi):
+            assert (outs[i] == exp[fi][f]).all(), "file %d frame %d" % (fi, f)
+            i += 1
+    assert i == sum(len(f[4]) for f in files)
+
+
+def test_one_shot_multi_gpu_entry_matches(tmp_path):
+    """jsp_batch_decode shards whole streams over the visible GPUs (1 here unless the box has more)."""
+    import ctypes as C
+    files, w, h = make_corpus(tmp_path)
+    streams = [avi.load_avi(p) for p, *_ in files]
+    specs, where = avi.gop_specs(streams)
+    lib = _lib.require_gpu()
+    n = len(specs)
+    descs = (_lib.StreamDescC * n)()
+    keep = []
+    total = 0
+    for i, sp in enumerate(specs):
+        off = np.ascontiguousarray(sp.frame_off, dtype=np.uint64); ln = np.ascontiguousarray(sp.frame_len, dtype=np.uint32)
+        keys = np.ascontiguousarray(sp.keys, dtype=np.uint8)
+        pal = np.frombuffer(sp.palette, dtype=np.uint8).copy() if sp.palette else None
+        keep += [off, ln, keys, pal]
+        d = descs[i]
+        d.codec, d.width, d.height, d.bpp = int(sp.codec), sp.width, sp.height, sp.bpp
+        d.palette = pal.ctypes.data if pal is not None else None
+        d.palette_bytes = pal.size if pal is not None else 0
+        d.n_frames = len(ln)
+        d.bytes = sp.bytes_buf.ctypes.data
+        d.frame_off, d.frame_len, d.frame_key = off.ctypes.data, ln.ctypes.data, keys.ctypes.data
+        total += len(ln)
+    outs = [np.zeros((h, w), dtype=np.int32) for _ in range(total)]
+    ptrs = (C.c_void_p * total)(*[o.ctypes.data for o in outs])
+    changed = np.zeros(total, dtype=np.uint8); signif = np.zeros(total, dtype=np.uint8); status = np.zeros(total, dtype=np.int32)
+    ngpu = max(1, min(2, lib.jsp_device_count()))
+    rc = lib.jsp_batch_decode(descs, n, ngpu, ptrs, changed.ctypes.data, signif.ctypes.data, status.ctypes.data)
+    assert rc == 0, _lib.last_error()
+    assert (status == 0).all()
+    exp = [O.decode_stream(codec, w, h, bpp, frames, keys=keys, palette=pal)[0] for _, codec, bpp, pal, frames, keys in files]
+    i = 0
+    for (fi, lo, hi) in where:
+        for f in range(lo, hi):
+            assert (outs[i] == exp[fi][f]).all(), "file %d frame %d" % (fi, f)
+            i += 1
