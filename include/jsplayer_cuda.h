@@ -84,6 +84,8 @@ enum {
     JSP_FRAME_CHANGED     = 1,   /* data_pnt == dst (the frame altered pixels)              */
     JSP_FRAME_SIGNIFICANT = 2,   /* PFrameResult.significant_changes                         */
     JSP_FRAME_ERROR       = 4,   /* DecoderState.error_occured / malformed bitstream         */
+    JSP_FRAME_DIFFERS     = 8,   /* key frames: Manager.frames_differ_significantly (Manager.hx:392-421) -- what
+                                    Manager.worker stores into CompressedFrame.significant_changes for I frames (:499-504) */
 };
 
 JSP_API jsp_batch *jsp_batch_create(int device, int insignificant_lines, int flags);
@@ -98,6 +100,11 @@ JSP_API int        jsp_batch_sync(jsp_batch *b);
  * row order; NULL entries are skipped.  flags[i] = JSP_FRAME_* bits. */
 JSP_API int        jsp_batch_download(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags);
 JSP_API int        jsp_batch_results(jsp_batch *b, uint8_t *flags);             /* flags only */
+/* Display epilogue of the caller (Manager.fill_bitmap_data, Manager.hx:363-381): pictures are converted on the device
+ * from 0x00RRGGBB to the Int32 view of canvas bytes R,G,B,A (alpha 255; ScreenPressor at 16 bpp: 0xFF000000 | c << 3),
+ * optionally flipped vertically (the negative-Y matrix Main applies when drawing, Main.hx:318,946), then downloaded. */
+enum { JSP_DISPLAY_FLIP = 1 };
+JSP_API int        jsp_batch_download_display(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags, int display_flags);
 /* upload + run + download, chunked and double-buffered over PCIe (the end-to-end path). */
 JSP_API int        jsp_batch_decode_host(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags);
 /* device pointer (as integer) of output picture i and of the output arena; for device-resident consumers */

@@ -8,7 +8,8 @@ LIB_PATH = os.path.join(HERE, "libjsplayer_cuda.so")
 JSP_N_KERNELS = 8
 KERNEL_NAMES = ["msv1_decode", "frame_copy", "sp_entropy_rc", "sp_entropy_ans", "sp_recon", "signif", "k6", "k7"]
 JSP_BATCH_SIGNIFICANCE = 1
-JSP_FRAME_CHANGED, JSP_FRAME_SIGNIFICANT, JSP_FRAME_ERROR = 1, 2, 4
+JSP_FRAME_CHANGED, JSP_FRAME_SIGNIFICANT, JSP_FRAME_ERROR, JSP_FRAME_DIFFERS = 1, 2, 4, 8
+JSP_DISPLAY_FLIP = 1
 
 
 class PFrameResultC(C.Structure):
@@ -53,6 +54,7 @@ PROTOTYPES = {
     "jsp_batch_run": (C.c_int, [C.c_void_p]),
     "jsp_batch_sync": (C.c_int, [C.c_void_p]),
     "jsp_batch_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jsp_batch_download_display": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "jsp_batch_results": (C.c_int, [C.c_void_p, C.c_void_p]),
     "jsp_batch_decode_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "jsp_batch_device_frame": (C.c_uint64, [C.c_void_p, C.c_int64]),

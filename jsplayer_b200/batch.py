@@ -181,6 +181,15 @@ class BatchDecoder:
         self._check(self._lib.jsp_batch_download(self._h, self._out_ptrs(outs), flags.ctypes.data), "jsp_batch_download")
         return outs, flags
 
+    def download_display(self, outs=None, flip=False):
+        """Pictures in the caller's display format (Manager.fill_bitmap_data): canvas R,G,B,A words, optional flip."""
+        if outs is None:
+            outs = self.alloc_outputs()
+        flags = np.zeros(self.n_frames, dtype=np.uint8)
+        self._check(self._lib.jsp_batch_download_display(self._h, self._out_ptrs(outs), flags.ctypes.data,
+                                                         _lib.JSP_DISPLAY_FLIP if flip else 0), "jsp_batch_download_display")
+        return outs, flags
+
     def results(self):
         flags = np.zeros(self.n_frames, dtype=np.uint8)
         self._check(self._lib.jsp_batch_results(self._h, flags.ctypes.data), "jsp_batch_results")

@@ -408,6 +408,8 @@ static bool run_status(jsp_batch *b, cudaStream_t st)
     const int exact = (b->flags & JSP_BATCH_SIGNIFICANCE) ? 1 : 0;
     if (exact && b->n_sig)
         launch_signif(b->d_sig_cur, b->d_sig_prev, b->d_sig_status, b->d_sig_first, b->d_sig_npx, (uint32_t)b->n_sig, b->sm_count, st);
+    if (b->n_kd)
+        launch_signif(b->d_kd_cur, b->d_kd_prev, b->d_kd_status, b->d_kd_first, b->d_kd_npx, (uint32_t)b->n_kd, b->sm_count, st, true);
     launch_status_final(b->d_status, b->d_frame_codec, (uint32_t)b->frames.size(), exact, st);
     return JSP_CUDA(cudaGetLastError());
 }
@@ -466,7 +468,8 @@ void jsp_batch_destroy(jsp_batch *b)
     void *ptrs[] = {b->d_bytes, b->d_out, b->d_pal, b->d_status, b->d_mframes, b->d_tile_tab, b->d_jobs, b->d_tile_map,
                     b->d_tile_cnt, b->d_tickets, b->d_sig_cur, b->d_sig_prev, b->d_sig_status, b->d_sig_first, b->d_sig_npx,
                     b->d_stream_first, b->d_stream_count, b->d_frame_codec, b->d_flush, b->d_spjobs, b->d_sp_state,
-                    b->d_sp_rows, b->d_sp_bts};
+                    b->d_sp_rows, b->d_sp_bts, b->d_kd_cur, b->d_kd_prev, b->d_kd_status, b->d_kd_first, b->d_kd_npx,
+                    b->d_disp, b->d_disp_jobs};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (b->h_status) cudaFreeHost(b->h_status);
     if (b->st_compute) cudaStreamDestroy(b->st_compute);
@@ -667,6 +670,46 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
             cudaMemcpy(b->d_sig_npx, npx.data(), npx.size() * 4, cudaMemcpyHostToDevice);
         }
     }
+    // key frames: Manager.frames_differ_significantly (Manager.hx:392-421).  Frame 0 of a stream and a key frame that
+    // follows a key frame are settled on the host (byte compare of the two compressed frames); a key frame that
+    // follows a non-key frame is compared pixel by pixel with the picture before it, on the device.
+    {
+        std::vector<const int32_t *> cur, prev; std::vector<uint32_t *> stp; std::vector<uint32_t> first, npx;
+        for (size_t f = 0; f < b->frames.size(); f++) {
+            FrameRec &R = b->frames[f]; const StreamRec &S = b->streams[R.stream];
+            if (!R.key) continue;
+            const jsp_stream_desc &D = sd[R.stream];
+            const int64_t fi = (int64_t)f - S.first_frame;
+            if (fi == 0) {
+                R.forced |= ST_KEYDIFF;              // `next_frame_to_decode == 0` -> true (Manager.hx:410-411)
+            } else if (D.frame_key[fi - 1]) {
+                const uint32_t l0 = D.frame_len[fi - 1], l1 = D.frame_len[fi];
+                if (l0 != l1 || (l1 && memcmp(D.bytes + D.frame_off[fi - 1], D.bytes + D.frame_off[fi], l1) != 0)) R.forced |= ST_KEYDIFF;
+            } else {
+                const size_t np = (size_t)S.w * S.h;
+                cur.push_back(b->d_out + R.out_off); prev.push_back(b->d_out + b->frames[f - 1].out_off);
+                stp.push_back(b->d_status + f);
+                first.push_back((uint32_t)std::min<size_t>(np, (size_t)std::max(0, b->insign_lines) * S.w)); npx.push_back((uint32_t)np);
+            }
+        }
+        b->n_kd = cur.size();
+        if (b->n_kd > b->kd_cap) {
+            void *old[] = {b->d_kd_cur, b->d_kd_prev, b->d_kd_status, b->d_kd_first, b->d_kd_npx};
+            for (void *p : old) if (p) cudaFree(p);
+            const size_t n = b->n_kd + 64;
+            if (!JSP_CUDA(cudaMalloc((void **)&b->d_kd_cur, n * 8)) || !JSP_CUDA(cudaMalloc((void **)&b->d_kd_prev, n * 8)) ||
+                !JSP_CUDA(cudaMalloc((void **)&b->d_kd_status, n * 8)) || !JSP_CUDA(cudaMalloc((void **)&b->d_kd_first, n * 4)) ||
+                !JSP_CUDA(cudaMalloc((void **)&b->d_kd_npx, n * 4))) return -1;
+            b->kd_cap = n;
+        }
+        if (b->n_kd) {
+            cudaMemcpy(b->d_kd_cur, cur.data(), cur.size() * 8, cudaMemcpyHostToDevice);
+            cudaMemcpy(b->d_kd_prev, prev.data(), prev.size() * 8, cudaMemcpyHostToDevice);
+            cudaMemcpy(b->d_kd_status, stp.data(), stp.size() * 8, cudaMemcpyHostToDevice);
+            cudaMemcpy(b->d_kd_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(b->d_kd_npx, npx.data(), npx.size() * 4, cudaMemcpyHostToDevice);
+        }
+    }
     if (!JSP_CUDA(cudaGetLastError())) return -1;
     return nf;
 }
@@ -702,6 +745,7 @@ static uint8_t public_flags(uint32_t v)
     if (v & ST_CHANGED) f |= JSP_FRAME_CHANGED;
     if (v & ST_SIGNIFICANT) f |= JSP_FRAME_SIGNIFICANT;
     if (v & (ST_ERROR | ST_NEEDS_PREV)) f |= JSP_FRAME_ERROR;
+    if (v & ST_KEYDIFF) f |= JSP_FRAME_DIFFERS;
     return f;
 }
 
@@ -729,8 +773,10 @@ int jsp_batch_results(jsp_batch *b, uint8_t *flags)
 }
 
 // D2H of pictures [lo, hi) on stream st; adjacent host destinations are merged into one copy
-static bool download_range(jsp_batch *b, int64_t lo, int64_t hi, int32_t *const *out_frames, cudaStream_t st)
+static bool download_range(jsp_batch *b, int64_t lo, int64_t hi, int32_t *const *out_frames, cudaStream_t st,
+                           const int32_t *arena = nullptr)
 {
+    if (!arena) arena = b->d_out;
     int64_t i = lo;
     while (i < hi) {
         if (!out_frames[i]) { i++; continue; }
@@ -739,7 +785,7 @@ static bool download_range(jsp_batch *b, int64_t lo, int64_t hi, int32_t *const 
         const bool rem = S.codec != JSP_CODEC_SCREENPRESSOR && ((S.w & 3) || (S.h & 3));
         if (rem) {   // the codec never writes the width/height remainder mod 4: leave the caller's pixels alone
             const size_t bw = (size_t)(S.w & ~3), bh = (size_t)(S.h & ~3);
-            if (bw && bh && !JSP_CUDA(cudaMemcpy2DAsync(out_frames[i], (size_t)S.w * 4, b->d_out + R.out_off, (size_t)S.w * 4,
+            if (bw && bh && !JSP_CUDA(cudaMemcpy2DAsync(out_frames[i], (size_t)S.w * 4, arena + R.out_off, (size_t)S.w * 4,
                                                         bw * 4, bh, cudaMemcpyDeviceToHost, st))) return false;
             i++; continue;
         }
@@ -749,7 +795,7 @@ static bool download_range(jsp_batch *b, int64_t lo, int64_t hi, int32_t *const 
                !((b->streams[b->frames[j].stream].w & 3) || (b->streams[b->frames[j].stream].h & 3)) && bytes < ((size_t)1 << 30)) {
             bytes += (size_t)b->streams[b->frames[j].stream].w * b->streams[b->frames[j].stream].h * 4; j++;
         }
-        if (!JSP_CUDA(cudaMemcpyAsync(out_frames[i], b->d_out + R.out_off, bytes, cudaMemcpyDeviceToHost, st))) return false;
+        if (!JSP_CUDA(cudaMemcpyAsync(out_frames[i], arena + R.out_off, bytes, cudaMemcpyDeviceToHost, st))) return false;
         i = j;
     }
     return true;
@@ -761,6 +807,42 @@ int jsp_batch_download(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags)
     if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
     if (jsp_batch_results(b, flags)) return -1;
     if (out_frames && !download_range(b, 0, (int64_t)b->frames.size(), out_frames, b->st_compute)) return -1;
+    return JSP_CUDA(cudaStreamSynchronize(b->st_compute)) ? 0 : -1;
+}
+
+int jsp_batch_download_display(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags, int display_flags)
+{
+    if (!b || !out_frames) return -1;
+    if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
+    if (jsp_batch_results(b, flags)) return -1;
+    if (!grow(b->d_disp, b->disp_cap, b->out_used)) return -1;
+    std::vector<DisplayJob> jobs; uint32_t maxpx = 0;
+    for (size_t i = 0; i < b->frames.size(); i++) {
+        if (!out_frames[i]) continue;
+        const FrameRec &R = b->frames[i]; const StreamRec &S = b->streams[R.stream];
+        DisplayJob J;
+        J.src = b->d_out + R.out_off; J.dst = b->d_disp + R.out_off; J.X = (uint32_t)S.w; J.Y = (uint32_t)S.h;
+        J.from_rgb15 = (S.codec == JSP_CODEC_SCREENPRESSOR && S.bpp == 16) ? 1u : 0u;      // convert_fromRGB15, Manager.hx:120
+        J.flip = (display_flags & JSP_DISPLAY_FLIP) ? 1u : 0u;
+        maxpx = std::max(maxpx, J.X * J.Y);
+        jobs.push_back(J);
+    }
+    if (!grow(b->d_disp_jobs, b->disp_jobs_cap, jobs.size() + 1)) return -1;
+    if (!jobs.empty()) {
+        if (!JSP_CUDA(cudaMemcpyAsync(b->d_disp_jobs, jobs.data(), jobs.size() * sizeof(DisplayJob), cudaMemcpyHostToDevice, b->st_compute))) return -1;
+        launch_display(b->d_disp_jobs, (uint32_t)jobs.size(), maxpx, b->sm_count, b->st_compute);
+        if (!JSP_CUDA(cudaGetLastError())) return -1;
+        if (!JSP_CUDA(cudaStreamSynchronize(b->st_compute))) return -1;     // `jobs` is pageable host memory
+    }
+    // MSVideo1 pictures whose size is not a multiple of 4 are delivered whole here (the remainder shows as black)
+    std::vector<int32_t *> outs(out_frames, out_frames + b->frames.size());
+    int64_t i = 0; const int64_t n = (int64_t)b->frames.size();
+    while (i < n) {
+        if (!outs[i]) { i++; continue; }
+        const FrameRec &R = b->frames[i]; const StreamRec &S = b->streams[R.stream];
+        if (!JSP_CUDA(cudaMemcpyAsync(outs[i], b->d_disp + R.out_off, (size_t)S.w * S.h * 4, cudaMemcpyDeviceToHost, b->st_compute))) return -1;
+        i++;
+    }
     return JSP_CUDA(cudaStreamSynchronize(b->st_compute)) ? 0 : -1;
 }
 

@@ -135,6 +135,12 @@ struct jsp_batch {
     uint32_t *d_stream_first = nullptr, *d_stream_count = nullptr; size_t streams_cap = 0, streams_cap2 = 0;
     uint8_t *d_frame_codec = nullptr; size_t frame_codec_cap = 0;
     void *d_flush = nullptr; size_t flush_bytes = 0;
+    // key-frame change detection (Manager.frames_differ_significantly): pixel-compare jobs
+    const int32_t **d_kd_cur = nullptr; const int32_t **d_kd_prev = nullptr; uint32_t **d_kd_status = nullptr;
+    uint32_t *d_kd_first = nullptr, *d_kd_npx = nullptr; size_t kd_cap = 0, n_kd = 0;
+    // display epilogue
+    int32_t *d_disp = nullptr; size_t disp_cap = 0;
+    jsp::DisplayJob *d_disp_jobs = nullptr; size_t disp_jobs_cap = 0;
 
     uint32_t *h_status = nullptr; size_t h_status_cap = 0;   // pinned
 

@@ -15,6 +15,7 @@ enum : uint32_t {
     ST_NEEDS_PREV   = 1u << 4,   // a frame scheduled as a key frame copied from a previous picture it was not ordered after
     ST_SIGNIFICANT  = 1u << 5,   // final PFrameResult.significant_changes
     ST_HAS_PREV     = 1u << 6,   // codec's prevFrame was non-null when this frame was decoded
+    ST_KEYDIFF      = 1u << 7,   // key frame differs significantly from the picture before it (Manager.hx:392-421)
 };
 
 // ---- MSVideo1 ----
@@ -59,7 +60,18 @@ void launch_msv1_decode(bool is8, const Msv1Frame *d_frames, const uint2 *d_tile
                         unsigned int *d_ticket, cudaStream_t st);
 void launch_frame_copy(const CopyJob *d_jobs, uint32_t n_jobs, uint32_t max_vec4, int sm_count, cudaStream_t st);
 void launch_signif(const int32_t *const *d_cur, const int32_t *const *d_prev, uint32_t *const *d_status,
-                   const uint32_t *d_first_px, const uint32_t *d_npx, uint32_t n_jobs, int sm_count, cudaStream_t st);
+                   const uint32_t *d_first_px, const uint32_t *d_npx, uint32_t n_jobs, int sm_count, cudaStream_t st,
+                   bool key_frames = false);
+
+// display epilogue (Manager.fill_bitmap_data, Manager.hx:363-381 + the render-time flip of Main.hx:946)
+struct DisplayJob {
+    const int32_t *src;
+    int32_t       *dst;
+    uint32_t X, Y;
+    uint32_t from_rgb15;     // ScreenPressor at 16 bpp: 0xFF000000 | (c << 3) instead of the R/B swap
+    uint32_t flip;
+};
+void launch_display(const DisplayJob *d_jobs, uint32_t n_jobs, uint32_t max_pixels, int sm_count, cudaStream_t st);
 
 void launch_status_scan(uint32_t *d_status, const uint32_t *d_stream_first, const uint32_t *d_stream_count,
                         uint32_t n_streams, int init_has_prev, cudaStream_t st);

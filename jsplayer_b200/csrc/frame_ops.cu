@@ -44,6 +44,8 @@ frame_copy_kernel(const CopyJob *__restrict__ jobs)
 }
 
 // MSVideo1.hx:195-204: does any pixel from `first_px` on differ from the previous picture?
+// KEY: the same compare for key frames as Manager.frames_differ_significantly does it (Manager.hx:413-419)
+template <bool KEY>
 __global__ void __launch_bounds__(256)
 signif_kernel(const int32_t *const *__restrict__ cur, const int32_t *const *__restrict__ prev,
               uint32_t *const *__restrict__ status, const uint32_t *__restrict__ first_px,
@@ -52,13 +54,41 @@ signif_kernel(const int32_t *const *__restrict__ cur, const int32_t *const *__re
     const uint32_t j = blockIdx.y;
     // only frames that pass the block-row test and had a previous picture reach the pixel compare
     const uint32_t stv = *status[j];
-    if ((stv & (ST_SIGNIF_ROWS | ST_HAS_PREV)) != (ST_SIGNIF_ROWS | ST_HAS_PREV)) return;
+    if (!KEY && (stv & (ST_SIGNIF_ROWS | ST_HAS_PREV)) != (ST_SIGNIF_ROWS | ST_HAS_PREV)) return;
     const int32_t *c = cur[j], *p = prev[j];
     const uint32_t n = npx[j];
     bool diff = false;
     for (uint32_t i = first_px[j] + blockIdx.x * 256 + threadIdx.x; i < n && !diff; i += gridDim.x * 256)
         diff = c[i] != p[i];
-    if (__syncthreads_or(diff) && threadIdx.x == 0) atomicOr(status[j], ST_PIXDIFF);
+    if (__syncthreads_or(diff) && threadIdx.x == 0) atomicOr(status[j], KEY ? ST_KEYDIFF : ST_PIXDIFF);
+}
+
+// Manager.fill_bitmap_data (canvas branch, Manager.hx:363-381): 0x00RRGGBB -> Int32 view of canvas bytes R,G,B,A.
+// grid = (chunks, jobs); one thread converts 4 horizontally adjacent pixels (16-byte load / store when X % 4 == 0).
+__global__ void __launch_bounds__(256)
+display_kernel(const DisplayJob *__restrict__ jobs)
+{
+    const DisplayJob J = jobs[blockIdx.y];
+    const uint32_t X = J.X, Y = J.Y;
+    auto conv = [&](uint32_t c) -> uint32_t {
+        return J.from_rgb15 ? (0xFF000000u | (c << 3)) : (0xFF000000u | __byte_perm(c, 0, 0x4012));   // bytes (B,G,R,x) -> (R,G,B,x)
+    };
+    if ((X & 3u) == 0) {
+        const uint32_t xv = X >> 2, n = xv * Y;
+        for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+            const uint32_t y = i / xv, x4 = i - y * xv;
+            const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(J.src + (size_t)y * X) + x4);
+            const uint32_t yo = J.flip ? Y - 1 - y : y;
+            __stcs(reinterpret_cast<uint4 *>(J.dst + (size_t)yo * X) + x4, make_uint4(conv(v.x), conv(v.y), conv(v.z), conv(v.w)));
+        }
+    } else {
+        const uint32_t n = X * Y;
+        for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+            const uint32_t y = i / X, x = i - y * X;
+            const uint32_t yo = J.flip ? Y - 1 - y : y;
+            J.dst[(size_t)yo * X + x] = (int32_t)conv((uint32_t)J.src[i]);
+        }
+    }
 }
 
 // prevFrame is non-null for frame f <=> some earlier frame of the stream altered pixels
@@ -122,15 +152,30 @@ void launch_frame_copy(const CopyJob *d_jobs, uint32_t n_jobs, uint32_t max_vec4
     }
 }
 
+void launch_display(const DisplayJob *d_jobs, uint32_t n_jobs, uint32_t max_pixels, int sm_count, cudaStream_t st)
+{
+    if (n_jobs == 0 || max_pixels == 0) return;
+    uint32_t chunks = (max_pixels / 4 + 255) / 256;
+    const uint32_t cap = ((uint32_t)sm_count * 16u + n_jobs - 1) / n_jobs;
+    if (chunks > cap) chunks = cap;
+    if (chunks == 0) chunks = 1;
+    for (uint32_t j0 = 0; j0 < n_jobs; j0 += 65535u) {
+        const uint32_t nj = n_jobs - j0 < 65535u ? n_jobs - j0 : 65535u;
+        display_kernel<<<dim3(chunks, nj), 256, 0, st>>>(d_jobs + j0);
+    }
+}
+
 void launch_signif(const int32_t *const *d_cur, const int32_t *const *d_prev, uint32_t *const *d_status,
-                   const uint32_t *d_first_px, const uint32_t *d_npx, uint32_t n_jobs, int sm_count, cudaStream_t st)
+                   const uint32_t *d_first_px, const uint32_t *d_npx, uint32_t n_jobs, int sm_count, cudaStream_t st,
+                   bool key_frames)
 {
     if (n_jobs == 0) return;
     uint32_t chunks = ((uint32_t)sm_count * 8u + n_jobs - 1) / n_jobs;
     if (chunks == 0) chunks = 1;
     for (uint32_t j0 = 0; j0 < n_jobs; j0 += 65535u) {
         const uint32_t nj = n_jobs - j0 < 65535u ? n_jobs - j0 : 65535u;
-        signif_kernel<<<dim3(chunks, nj), 256, 0, st>>>(d_cur + j0, d_prev + j0, d_status + j0, d_first_px + j0, d_npx + j0);
+        if (key_frames) signif_kernel<true><<<dim3(chunks, nj), 256, 0, st>>>(d_cur + j0, d_prev + j0, d_status + j0, d_first_px + j0, d_npx + j0);
+        else signif_kernel<false><<<dim3(chunks, nj), 256, 0, st>>>(d_cur + j0, d_prev + j0, d_status + j0, d_first_px + j0, d_npx + j0);
     }
 }
 

@@ -106,6 +106,66 @@ static void decode_stream_impl(ora_dec *d, int n_frames, const uint8_t *bytes, c
 int ora_decode_stream(int codec, int width, int height, int bpp, const uint8_t *palette, int palette_bytes,
                       int insignificant_lines, int n_frames, const uint8_t *bytes, const uint64_t *frame_off,
                       const uint32_t *frame_len, const uint8_t *frame_key,
+                      int32_t *out, uint8_t *changed, uint8_t *significant, int32_t *status);
+
+/* ---- the caller's side of the path (reference src/Manager.hx), restated for the "next" rows of SURVEY.md 8f ---- */
+
+/* Manager.fill_bitmap_data, canvas branch (Manager.hx:363-381): 0x00RRGGBB -> the Int32 view of canvas bytes R,G,B,A
+ * with alpha 255; ScreenPressor at 16 bpp stores 5-bit channels and is shifted instead (convert_fromRGB15,
+ * Manager.hx:120,366-370).  flip: the vertical flip Main applies at render time (Main.hx:318,946). */
+void ora_display_convert(const int32_t *src, int32_t *dst, int X, int Y, int from_rgb15, int flip)
+{
+    for (int y = 0; y < Y; y++) {
+        const int32_t *s = src + (size_t)y * X;
+        int32_t *d = dst + (size_t)(flip ? Y - 1 - y : y) * X;
+        for (int x = 0; x < X; x++) {
+            const uint32_t c = (uint32_t)s[x];
+            d[x] = (int32_t)(from_rgb15 ? (0xFF000000u | (c << 3))
+                                        : (0xFF000000u | ((c & 0xFF) << 16) | (c & 0xFF00) | ((c >> 16) & 0xFF)));
+        }
+    }
+}
+
+/* Manager.frames_differ_significantly (Manager.hx:392-421) for key frame n of a stream: prev_key / prev_data = the
+ * previous frame record, pnt1 = the new picture, pnt2 = the picture shown before it (NULL: nothing yet -> the
+ * reference would throw; defined as "differs"). */
+int ora_frames_differ(int n, int prev_key, const uint8_t *prev_data, int prev_len, const uint8_t *cur_data, int cur_len,
+                      const int32_t *pnt1, const int32_t *pnt2, int X, int Y, int insignificant_lines)
+{
+    if (n > 0) {
+        if (prev_key && prev_data) {
+            if (prev_len == cur_len) return memcmp(prev_data, cur_data, (size_t)cur_len) != 0;
+            return 1;
+        }
+    } else return 1;
+    if (!pnt2) return 1;
+    for (size_t i = (size_t)insignificant_lines * X; i < (size_t)X * Y; i++)
+        if (pnt1[i] != pnt2[i]) return 1;
+    return 0;
+}
+
+/* ora_decode_stream + differs[f] = Manager's significance of key frame f (0 for non-key frames) */
+int ora_decode_stream_differs(int codec, int width, int height, int bpp, const uint8_t *palette, int palette_bytes,
+                              int insignificant_lines, int n_frames, const uint8_t *bytes, const uint64_t *frame_off,
+                              const uint32_t *frame_len, const uint8_t *frame_key, int32_t *out, uint8_t *differs)
+{
+    const size_t npix = (size_t)width * height;
+    ora_decode_stream(codec, width, height, bpp, palette, palette_bytes, insignificant_lines, n_frames, bytes, frame_off,
+                      frame_len, frame_key, out, NULL, NULL, NULL);
+    for (int f = 0; f < n_frames; f++) {
+        differs[f] = 0;
+        if (!frame_key[f]) continue;
+        differs[f] = (uint8_t)ora_frames_differ(f, f > 0 ? frame_key[f - 1] : 0, f > 0 ? bytes + frame_off[f - 1] : NULL,
+                                                f > 0 ? (int)frame_len[f - 1] : 0, bytes + frame_off[f], (int)frame_len[f],
+                                                out + (size_t)f * npix, f > 0 ? out + (size_t)(f - 1) * npix : NULL,
+                                                width, height, insignificant_lines);
+    }
+    return 0;
+}
+
+int ora_decode_stream(int codec, int width, int height, int bpp, const uint8_t *palette, int palette_bytes,
+                      int insignificant_lines, int n_frames, const uint8_t *bytes, const uint64_t *frame_off,
+                      const uint32_t *frame_len, const uint8_t *frame_key,
                       int32_t *out, uint8_t *changed, uint8_t *significant, int32_t *status)
 {
     ora_dec *d = ora_create(codec, width, height, bpp, palette, palette_bytes);

@@ -50,6 +50,9 @@ def load():
         lib.ora_decode_stream.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]
+        lib.ora_display_convert.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.ora_decode_stream_differs.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ora_decode_streams_mt.restype = C.c_double
         lib.ora_decode_streams_mt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         _lib = lib
@@ -129,3 +132,30 @@ def decode_stream(codec, width, height, bpp, frames, keys=None, palette=None, in
                           off.ctypes.data, ln.ctypes.data, k.ctypes.data, out.ctypes.data, changed.ctypes.data,
                           signif.ctypes.data, status.ctypes.data)
     return out, changed, signif, status
+
+
+def display_convert(pic, from_rgb15=False, flip=False):
+    """Manager.fill_bitmap_data (canvas branch) + optional render-time flip; pic: (h, w) int32."""
+    pic = np.ascontiguousarray(pic, dtype=np.int32)
+    out = np.empty_like(pic)
+    load().ora_display_convert(pic.ctypes.data, out.ctypes.data, pic.shape[1], pic.shape[0], int(from_rgb15), int(flip))
+    return out
+
+
+def key_frame_differs(codec, width, height, bpp, frames, keys, palette=None, insignificant_lines=0):
+    """Manager.frames_differ_significantly for every key frame of the stream (0 for the others)."""
+    lib = load()
+    n = len(frames)
+    ln = np.array([len(f) for f in frames], dtype=np.uint32)
+    off = np.zeros(n, dtype=np.uint64)
+    if n:
+        off[1:] = np.cumsum(ln.astype(np.uint64))[:-1]
+    blob = np.frombuffer(b"".join(bytes(f) for f in frames) + b"\0", dtype=np.uint8).copy()
+    k = np.asarray(keys, dtype=np.uint8).copy()
+    pal = _u8(palette) if palette else None
+    out = np.zeros((n, height, width), dtype=np.int32)
+    differs = np.zeros(n, dtype=np.uint8)
+    lib.ora_decode_stream_differs(codec, width, height, bpp, pal.ctypes.data if pal is not None else None,
+                                  pal.size if pal is not None else 0, insignificant_lines, n, blob.ctypes.data,
+                                  off.ctypes.data, ln.ctypes.data, k.ctypes.data, out.ctypes.data, differs.ctypes.data)
+    return differs

@@ -117,3 +117,15 @@ def test_significance_16bit():
     assert list(ch) == [1, 1] and list(sg) == [1, 0]
     out, ch, sg, st = O.decode_stream(O.CODEC_MSVC16, w, h, 16, [f0, f1], keys=[0, 0], insignificant_lines=0)
     assert list(sg) == [1, 1]
+
+
+def test_display_convert_kat():
+    """Manager.hx:379: 0x00RRGGBB -> 0xFF000000 | B << 16 | G << 8 | R (the Int32 view of canvas bytes R,G,B,A);
+    Manager.hx:369: ScreenPressor 16 bpp -> 0xFF000000 | c << 3; flip = Main.hx:946."""
+    a = np.array([[0x00112233, 0x00AABBCC], [0x00000001, 0x00FF0000]], dtype=np.int32)
+    d = O.display_convert(a).view(np.uint32)
+    assert d.tolist() == [[0xFF332211, 0xFFCCBBAA], [0xFF010000, 0xFF0000FF]]
+    d = O.display_convert(a, flip=True).view(np.uint32)
+    assert d.tolist() == [[0xFF010000, 0xFF0000FF], [0xFF332211, 0xFFCCBBAA]]
+    r = np.array([[0x001F1F1F, 0x00010203]], dtype=np.int32)
+    assert O.display_convert(r, from_rgb15=True).view(np.uint32).tolist() == [[0xFFF8F8F8, 0xFF081018]]
