@@ -57,13 +57,17 @@ struct RcState {                                               // per stream, in
     uint32_t *rows;                                            // RC_ROWS * RC_ROW_STRIDE u32, separately allocated
 };
 
-// floor(a / b) for b <= 2^17 (a table total): float reciprocal estimate, one refinement, exact fix-up loops
+// floor(a / b) for 5 <= b <= 2^17 (a table total), rb = fl(1 / b).  The float estimate is within 2^10 / b + 1 of the
+// quotient, so |rem| < 2^24 is exact in float and one refinement lands within one of the quotient; the two
+// predicated corrections make it exact (the trailing loops never run; they keep the result exact by construction).
 __device__ __forceinline__ uint32_t udiv_small(uint32_t a, uint32_t b, float rb)
 {
     uint32_t q = __float2uint_rz(__uint2float_rz(a) * rb);
     int32_t rem = (int32_t)(a - q * b);
     const int32_t adj = __float2int_rd(__int2float_rn(rem) * rb);
     q += (uint32_t)adj; rem -= adj * (int32_t)b;
+    if (rem < 0) { q--; rem += (int32_t)b; }
+    if (rem >= (int32_t)b) { q++; rem -= (int32_t)b; }
     while (rem < 0) { q--; rem += (int32_t)b; }
     while (rem >= (int32_t)b) { q++; rem -= (int32_t)b; }
     return q;
@@ -163,8 +167,7 @@ struct RcCoder {
             p = c;
             t.P[lane] = p;
         } else if (lane >= s) t.P[lane] = p;
-        __syncwarp();
-        return s;
+        return s;                                              // a lane reads back only its own P[lane]: no barrier needed
     }
 
     // RangeCoder.hx:51-80 (256 / 512 symbols) and :82-130 (colour rows; the 16 group sums are derived data)
@@ -195,18 +198,33 @@ struct RcCoder {
         const uint32_t r = udiv_small(range, tot, __frcp_rn(__uint2float_rn(tot)));
         const uint32_t codev = poisoned ? 0u : code;
         const uint32_t br = base * r;
+        if (codev >= tot * r) { range = r; fail = true; return 32 * K - 1; }     // value >= total: not a valid stream
         const int L = __popc(__ballot_sync(FULLMASK, br <= codev)) - 1;          // lane 0 has base 0: L >= 0
         const uint32_t t = codev - br;                                           // meaningful in lane L only
-        uint32_t lo = 0, hi = 0; int m = 0; bool open = true;
+        // in lane L the symbol's inclusive prefix exceeds t (the next lane's base is above the value), so
+        // m = #{q : lp[q] * r <= t} is at most K - 1: a binary search over lp[0 .. K-2] finds it together with
+        // the two neighbouring products lo = lp[m-1] * r (0 if m = 0) and hi = lp[m] * r
+        uint32_t lo = 0, hi = lp[K - 1] * r; int m = 0;
+        if constexpr (K == 8) {
+            const uint32_t pa = lp[3] * r; const bool a = pa <= t;
+            if (a) lo = pa; else hi = pa;
+            const uint32_t pb = (a ? lp[5] : lp[1]) * r; const bool bq = pb <= t;
+            if (bq) lo = pb; else hi = pb;
+            const uint32_t v = bq ? (a ? lp[6] : lp[2]) : (a ? lp[4] : lp[0]);
+            const uint32_t pc = v * r; const bool c = pc <= t;
+            if (c) lo = pc; else hi = pc;
+            m = (a ? 4 : 0) + (bq ? 2 : 0) + (c ? 1 : 0);
+        } else {
+            bool open = true;
 #pragma unroll
-        for (int q = 0; q < K; q++) {
-            const uint32_t pr = lp[q] * r;
-            const bool le = pr <= t;
-            if (le) { lo = pr; m++; }
-            else if (open) { hi = pr; open = false; }
+            for (int q = 0; q < K - 1; q++) {
+                const uint32_t pr = lp[q] * r;
+                const bool le = pr <= t;
+                if (le) { lo = pr; m++; }
+                else if (open) { hi = pr; open = false; }
+            }
         }
         const int mL = __shfl_sync(FULLMASK, m, L);
-        if (mL >= K) { range = r; fail = true; return 32 * K - 1; }             // value >= total: not a valid stream
         const uint32_t lo_abs = __shfl_sync(FULLMASK, br + lo, L), width = __shfl_sync(FULLMASK, hi - lo, L);
         consume(lo_abs, width);
         tot += step;
@@ -233,11 +251,9 @@ struct RcCoder {
             for (int q = 0; q < K / 4; q++) o4[q] = make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
         }
         if (all || lane > L) tab[32 * K + lane] = base;
-        if (lane == 0) {
-            if (IS_ROW) *reinterpret_cast<uint2 *>(tab + 32 * K + 32) = make_uint2(tot, gen);
-            else tab[32 * K + 32] = tot;
-        }
-        __syncwarp();
+        // every lane writes the (identical) total: a lane only ever reads back what it wrote itself, no barrier needed
+        if (IS_ROW) *reinterpret_cast<uint2 *>(tab + 32 * K + 32) = make_uint2(tot, gen);
+        else tab[32 * K + 32] = tot;
         return L * K + mL;
     }
 
