@@ -143,7 +143,7 @@ static void classify_sp(const StreamRec &S, SpHost &H, FrameRec &R, const uint8_
 
 struct HostTables {
     std::vector<Msv1Frame> mframes;
-    std::vector<uint2> tile_tab;
+    std::vector<Msv1Tile> tile_tab;
     std::vector<CopyJob> jobs;
     std::vector<SpJob> spjobs;
 };
@@ -205,7 +205,15 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             size_t live = fr.size();
             for (uint32_t t = 0; t < max_tiles; t++) {
                 while (live > 0 && b->frames[fr[live - 1]].n_tiles <= t) live--;
-                for (size_t i = 0; i < live; i++) T.tile_tab.push_back(make_uint2((uint32_t)fr[i] + mframe_base, t));
+                for (size_t i = 0; i < live; i++) {
+                    const FrameRec &R = b->frames[fr[i]];
+                    const size_t byte0 = (size_t)t * MSV1_TILE_BYTES;
+                    Msv1Tile e;
+                    e.src = b->d_bytes + R.d_src + byte0;
+                    e.avail = R.len > byte0 ? (uint32_t)std::min<size_t>(MSV1_STAGE_BYTES, R.len - byte0) : 0u;
+                    e.frame = (uint32_t)fr[i] + mframe_base;
+                    T.tile_tab.push_back(e);
+                }
             }
             plan.launches.push_back({JSP_K_MSV1_DECODE, kind, first, (uint32_t)(T.tile_tab.size() - first), 0, (uint32_t)ticket_cursor});
             ticket_cursor++;
@@ -305,7 +313,7 @@ static bool upload_tables(jsp_batch *b, HostTables &T, size_t n_states, size_t n
     }
     if (!grow(b->d_tickets, b->tickets_cap, n_tickets + 1)) return false;
     if (!T.mframes.empty() && !JSP_CUDA(cudaMemcpy(b->d_mframes, T.mframes.data(), T.mframes.size() * sizeof(Msv1Frame), cudaMemcpyHostToDevice))) return false;
-    if (!T.tile_tab.empty() && !JSP_CUDA(cudaMemcpy(b->d_tile_tab, T.tile_tab.data(), T.tile_tab.size() * sizeof(uint2), cudaMemcpyHostToDevice))) return false;
+    if (!T.tile_tab.empty() && !JSP_CUDA(cudaMemcpy(b->d_tile_tab, T.tile_tab.data(), T.tile_tab.size() * sizeof(Msv1Tile), cudaMemcpyHostToDevice))) return false;
     if (!T.jobs.empty() && !JSP_CUDA(cudaMemcpy(b->d_jobs, T.jobs.data(), T.jobs.size() * sizeof(CopyJob), cudaMemcpyHostToDevice))) return false;
     if (!grow(b->d_spjobs, b->spjobs_cap, T.spjobs.size() + 1)) return false;
     if (!T.spjobs.empty() && !JSP_CUDA(cudaMemcpy(b->d_spjobs, T.spjobs.data(), T.spjobs.size() * sizeof(SpJob), cudaMemcpyHostToDevice))) return false;
@@ -330,7 +338,7 @@ static bool run_plan(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *
             break;
         case JSP_K_MSV1_DECODE:
             launch_msv1_decode(L.kind == FK_MSV8, b->d_mframes, b->d_tile_tab + L.first, L.count,
-                               b->d_tile_map, b->d_tile_cnt, b->d_tickets + L.ticket, st);
+                               b->d_tile_map, b->d_tile_cnt, b->d_tickets + L.ticket, b->sm_count, st);
             break;
         case JSP_K_SP_ENTROPY_RC:
             launch_sp_rc(b->d_spjobs + L.first, L.count, st);

@@ -118,7 +118,7 @@ struct jsp_batch {
     int32_t *d_pal = nullptr;     size_t pal_cap = 0;
     uint32_t *d_status = nullptr; size_t status_cap = 0;
     jsp::Msv1Frame *d_mframes = nullptr; size_t mframes_cap = 0;
-    uint2 *d_tile_tab = nullptr;  size_t tile_tab_cap = 0;
+    jsp::Msv1Tile *d_tile_tab = nullptr;  size_t tile_tab_cap = 0;
     jsp::CopyJob *d_jobs = nullptr; size_t jobs_cap = 0;
     unsigned long long *d_tile_map = nullptr, *d_tile_cnt = nullptr; size_t states_cap = 0;
     unsigned int *d_tickets = nullptr; size_t tickets_cap = 0;

@@ -38,6 +38,14 @@ struct Msv1Frame {
     uint32_t insign_blocks;  // (insignificant_lines+3)>>2
     uint32_t flags;          // MSV1_F_*
     uint32_t inv_nbx;        // floor(2^32 / nbx): block row = umulhi(block, inv_nbx) (+1 fix-up)
+    uint32_t pad;            // sizeof == 80: copied to shared memory in 16-byte units
+};
+
+// one 4 KiB bitstream tile of a frame, in launch (ticket) order: everything the prefetch needs in ONE 16-byte load
+struct Msv1Tile {
+    const uint8_t *src;      // first byte of the tile (device)
+    uint32_t avail;          // bytes of the frame from there on, capped at MSV1_STAGE_BYTES
+    uint32_t frame;          // index into the frame descriptor table
 };
 
 // whole-picture copy / fill jobs (unchanged frames, flat frames, P-frame pre-copies)
@@ -55,9 +63,9 @@ constexpr int MSV1_TILE_BYTES = MSV1_TILE_WORDS * 2;                  // 4096
 constexpr int MSV1_STAGE_BYTES = MSV1_TILE_BYTES + 32;                // + look-ahead for an opcode that starts in the last word
 
 // host-callable launchers (implemented in the .cu files)
-void launch_msv1_decode(bool is8, const Msv1Frame *d_frames, const uint2 *d_tile_tab, uint32_t n_ctas,
+void launch_msv1_decode(bool is8, const Msv1Frame *d_frames, const Msv1Tile *d_tiles, uint32_t n_tiles,
                         unsigned long long *d_tile_map, unsigned long long *d_tile_cnt,
-                        unsigned int *d_ticket, cudaStream_t st);
+                        unsigned int *d_ticket, int sm_count, cudaStream_t st);
 void launch_frame_copy(const CopyJob *d_jobs, uint32_t n_jobs, uint32_t max_vec4, int sm_count, cudaStream_t st);
 void launch_signif(const int32_t *const *d_cur, const int32_t *const *d_prev, uint32_t *const *d_status,
                    const uint32_t *d_first_px, const uint32_t *d_npx, uint32_t n_jobs, int sm_count, cudaStream_t st,

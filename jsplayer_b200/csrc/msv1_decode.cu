@@ -87,6 +87,8 @@ __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
 }
 __device__ __forceinline__ uint32_t rgb15(uint32_t c)
 {
+    // measured alternative: isolating the fields with multiply / multiply-high pairs (no ALU-pipe masks at all) costs
+    // two more instructions per colour and is 5 % slower -- the kernel is bound by issue slots, not by one pipe
     return mad_u32(c & 0x7C00u, 512u, mad_u32(c & 0x3E0u, 64u, (c & 0x1Fu) * 8u));
 }
 __device__ __forceinline__ uint32_t rgb15_hi(uint32_t x)
@@ -114,7 +116,9 @@ __device__ __forceinline__ uint4 ld_global_cs(const void *p)
 }
 
 struct Smem {
-    alignas(16) uint8_t bytes[MSV1_STAGE_BYTES];
+    alignas(16) uint8_t stage[2][MSV1_STAGE_BYTES];   // double-buffered bitstream tiles (cp.async prefetch)
+    alignas(16) Msv1Frame fd[2];                        // frame descriptors of the two staged tiles
+    uint32_t tk[4];                                     // tickets handed from thread 0 to the CTA
     uint32_t blk[MSV1_TILE_WORDS];     // absolute block index of opcode k
     uint16_t pos[MSV1_TILE_WORDS];     // word position in the tile | 0x8000 for copy runs
     uint16_t runs[MSV1_TILE_WORDS];    // opcode indices of the short skip runs
@@ -178,78 +182,116 @@ __device__ __forceinline__ void copy_block(int32_t *out, const int32_t *prev, ui
     }
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(__cvta_generic_to_global(gsrc)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Starts the copy of one bitstream tile (+32 B look-ahead, zero-filled past the end of the frame) and of its frame
+// descriptor into shared memory.  16-byte aligned full chunks travel as cp.async (no registers, no waiting);
+// the rare unaligned / trailing chunks are assembled from 32-bit loads.
+__device__ __forceinline__ void stage_tile(const Msv1Tile &e, const Msv1Frame *frames, uint8_t *dst, Msv1Frame *fd, uint32_t tid)
+{
+    const uint8_t *g = e.src;
+    const int avail = (int)e.avail;
+    const bool aligned = (reinterpret_cast<uintptr_t>(g) & 15u) == 0;
+    uint4 *s4 = reinterpret_cast<uint4 *>(dst);
+    for (int c = tid; c < MSV1_STAGE_BYTES / 16; c += MSV1_THREADS) {
+        const int b0 = c * 16;
+        if (aligned && b0 + 16 <= avail) { cp_async16(s4 + c, g + b0); continue; }
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (b0 < avail) {
+            // unaligned source or the chunk straddles the end: assemble from aligned 32-bit words
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int o = b0 + 4 * k;
+                uint32_t val = 0;
+                if (o < avail) {
+                    const uintptr_t addr = reinterpret_cast<uintptr_t>(g + o);
+                    const uint32_t *ga = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+                    const uint32_t sh = (uint32_t)(addr & 3u) * 8u;
+                    const uint32_t lo = __ldg(ga);
+                    const uint32_t hi = (sh != 0 && o + 4 - (int)(sh >> 3) < avail) ? __ldg(ga + 1) : 0u;
+                    val = __funnelshift_r(lo, hi, sh);
+                    const int rem = avail - o;
+                    if (rem < 4) val &= (1u << (8 * rem)) - 1u;
+                }
+                w[k] = val;
+            }
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        s4[c] = v;
+    }
+    static_assert(sizeof(Msv1Frame) % 16 == 0, "Msv1Frame is copied in 16-byte units");
+    if (tid < sizeof(Msv1Frame) / 16)
+        cp_async16(reinterpret_cast<uint4 *>(fd) + tid, reinterpret_cast<const uint4 *>(frames + e.frame) + tid);
+}
+
+// Persistent CTAs: a CTA works through tickets (tiles in table order).  While it decodes tile T0 the bitstream and
+// descriptor of T1 are in flight (cp.async into the other shared-memory buffer), the table entry of T2 is in
+// flight in registers and the atomic for T3's ticket has been issued -- the four dependent global latencies a tile
+// needs before its first instruction are all hidden behind the previous tile's work.  `depth0` (small launches:
+// one tile per CTA, nothing held back) keeps the look-back chain of a single frame short.
 template <bool IS8>
 __global__ void __launch_bounds__(MSV1_THREADS)
-msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict__ tile_tab,
+msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restrict__ tiles, uint32_t n_tiles, int depth0,
                    u64 *__restrict__ tile_map, u64 *__restrict__ tile_cnt, unsigned int *__restrict__ ticket)
 {
     constexpr int NENT = IS8 ? 5 : 9;      // possible entry offsets into a segment (longest opcode: 5 / 9 words)
     __shared__ Smem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t FULL = 0xffffffffu;
+    const uint32_t NONE = 0xFFFFFFFFu;
 
-    // ---- work assignment: tickets hand tiles out in table order, so every tile a CTA may wait for has
-    //      already been started by a CTA that never waits for a later one (forward progress) ----
+    // ---- work assignment: tickets hand tiles out in table order, so every tile a CTA may wait for is held by a
+    //      resident CTA that only ever waits for lower tickets (forward progress) ----
     if (tid == 0) {
-        sm.ticket = atomicAdd(ticket, 1u);
-        sm.nruns = 0; sm.big_blk0 = 0xFFFFFFFFu; sm.flags = 0; sm.terminated = 0; sm.any_runs = 0;
+        sm.tk[0] = atomicAdd(ticket, 1u);
+        sm.tk[1] = depth0 ? NONE : atomicAdd(ticket, 1u);
+        sm.tk[2] = depth0 ? NONE : atomicAdd(ticket, 1u);
     }
     __syncthreads();
-    const uint2 tt = tile_tab[sm.ticket];
-    const Msv1Frame F = frames[tt.x];
-    const uint32_t tile = tt.y;
+    uint32_t tk0 = sm.tk[0], tk1 = sm.tk[1], tk2 = sm.tk[2];
+    if (tk0 >= n_tiles) return;
+    Msv1Tile e0 = tiles[tk0], e1 = e0, e2 = e0;
+    if (tk1 < n_tiles) e1 = tiles[tk1];
+    if (tk2 < n_tiles) e2 = tiles[tk2];
+    stage_tile(e0, frames, sm.stage[0], &sm.fd[0], tid);
+    cp_async_commit();
+    int cur = 0;
+  for (;;) {
+    uint32_t tk3 = NONE;
+    if (tid == 0) {
+        if (!depth0 && tk2 < n_tiles) tk3 = atomicAdd(ticket, 1u);       // consumed at the end of this tile
+        sm.nruns = 0; sm.big_blk0 = 0xFFFFFFFFu; sm.flags = 0; sm.terminated = 0; sm.any_runs = 0;
+    }
+    if (tk1 < n_tiles) stage_tile(e1, frames, sm.stage[cur ^ 1], &sm.fd[cur ^ 1], tid);
+    cp_async_commit();
+    cp_async_wait<1>();                    // everything but the group just committed has landed: this tile is in
+    __syncthreads();
+    uint8_t *const sbytes = sm.stage[cur];
+    const Msv1Frame &F = sm.fd[cur];
     const uint32_t len = F.len, X = F.X, nbx = F.nbx, nblocks = F.nblocks;
+    const uint32_t tile = (uint32_t)((e0.src - F.src) / MSV1_TILE_BYTES);
     const uint32_t tile_byte0 = tile * MSV1_TILE_BYTES;
     const uint32_t n_words = (len + 1u) >> 1;                      // an odd trailing byte is a half word (see below)
     const uint32_t tile_words = n_words > tile * MSV1_TILE_WORDS
                                     ? min((uint32_t)MSV1_TILE_WORDS, n_words - tile * MSV1_TILE_WORDS) : 0u;
     const bool vec_ok = ((X & 3u) == 0) && ((reinterpret_cast<uintptr_t>(F.out) & 15u) == 0) &&
                         ((reinterpret_cast<uintptr_t>(F.prev) & 15u) == 0);
-
-    // ---- stage the tile (+32 B look-ahead) into shared memory, zero-filled past the end of the frame ----
-    {
-        const uint8_t *g = F.src + tile_byte0;
-        const int avail = (int)min((uint32_t)MSV1_STAGE_BYTES, len > tile_byte0 ? len - tile_byte0 : 0u);
-        const bool aligned = (reinterpret_cast<uintptr_t>(g) & 15u) == 0;
-        uint4 *s4 = reinterpret_cast<uint4 *>(sm.bytes);
-        for (int c = tid; c < MSV1_STAGE_BYTES / 16; c += MSV1_THREADS) {
-            const int b0 = c * 16;
-            uint4 v;
-            if (aligned && b0 + 16 <= avail) {
-                v = ld_global_cs(g + b0);
-            } else if (b0 >= avail) {
-                v = make_uint4(0, 0, 0, 0);
-            } else {
-                // unaligned source or the chunk straddles the end: assemble from aligned 32-bit words
-                uint32_t w[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int o = b0 + 4 * k;
-                    uint32_t val = 0;
-                    if (o < avail) {
-                        const uintptr_t addr = reinterpret_cast<uintptr_t>(g + o);
-                        const uint32_t *ga = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
-                        const uint32_t sh = (uint32_t)(addr & 3u) * 8u;
-                        const uint32_t lo = __ldg(ga);
-                        const uint32_t hi = (sh != 0 && o + 4 - (int)(sh >> 3) < avail) ? __ldg(ga + 1) : 0u;
-                        val = __funnelshift_r(lo, hi, sh);
-                        const int rem = avail - o;
-                        if (rem < 4) val &= (1u << (8 * rem)) - 1u;
-                    }
-                    w[k] = val;
-                }
-                v = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            s4[c] = v;
-        }
-        if (IS8) for (int i = tid; i < 256; i += MSV1_THREADS) sm.pal[i] = F.pal ? F.pal[i] : 0;
+    if (IS8) {
+        for (int i = tid; i < 256; i += MSV1_THREADS) sm.pal[i] = F.pal ? F.pal[i] : 0;
+        __syncthreads();
     }
-    __syncthreads();
     // An odd frame length leaves a half word {a, undefined}.  The reference then takes the 1-colour
     // branch with (undefined<<8)+a (MSVideo1.hx:171-173) / pal[a] (:353); patching the missing high byte
     // to 0x80 selects exactly that class with exactly that colour (bit 15 is ignored by fromRGB15).
     if ((len & 1u) && len >= tile_byte0 && len - tile_byte0 < (uint32_t)MSV1_STAGE_BYTES) {
-        if (tid == 0) sm.bytes[len - tile_byte0] = 0x80;
+        if (tid == 0) sbytes[len - tile_byte0] = 0x80;
         __syncthreads();
     }
 
@@ -260,7 +302,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
     uint32_t skipmask = 0, termmask = 0;      // per word: "is a copy run" / "ends the frame" if an opcode starts there
     u64 M;
     {
-        const uint32_t *sw = reinterpret_cast<const uint32_t *>(sm.bytes) + tid * 8;
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(sbytes) + tid * 8;
         const uint4 v0 = *reinterpret_cast<const uint4 *>(sw);
         const uint4 v1 = *reinterpret_cast<const uint4 *>(sw + 4);
         const uint32_t r[9] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, sw[8]};
@@ -376,7 +418,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
         uint32_t m = runs & ~termmask;
         while (m) {
             const int p = __ffs(m) - 1; m &= m - 1;
-            const uint8_t *o = sm.bytes + (tid * MSV1_SEG_WORDS + p) * 2;
+            const uint8_t *o = sbytes + (tid * MSV1_SEG_WORDS + p) * 2;
             blocks += (((uint32_t)o[1] - 0x84u) << 8) | o[0];
         }
         if (lterm) blocks = nblocks;
@@ -451,7 +493,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
                 sm.blk[opi] = blk;
                 if (big) { sm.big_blk0 = blk; blk = nblocks; }
                 else if (run) {
-                    const uint8_t *o = sm.bytes + (tid * MSV1_SEG_WORDS + p) * 2;
+                    const uint8_t *o = sbytes + (tid * MSV1_SEG_WORDS + p) * 2;
                     sm.runs[atomicAdd(&sm.nruns, 1u)] = (uint16_t)opi;
                     blk = sat_add(blk, (((uint32_t)o[1] - 0x84u) << 8) | o[0], nblocks);
                 } else blk = sat_add(blk, 1u, nblocks);
@@ -473,7 +515,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
             uint32_t col[8], flags;
             if (abs0 + (IS8 ? 10u : 18u) <= len) {
                 // the opcode as aligned 32-bit words, shifted down by 16 bits when it starts on an odd word
-                const uint32_t *q = reinterpret_cast<const uint32_t *>(sm.bytes) + (pw >> 1);
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(sbytes) + (pw >> 1);
                 const uint32_t sh = (pw & 1u) * 16u;
                 if (IS8) {
                     const uint32_t v0 = __funnelshift_r(q[0], q[1], sh), v1 = __funnelshift_r(q[1], q[2], sh),
@@ -509,7 +551,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
                 }
             } else {
                 // the opcode runs past the end of the frame: JavaScript `undefined` reads, byte by byte
-                const uint8_t *o = sm.bytes + pw * 2;
+                const uint8_t *o = sbytes + pw * 2;
                 auto rd = [&](uint32_t i) -> int { return abs0 + i < len ? (int)o[i] : -1; };
                 auto w16 = [&](uint32_t i) -> uint32_t { return abs0 + i + 1 < len ? (uint32_t)o[i] | ((uint32_t)o[i + 1] << 8) : 0u; };
                 const int a = rd(0), b = rd(1);
@@ -552,7 +594,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
         for (uint32_t r = warp; r < nruns; r += 4) {
             const uint32_t op = sm.runs[r];
             const uint32_t blk0 = sm.blk[op];
-            const uint8_t *o = sm.bytes + (sm.pos[op] & 0x7FFFu) * 2;
+            const uint8_t *o = sbytes + (sm.pos[op] & 0x7FFFu) * 2;
             uint32_t n = (((uint32_t)o[1] - 0x84u) << 8) | o[0];
             n = min(n, nblocks - min(blk0, nblocks));
             for (uint32_t j = lane; j < n; j += 32) {
@@ -583,21 +625,37 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const uint2 *__restrict
     }
     myflags = __reduce_or_sync(FULL, myflags);
     if (lane == 0 && myflags) atomicOr(&sm.flags, myflags);
-    __syncthreads();
+    if (tid == 0) sm.tk[3] = tk3;
+    __syncthreads();                       // also: every thread is done with this tile's shared-memory buffers
     if (tid == 0 && sm.flags) atomicOr(F.status, sm.flags);
+    // ---- rotate the pipeline ----
+    tk0 = tk1; e0 = e1;
+    tk1 = tk2; e1 = e2;
+    tk2 = sm.tk[3];
+    if (tk0 >= n_tiles) break;
+    if (tk2 < n_tiles) e2 = tiles[tk2];
+    cur ^= 1;
+    __syncthreads();                       // sm.tk[3] and sm.flags are rewritten by thread 0 at the top of the loop
+  }
+    cp_async_wait<0>();
 }
 
 }  // namespace
 
-void launch_msv1_decode(bool is8, const Msv1Frame *d_frames, const uint2 *d_tile_tab, uint32_t n_ctas,
+void launch_msv1_decode(bool is8, const Msv1Frame *d_frames, const Msv1Tile *d_tiles, uint32_t n_tiles,
                         unsigned long long *d_tile_map, unsigned long long *d_tile_cnt,
-                        unsigned int *d_ticket, cudaStream_t st)
+                        unsigned int *d_ticket, int sm_count, cudaStream_t st)
 {
-    if (n_ctas == 0) return;
+    if (n_tiles == 0) return;
+    // resident CTAs per SM (registers / shared memory allow 8-10): a persistent grid when there is work for several
+    // rounds, else one CTA per tile
+    const uint32_t capacity = (uint32_t)sm_count * 8u;
+    const int depth0 = n_tiles < 6u * capacity ? 1 : 0;
+    const uint32_t grid = depth0 ? n_tiles : capacity;
     if (is8)
-        msv1_decode_kernel<true><<<n_ctas, MSV1_THREADS, 0, st>>>(d_frames, d_tile_tab, d_tile_map, d_tile_cnt, d_ticket);
+        msv1_decode_kernel<true><<<grid, MSV1_THREADS, 0, st>>>(d_frames, d_tiles, n_tiles, depth0, d_tile_map, d_tile_cnt, d_ticket);
     else
-        msv1_decode_kernel<false><<<n_ctas, MSV1_THREADS, 0, st>>>(d_frames, d_tile_tab, d_tile_map, d_tile_cnt, d_ticket);
+        msv1_decode_kernel<false><<<grid, MSV1_THREADS, 0, st>>>(d_frames, d_tiles, n_tiles, depth0, d_tile_map, d_tile_cnt, d_ticket);
 }
 
 }  // namespace jsp

@@ -201,3 +201,28 @@ def test_full_size_properties_1080p_batch():
     assert (outs2[0] == outs[0]).all() and (outs2[1] == outs[1]).all()
     exp, *_ = oracle_stream(False, w, h, list(specs[3].frames))
     assert (outs[3] == exp[0]).all()
+
+
+def test_persistent_mode_large_batch():
+    """Enough 4 KiB bitstream tiles (> 6 x 8 CTAs x SM count) to put msv1_decode_kernel into its persistent,
+    prefetching mode: key + P frames with skip runs at 1080p, RGB555 and 8-bit, against the oracle."""
+    w, h = 1920, 1080
+    specs, exp = [], []
+    pal = synth.random_palette(5)
+    for s in range(64):
+        is8 = s % 2 == 1
+        frames = [synth.msv1_frame(is8, w, h, 1000 + s, mix=(10, 30, 60))] + \
+                 [synth.msv1_frame(is8, w, h, 2000 + s, skip_permille=300, mean_skip=25, mix=(10, 30, 60))]
+        specs.append(StreamSpec(CodecType.codec_msvc8 if is8 else CodecType.codec_msvc16, w, h, 8 if is8 else 16,
+                                frames=frames, palette=pal if is8 else None))
+        if s % 16 in (0, 1, 15):
+            exp.append((2 * s, O.decode_stream(O.CODEC_MSVC8 if is8 else O.CODEC_MSVC16, w, h, 8 if is8 else 16, frames,
+                                               palette=pal if is8 else None)[0]))
+    bd = BatchDecoder()
+    bd.configure(specs)
+    outs, flags = bd.decode_host()
+    bd.close()
+    assert not (flags & _lib.JSP_FRAME_ERROR).any()
+    for first, e in exp:
+        for f in range(2):
+            assert (outs[first + f] == e[f]).all(), "frame %d" % (first + f)
