@@ -89,6 +89,21 @@ __device__ __forceinline__ void sp_undo_frame(const SpJob &J, bool iframe)
     __syncwarp();
 }
 
+// cx + cx1 stays below 4096 on every valid stream (cx < 64, cx1 <= 0xFC0; 16 bpp v2: 5-bit channel values).  A corrupt
+// stream can exceed it -- the reference would read outside cntab[] -- so the index wraps inside its channel and the
+// frame is reported as failed; never an out-of-bounds access on the device.
+template <class Coder>
+__device__ __forceinline__ int sp_ctx_index(Coder &ec, int channel, int cx, int cx1)
+{
+    int i = cx + cx1;
+    if (i < 0 || i >= 4096) { ec.fail = true; i &= 4095; }
+    return channel * 4096 + i;
+}
+
+// Zero-length runs are legal syntax and cost almost no bits once their model has adapted, so a hostile stream could keep
+// a warp busy for ever.  No encoder emits them: a frame that needs more run-loop iterations than this is failed.
+__device__ __forceinline__ long sp_run_budget(long X, long Y) { return 2 * X * Y + 16 * ((X + 15) / 16) * ((Y + 15) / 16) + 4096; }
+
 // ---- the frame loops, generic over the entropy coder (EntroCoder interface, EntroCoders.hx:8-24) ----
 template <class Coder>
 __device__ void sp_decode_iframe(Coder &ec, const SpJob &J)
@@ -106,15 +121,17 @@ __device__ void sp_decode_iframe(Coder &ec, const SpJob &J)
     long di = 0, k = 0;
     uint32_t clr = 0, lastval = 0;
     auto decode_rgb = [&]() -> uint32_t {       // ScreenPressor.hx:173-183
-        const int r = ec.decodeClr(cx + cx1);
+        const int r = ec.decodeClr(sp_ctx_index(ec, 0, cx, cx1));
         cx1 = (cx << 6) & 0xFC0; cx = r >> cxshift;
-        const int g = ec.decodeClr(4096 + cx + cx1);
+        const int g = ec.decodeClr(sp_ctx_index(ec, 1, cx, cx1));
         cx1 = (cx << 6) & 0xFC0; cx = g >> cxshift;
-        const int b = ec.decodeClr(2 * 4096 + cx + cx1);
+        const int b = ec.decodeClr(sp_ctx_index(ec, 2, cx, cx1));
         cx1 = (cx << 6) & 0xFC0; cx = b >> cxshift;
         return ((uint32_t)b << 16) + ((uint32_t)g << 8) + (uint32_t)r;
     };
+    long budget = sp_run_budget(X, J.Y);
     while (k < X + 1) {                            // first X+1 pixels: (colour, run) pairs, :170-197
+        if (--budget < 0) ec.fail = true;
         clr = decode_rgb();
         const int n = ec.decodeN(0);
         if (ec.failed()) return;
@@ -129,6 +146,7 @@ __device__ void sp_decode_iframe(Coder &ec, const SpJob &J)
     __syncwarp();
     int ptype = 0;
     while (di < end) {                             // :218-286
+        if (--budget < 0) ec.fail = true;
         ptype = ec.decodeP(ptype);
         if (ptype == 0) clr = decode_rgb();
         int n = ec.decodeN(ptype);
@@ -167,7 +185,9 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
     __syncwarp();
     bool signif = false;
     long x = xx1;
+    long budget = sp_run_budget(X, Y);
     while (x <= xx2) {                             // block types, run-length coded (:336-344)
+        if (--budget < 0) ec.fail = true;
         const int bt = ec.decodeBT();
         const int n = ec.decodeBN();
         if (ec.failed()) return;
@@ -186,11 +206,11 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
     uint32_t clr = 0;
     int lastmx = 0, lastmy = 0;
     auto decode_rgb = [&]() -> uint32_t {
-        const int r = ec.decodeClr(cx + cx1);
+        const int r = ec.decodeClr(sp_ctx_index(ec, 0, cx, cx1));
         cx1 = (cx << 6) & 0xFC0; cx = r >> cxshift;
-        const int g = ec.decodeClr(4096 + cx + cx1);
+        const int g = ec.decodeClr(sp_ctx_index(ec, 1, cx, cx1));
         cx1 = (cx << 6) & 0xFC0; cx = g >> cxshift;
-        const int b = ec.decodeClr(2 * 4096 + cx + cx1);
+        const int b = ec.decodeClr(sp_ctx_index(ec, 2, cx, cx1));
         cx1 = (cx << 6) & 0xFC0; cx = b >> cxshift;
         return ((uint32_t)b << 16) + ((uint32_t)g << 8) + (uint32_t)r;
     };
@@ -232,6 +252,7 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
         } else {                                   // data (:406-467): runs in raster order inside the rectangle
             int xq = x1, y = y1, ptype = 0;
             while (y < y2) {
+                if (--budget < 0) ec.fail = true;
                 ptype = ec.decodeP(ptype);
                 if (ptype == 0) clr = decode_rgb();
                 int n = ec.decodeN(ptype);

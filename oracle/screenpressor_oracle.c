@@ -33,6 +33,8 @@ struct sp_dec {
     int decodedI;
     int last_one_was_flat;      /* Null<Int>: -1 = null */
     int decodingBools;
+    int ctx_fail;               /* a colour context index left its channel's 4096 contexts (see ctx_index) */
+    long budget;                /* run-loop iterations left in this frame (see SP_RUN_BUDGET) */
 };
 
 sp_dec *sp_new(int w, int h, int bpp)
@@ -89,14 +91,30 @@ static int renew_i(sp_dec *s)
 static inline int32_t px_get(const int32_t *p, long i, long end) { return (i >= 0 && i < end) ? p[i] : 0; }
 
 /* the three colour symbols of one pixel, ScreenPressor.hx:173-183 / :224-234 / :419-429 */
+/* Defined behaviour (not in the reference): zero-length runs are legal syntax and cost almost no bits once their model
+ * has adapted, so a hostile stream can keep a decoder busy for ever.  No encoder emits them; a frame that needs more
+ * run-loop iterations than 2 per pixel + 16 per block + 4096 is reported as failed (ctx_fail doubles as the flag). */
+#define SP_RUN_BUDGET(X, Y) (2L * (X) * (Y) + 16L * (((X) + 15) / 16) * (((Y) + 15) / 16) + 4096)
+#define SP_SPEND(s) do { if (--(s)->budget < 0) (s)->ctx_fail = 1; } while (0)
+
+/* Defined behaviour (not in the reference): cx + cx1 stays below 4096 on every valid stream (cx < 64, cx1 <= 0xFC0;
+ * 16 bpp v2: 5-bit channel values).  A corrupt stream can exceed it -- the reference would read outside cntab[] --
+ * so the index wraps inside its channel and the frame is reported as failed. */
+static inline int ctx_index(sp_dec *s, int channel)
+{
+    int i = s->cx + s->cx1;
+    if (i < 0 || i >= CC_CXMAX) { s->ctx_fail = 1; i &= CC_CXMAX - 1; }
+    return channel * CC_CXMAX + i;
+}
+
 static inline int32_t decode_rgb(sp_dec *s)
 {
     entro *ec = s->ec;
-    int r = ec->decodeClr(ec, s->cx + s->cx1);
+    int r = ec->decodeClr(ec, ctx_index(s, 0));
     s->cx1 = (s->cx << 6) & 0xFC0; s->cx = r >> s->SC_CXSHIFT;
-    int g = ec->decodeClr(ec, 4096 + s->cx + s->cx1);
+    int g = ec->decodeClr(ec, ctx_index(s, 1));
     s->cx1 = (s->cx << 6) & 0xFC0; s->cx = g >> s->SC_CXSHIFT;
-    int b = ec->decodeClr(ec, 2 * 4096 + s->cx + s->cx1);
+    int b = ec->decodeClr(ec, ctx_index(s, 2));
     s->cx1 = (s->cx << 6) & 0xFC0; s->cx = b >> s->SC_CXSHIFT;
     return (b << 16) + (g << 8) + r;
 }
@@ -141,13 +159,19 @@ int sp_decompress_i(sp_dec *s, const uint8_t *src, int len, int32_t *dst)
     renew_i(s);
     entro *ec = s->ec;
     ec->decodeBegin(ec, src, len, 1);
+    /* the reference always runs DecompressI to its end (:293); a frame that FAILS here (defined behaviour) still
+     * counts as "an I frame has been seen", so later P frames are decoded -- from nothing (prevFrame is null) */
+    s->decodedI = 1;
+    s->ctx_fail = 0;                                          /* the failure report is per frame */
+    s->budget = SP_RUN_BUDGET(s->X, s->Y);
     s->cx = s->cx1 = 0;
     int k = 0;
     lasti = di;
     while (k < X + 1) {                                       /* :170-197 */
+        SP_SPEND(s);
         clr = decode_rgb(s);
         int n = ec->decodeN(ec, 0);
-        if (ec->failed(ec)) return ORA_ERROR_OCCURED;
+        if ((ec->failed(ec) || s->ctx_fail)) return ORA_ERROR_OCCURED;
         k += n;
         while (n-- > 0) { if (di < end) dst[di] = clr; di++; }
         lasti = di - 1;
@@ -156,10 +180,11 @@ int sp_decompress_i(sp_dec *s, const uint8_t *src, int len, int32_t *dst)
     const long off = -X - 1;
     int ptype = 0;
     while (di < end) {                                        /* :218-286 */
+        SP_SPEND(s);
         ptype = ec->decodeP(ec, ptype);
         if (ptype == 0) clr = decode_rgb(s);
         int n = ec->decodeN(ec, ptype);
-        if (ec->failed(ec)) return ORA_ERROR_OCCURED;
+        if ((ec->failed(ec) || s->ctx_fail)) return ORA_ERROR_OCCURED;
         switch (ptype) {
         case 0:
             while (n-- > 0) { if (di < end) dst[di] = clr; di++; }
@@ -204,6 +229,8 @@ int sp_decompress_p(sp_dec *s, const uint8_t *src, int len, int32_t *dst, const 
     entro *ec = s->ec;
     if (ec->differentConstantsFor16bpp(ec) && s->bpp == 16) { maskcx1 = 0xFF00; shiftcx1 = 2; shiftcx = 16; }
     ec->decodeBegin(ec, src, len, 1);
+    s->ctx_fail = 0;                                          /* the failure report is per frame */
+    s->budget = SP_RUN_BUDGET(s->X, s->Y);
     int t = ec->decodeX(ec);
     int xx1 = ec->decodeX(ec); xx1 = (xx1 << 8) + t;
     t = ec->decodeX(ec);
@@ -212,9 +239,10 @@ int sp_decompress_p(sp_dec *s, const uint8_t *src, int len, int32_t *dst, const 
     for (int i = 0; i < nb; i++) s->bts[i] = 0;
     long x = xx1;
     while (x <= xx2) {                                        /* :336-344 */
+        SP_SPEND(s);
         int bt = ec->decodeBT(ec);
         int n = ec->decodeBN(ec);
-        if (ec->failed(ec)) return ORA_ERROR_OCCURED;
+        if ((ec->failed(ec) || s->ctx_fail)) return ORA_ERROR_OCCURED;
         for (int i = 0; i < n; i++) { if (x >= 0 && x < nb) s->bts[x] = bt; x++; }
     }
     int signif = 0;
@@ -244,7 +272,7 @@ int sp_decompress_p(sp_dec *s, const uint8_t *src, int len, int32_t *dst, const 
                 int mx, my;
                 if (s->decodingBools && ec->decodeBool(ec)) { mx = lastmx; my = lastmy; }
                 else { mx = ec->decodeMX(ec) - SP_MSR_X; my = ec->decodeMY(ec) - SP_MSR_Y; }
-                if (ec->failed(ec)) return ORA_ERROR_OCCURED;
+                if ((ec->failed(ec) || s->ctx_fail)) return ORA_ERROR_OCCURED;
                 lastmx = mx; lastmy = my;
                 for (int y = y1; y < y2; y++) {
                     long i = (long)y * X + x1, j = (long)(y + my) * X + (x1 + mx);
@@ -255,11 +283,12 @@ int sp_decompress_p(sp_dec *s, const uint8_t *src, int len, int32_t *dst, const 
                 int xq = x1, y = y1;
                 int ptype = 0;
                 while (y < y2) {
+                    SP_SPEND(s);
                     long i = (long)y * X + xq;
                     ptype = ec->decodeP(ec, ptype);
                     if (ptype == 0) clr = decode_rgb(s);
                     int n = ec->decodeN(ec, ptype);
-                    if (ec->failed(ec)) return ORA_ERROR_OCCURED;
+                    if ((ec->failed(ec) || s->ctx_fail)) return ORA_ERROR_OCCURED;
                     for (int c = 0; c < n; c++) {
                         switch (ptype) {
                         case 1: clr = px_get(dst, i - 1, end); break;

@@ -192,3 +192,20 @@ def test_independent_segments_run_concurrently(version):
     frames.insert(5, enc.flat(0x0A0B0C)); keys.insert(5, 1)      # a model-resetting flat frame is a segment of its own
     frames.insert(6, b"\0"); keys.insert(6, 0)
     check(w, h, 24, frames, keys, insign=16)
+
+
+def test_16bpp_corrupt_stream_stays_in_bounds():
+    """16 bpp v2 streams index colour contexts with whole channel bytes (SC_CXSHIFT 0, ScreenPressor.hx:59,200-202):
+    corrupt symbols above 31 push cx + cx1 past a channel's 4096 contexts.  Defined behaviour: wrap + failed frame."""
+    w, h = 64, 48
+    frames, keys, pics = synth.sp_stream(w, h, 3, seed=8, version=2, bpp=16, change_permille=200)
+    rng = np.random.default_rng(12)
+    for trial in range(6):
+        bad = bytearray(frames[0])
+        for _ in range(6):
+            bad[int(rng.integers(8, len(bad)))] ^= int(rng.integers(1, 256))
+        check(w, h, 16, [bytes(bad), frames[1], frames[2]], keys)
+        badp = bytearray(frames[1])
+        for _ in range(3):
+            badp[int(rng.integers(2, len(badp)))] ^= int(rng.integers(1, 256))
+        check(w, h, 16, [frames[0], bytes(badp), frames[2]], keys)
