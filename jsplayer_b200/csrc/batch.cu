@@ -781,10 +781,9 @@ int jsp_batch_results(jsp_batch *b, uint8_t *flags)
 }
 
 // D2H of pictures [lo, hi) on stream st; adjacent host destinations are merged into one copy
-static bool download_range(jsp_batch *b, int64_t lo, int64_t hi, int32_t *const *out_frames, cudaStream_t st,
-                           const int32_t *arena = nullptr)
+static bool download_range(jsp_batch *b, int64_t lo, int64_t hi, int32_t *const *out_frames, cudaStream_t st)
 {
-    if (!arena) arena = b->d_out;
+    const int32_t *arena = b->d_out;
     int64_t i = lo;
     while (i < hi) {
         if (!out_frames[i]) { i++; continue; }

@@ -81,7 +81,7 @@ static void ea_begin(entro *e, const uint8_t *src, int len, int pos0)   /* :229-
     rans_init(&a->rans, pos0);
     a->nDec = 0;
 }
-extern unsigned long long g_ora_symbols;
+extern __thread unsigned long long g_ora_symbols;
 static inline void ea_count(entro_ans *a)
 {
     g_ora_symbols++;

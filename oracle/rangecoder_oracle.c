@@ -42,9 +42,9 @@ static void rc_begin(rangecoder *rc, const uint8_t *src, int len, int pos0)
 }
 
 /* RangeCoder.hx:45-49 */
-/* test hook: entropy-coded symbols decoded so far by this library (both coders; racy under threads, read by
- * single-threaded callers to report symbols per frame) */
-unsigned long long g_ora_symbols = 0;
+/* test hook: entropy-coded symbols decoded so far by the calling thread (both coders).  Thread-local: a shared
+ * counter would make the multi-threaded CPU baseline fight over one cache line. */
+__thread unsigned long long g_ora_symbols = 0;
 unsigned long long ora_symbol_count(int reset) { unsigned long long v = g_ora_symbols; if (reset) g_ora_symbols = 0; return v; }
 
 static inline uint32_t rc_get_freq(rangecoder *rc, uint32_t tot)
