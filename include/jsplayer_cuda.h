@@ -113,7 +113,8 @@ JSP_API uint64_t   jsp_batch_device_frame(jsp_batch *b, int64_t i);
  * `warmup` untimed passes.  ms_total = whole region; kernel_ms[k] (may be NULL, k < JSP_N_KERNELS) =
  * summed device time of kernel class k over the timed passes, launches[k] = launch count. */
 enum { JSP_K_MSV1_DECODE = 0, JSP_K_FRAME_COPY = 1, JSP_K_SP_ENTROPY_RC = 2, JSP_K_SP_ENTROPY_ANS = 3,
-       JSP_K_SP_RECON = 4, JSP_K_SIGNIF = 5, JSP_N_KERNELS = 8 };
+       JSP_K_SP_RECON = 4, JSP_K_SIGNIF = 5, JSP_K_SP_ENTROPY_MIXED = 6 /* range-coder and rANS jobs in one launch */,
+       JSP_N_KERNELS = 8 };
 JSP_API int        jsp_batch_time_runs(jsp_batch *b, int warmup, int iters, int flush_l2,
                                        float *ms_total, float *kernel_ms, int64_t *launches);
 /* Algorithmic bytes one jsp_batch_run() moves: output store + compressed read +

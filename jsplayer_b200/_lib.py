@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libjsplayer_cuda.so")
 
 JSP_N_KERNELS = 8
-KERNEL_NAMES = ["msv1_decode", "frame_copy", "sp_entropy_rc", "sp_entropy_ans", "sp_recon", "signif", "k6", "k7"]
+KERNEL_NAMES = ["msv1_decode", "frame_copy", "sp_entropy_rc", "sp_entropy_ans", "sp_recon", "signif", "sp_entropy_mixed", "k7"]
 JSP_BATCH_SIGNIFICANCE = 1
 JSP_FRAME_CHANGED, JSP_FRAME_SIGNIFICANT, JSP_FRAME_ERROR, JSP_FRAME_DIFFERS = 1, 2, 4, 8
 JSP_DISPLAY_FLIP = 1

@@ -12,6 +12,7 @@
 #include <mutex>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -175,6 +176,7 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
                 FrameRec &R = b->frames[f];
                 if (R.kind != FK_COPY && R.kind != FK_SP_P && R.kind != FK_SP_FLAT) continue;
                 const StreamRec &S = b->streams[R.stream];
+                if (S.codec == JSP_CODEC_SCREENPRESSOR) continue;          // ScreenPressor levels are planned below
                 CopyJob J;
                 J.dst = b->d_out + R.out_off;
                 J.src = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
@@ -218,30 +220,54 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             plan.launches.push_back({JSP_K_MSV1_DECODE, kind, first, (uint32_t)(T.tile_tab.size() - first), 0, (uint32_t)ticket_cursor});
             ticket_cursor++;
         }
-        // ScreenPressor: one warp per frame of this level (after the copies that prepared the pictures),
-        // one launch per entropy coder (range coder v2 / rANS v3, v4)
-        for (int ans = 0; ans < 2; ans++) {
-            const size_t first = T.spjobs.size();
+    }
+    // ScreenPressor: per level, the whole-picture copies / fills that prepare the pictures, then one warp per frame.
+    // Range-coder and rANS streams share the launch.  (Measured: dealing the chains -- frames sharing one model-state
+    // slot -- into groups with their own CUDA streams, so that levels need not wait for their slowest warp, changes
+    // nothing: a batch lasts as long as its slowest CHAIN, 534-545 ms for C4 at 1 to 32 groups.)
+    for (int lv = 0; lv <= max_level; lv++) {
+        {
+            const size_t first = T.jobs.size(); uint32_t maxv = 0;
             for (int64_t f : by_level[lv]) {
-                FrameRec &R = b->frames[f];
-                if (R.kind != FK_SP_I && R.kind != FK_SP_P && !(R.kind == FK_SP_FLAT && (R.sp_flags & SPJ_RENEW))) continue;
+                const FrameRec &R = b->frames[f];
                 const StreamRec &S = b->streams[R.stream];
-                const SpHost &H = b->sp_hosts[R.stream];
-                if ((H.version > 2) != (ans != 0)) continue;
-                SpJob J{};
-                J.src = b->d_bytes + R.d_src; J.len = R.len;
+                if (S.codec != JSP_CODEC_SCREENPRESSOR) continue;
+                if (R.kind != FK_COPY && R.kind != FK_SP_P && R.kind != FK_SP_FLAT) continue;
+                CopyJob J;
                 J.dst = b->d_out + R.out_off;
-                J.prev = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
-                J.status = b->d_status + f;
-                const size_t slot = R.sp_seg > 0 ? (size_t)(R.sp_seg % H.n_slots) : 0;
-                J.state = b->d_sp_state + H.state_off + slot * H.state_stride;
-                J.bts = b->d_sp_bts + H.bts_off + slot * H.bts_stride;
-                J.X = (uint32_t)S.w; J.Y = (uint32_t)S.h; J.flags = R.sp_flags;
-                J.insign_blocks = (uint32_t)(((S.w + 15) / 16) * ((std::max(0, b->insign_lines) + 15) / 16));
-                T.spjobs.push_back(J);
+                J.src = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
+                J.value = 0;
+                if (R.kind == FK_SP_FLAT) { J.src = nullptr; J.value = R.fill_value; }
+                J.n_vec4 = (uint32_t)(((size_t)S.w * S.h * 4 + 15) / 16);
+                maxv = std::max(maxv, J.n_vec4);
+                T.jobs.push_back(J);
             }
-            if (T.spjobs.size() > first)
-                plan.launches.push_back({ans ? JSP_K_SP_ENTROPY_ANS : JSP_K_SP_ENTROPY_RC, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), 0, 0});
+            if (T.jobs.size() > first)
+                plan.launches.push_back({JSP_K_FRAME_COPY, FK_COPY, first, (uint32_t)(T.jobs.size() - first), maxv, 0});
+        }
+        const size_t first = T.spjobs.size();
+        int n_rc = 0, n_ans = 0;
+        for (int64_t f : by_level[lv]) {
+            const FrameRec &R = b->frames[f];
+            if (R.kind != FK_SP_I && R.kind != FK_SP_P && !(R.kind == FK_SP_FLAT && (R.sp_flags & SPJ_RENEW))) continue;
+            const StreamRec &S = b->streams[R.stream];
+            const SpHost &H = b->sp_hosts[R.stream];
+            SpJob J{};
+            J.src = b->d_bytes + R.d_src; J.len = R.len;
+            J.dst = b->d_out + R.out_off;
+            J.prev = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
+            J.status = b->d_status + f;
+            const size_t slot = R.sp_seg > 0 ? (size_t)(R.sp_seg % H.n_slots) : 0;
+            J.state = b->d_sp_state + H.state_off + slot * H.state_stride;
+            J.bts = b->d_sp_bts + H.bts_off + slot * H.bts_stride;
+            J.X = (uint32_t)S.w; J.Y = (uint32_t)S.h; J.flags = R.sp_flags | (H.version > 2 ? SPJ_ANS : 0u);
+            J.insign_blocks = (uint32_t)(((S.w + 15) / 16) * ((std::max(0, b->insign_lines) + 15) / 16));
+            (H.version > 2 ? n_ans : n_rc)++;
+            T.spjobs.push_back(J);
+        }
+        if (T.spjobs.size() > first) {
+            const int kclass = n_ans == 0 ? JSP_K_SP_ENTROPY_RC : (n_rc == 0 ? JSP_K_SP_ENTROPY_ANS : JSP_K_SP_ENTROPY_MIXED);
+            plan.launches.push_back({kclass, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), 0, 0});
         }
     }
     plan.n_spjobs = T.spjobs.size() - plan.spjob_off;
@@ -331,7 +357,7 @@ static bool run_plan(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *
         !JSP_CUDA(cudaMemsetAsync(b->d_status + P.frame_lo, 0, (size_t)(P.frame_hi - P.frame_lo) * 4, st))) return false;
     int k = 0;
     for (const Launch &L : P.launches) {
-        if (ev) { cudaEventRecord(ev[k], st); ev_class->push_back(L.kclass); k++; }
+        if (ev) { cudaEventRecord(ev[2 * k], st); ev_class->push_back(L.kclass); }
         switch (L.kclass) {
         case JSP_K_FRAME_COPY:
             launch_frame_copy(b->d_jobs + L.first, L.count, L.max_vec4, b->sm_count, st);
@@ -340,16 +366,14 @@ static bool run_plan(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *
             launch_msv1_decode(L.kind == FK_MSV8, b->d_mframes, b->d_tile_tab + L.first, L.count,
                                b->d_tile_map, b->d_tile_cnt, b->d_tickets + L.ticket, b->sm_count, st);
             break;
-        case JSP_K_SP_ENTROPY_RC:
-            launch_sp_rc(b->d_spjobs + L.first, L.count, st);
-            break;
-        case JSP_K_SP_ENTROPY_ANS:
-            launch_sp_ans(b->d_spjobs + L.first, L.count, st);
+        case JSP_K_SP_ENTROPY_RC: case JSP_K_SP_ENTROPY_ANS: case JSP_K_SP_ENTROPY_MIXED:
+            launch_sp_decode(b->d_spjobs + L.first, L.count, st);
             break;
         default: break;
         }
+        if (ev) cudaEventRecord(ev[2 * k + 1], st);
+        k++;
     }
-    if (ev) cudaEventRecord(ev[k], st);
     return JSP_CUDA(cudaGetLastError());
 }
 
@@ -473,6 +497,8 @@ void jsp_batch_destroy(jsp_batch *b)
     cudaSetDevice(b->device);
     cudaDeviceSynchronize();
     for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : b->ev_sync) cudaEventDestroy(e);
+
     void *ptrs[] = {b->d_bytes, b->d_out, b->d_pal, b->d_status, b->d_mframes, b->d_tile_tab, b->d_jobs, b->d_tile_map,
                     b->d_tile_cnt, b->d_tickets, b->d_sig_cur, b->d_sig_prev, b->d_sig_status, b->d_sig_first, b->d_sig_npx,
                     b->d_stream_first, b->d_stream_count, b->d_frame_codec, b->d_flush, b->d_spjobs, b->d_sp_state,
@@ -865,9 +891,9 @@ int jsp_batch_decode_host(jsp_batch *b, int32_t *const *out_frames, uint8_t *fla
     // transfer-bound batches: three-stream pipeline over chunks of whole streams (PCIe is full duplex)
     if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
     const size_t nc = b->chunks.size();
-    while (b->ev_pool.size() < 2 * nc + 2) { cudaEvent_t e; if (!JSP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming))) return -1; b->ev_pool.push_back(e); }
-    // the pool may also hold timing events; any event works for ordering
-    cudaEvent_t ev0 = b->ev_pool[2 * nc];
+    const size_t eb = 0;
+    while (b->ev_sync.size() < eb + 2 * nc + 2) { cudaEvent_t e; if (!JSP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming))) return -1; b->ev_sync.push_back(e); }
+    cudaEvent_t ev0 = b->ev_sync[eb + 2 * nc];
     if (!JSP_CUDA(cudaEventRecord(ev0, b->st_compute))) return -1;           // order after earlier work on the compute stream
     if (!JSP_CUDA(cudaStreamWaitEvent(b->st_in, ev0, 0)) || !JSP_CUDA(cudaStreamWaitEvent(b->st_out, ev0, 0))) return -1;
     const int reruns = b->rerun_count;
@@ -875,11 +901,11 @@ int jsp_batch_decode_host(jsp_batch *b, int32_t *const *out_frames, uint8_t *fla
         const Plan &P = b->chunks[c];
         for (const CopyRange &r : P.uploads)
             if (!JSP_CUDA(cudaMemcpyAsync(b->d_bytes + r.d_off, r.h, r.bytes, cudaMemcpyHostToDevice, b->st_in))) return -1;
-        if (!JSP_CUDA(cudaEventRecord(b->ev_pool[2 * c], b->st_in))) return -1;
-        if (!JSP_CUDA(cudaStreamWaitEvent(b->st_compute, b->ev_pool[2 * c], 0))) return -1;
+        if (!JSP_CUDA(cudaEventRecord(b->ev_sync[eb + 2 * c], b->st_in))) return -1;
+        if (!JSP_CUDA(cudaStreamWaitEvent(b->st_compute, b->ev_sync[eb + 2 * c], 0))) return -1;
         if (!run_plan(b, P, b->st_compute)) return -1;
-        if (!JSP_CUDA(cudaEventRecord(b->ev_pool[2 * c + 1], b->st_compute))) return -1;
-        if (!JSP_CUDA(cudaStreamWaitEvent(b->st_out, b->ev_pool[2 * c + 1], 0))) return -1;
+        if (!JSP_CUDA(cudaEventRecord(b->ev_sync[eb + 2 * c + 1], b->st_compute))) return -1;
+        if (!JSP_CUDA(cudaStreamWaitEvent(b->st_out, b->ev_sync[eb + 2 * c + 1], 0))) return -1;
         if (!download_range(b, P.frame_lo, P.frame_hi, out_frames, b->st_out)) return -1;
     }
     if (!run_status(b, b->st_compute)) return -1;
@@ -912,6 +938,10 @@ int jsp_batch_kernel_bytes(jsp_batch *b, uint64_t *bytes)
 {
     if (!b || !bytes) return -1;
     for (int k = 0; k < JSP_N_KERNELS; k++) bytes[k] = b->stat_k_bytes[k];
+    if (bytes[JSP_K_SP_ENTROPY_RC] && bytes[JSP_K_SP_ENTROPY_ANS]) {       // both coders present: their jobs share launches
+        bytes[JSP_K_SP_ENTROPY_MIXED] = bytes[JSP_K_SP_ENTROPY_RC] + bytes[JSP_K_SP_ENTROPY_ANS];
+        bytes[JSP_K_SP_ENTROPY_RC] = bytes[JSP_K_SP_ENTROPY_ANS] = 0;
+    }
     return 0;
 }
 
@@ -943,7 +973,7 @@ int jsp_batch_time_runs(jsp_batch *b, int warmup, int iters, int flush_l2, float
     if (kernel_ms || launches) {
         // attribution pass: one extra run with an event in front of every launch
         const size_t n = b->whole.launches.size();
-        while (b->ev_pool.size() < n + 1) { cudaEvent_t e; cudaEventCreate(&e); b->ev_pool.push_back(e); }
+        while (b->ev_pool.size() < 2 * n + 2) { cudaEvent_t e; cudaEventCreate(&e); b->ev_pool.push_back(e); }
         float acc[JSP_N_KERNELS] = {0}; int64_t cnt[JSP_N_KERNELS] = {0};
         for (int i = 0; i < iters; i++) {
             if (flush_l2) cudaMemsetAsync(b->d_flush, i & 0xFF, b->flush_bytes, st);
@@ -951,7 +981,7 @@ int jsp_batch_time_runs(jsp_batch *b, int warmup, int iters, int flush_l2, float
             if (!run_plan(b, b->whole, st, b->ev_pool.data(), &cls)) return -1;
             if (!JSP_CUDA(cudaStreamSynchronize(st))) return -1;
             for (size_t k = 0; k < cls.size(); k++) {
-                float ms = 0.f; cudaEventElapsedTime(&ms, b->ev_pool[k], b->ev_pool[k + 1]);
+                float ms = 0.f; cudaEventElapsedTime(&ms, b->ev_pool[2 * k], b->ev_pool[2 * k + 1]);
                 acc[cls[k]] += ms; cnt[cls[k]]++;
             }
             if (!run_status(b, st)) return -1;

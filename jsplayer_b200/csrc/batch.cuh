@@ -35,16 +35,15 @@ struct SpHost {
     int n_slots = 1, n_segments = 0;
 };
 
-// sp_rc.cu
+// sp_decode.cu (sp_rc.cuh)
 size_t sp_rc_state_bytes();
 size_t sp_rc_rows_bytes();
 void sp_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t st);
-void launch_sp_rc(const SpJob *d_jobs, uint32_t n_jobs, cudaStream_t st);
-// sp_ans.cu
+// sp_decode.cu (sp_ans.cuh)
 size_t sp_ans_state_bytes();
 size_t sp_ans_ctx_bytes();
 void sp_ans_state_init(void *d_state, void *d_ctx, uint32_t gen0, cudaStream_t st);
-void launch_sp_ans(const SpJob *d_jobs, uint32_t n_jobs, cudaStream_t st);
+void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, cudaStream_t st);   // sp_decode.cu: both coders, one launch
 
 struct StreamRec {
     int codec, w, h, bpp;
@@ -105,7 +104,9 @@ struct jsp_batch {
     int insign_lines = 0;
     int flags = 0;
     cudaStream_t st_compute = nullptr, st_in = nullptr, st_out = nullptr;
-    std::vector<cudaEvent_t> ev_pool;
+    std::vector<cudaEvent_t> ev_pool;              // timing events (jsp_batch_time_runs)
+    std::vector<cudaEvent_t> ev_sync;              // ordering-only events (end-to-end pipeline)
+
 
     std::vector<jsp::StreamRec> streams;
     std::vector<jsp::FrameRec> frames;

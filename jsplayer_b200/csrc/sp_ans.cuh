@@ -1,4 +1,4 @@
-// sp_ans.cu -- ScreenPressor v3 / v4 entropy decode on sm_100a: byte-wise rANS with adaptive context models.
+// sp_ans.cuh -- ScreenPressor v3 / v4 entropy decode on sm_100a: byte-wise rANS with adaptive context models.
 // Replaces reference src/ANS.hx (whole file) and EntroCoderANS (src/EntroCoders.hx:182-313), one stream per warp.
 //
 //  * rANS state, read position and symbol counter are replicated in every lane; the bitstream is read through a
@@ -16,6 +16,7 @@
 //  * renewI (EntroCoders.hx:216-227) is O(1) for the 12288 contexts: a generation number in the header.
 //
 // JavaScript typed-array semantics (Uint16Array wrap of freqs / cnts, Uint8Array decTable and symbols) are explicit.
+#pragma once
 #include "sp_common.cuh"
 #include <cstddef>
 #include <cstring>
@@ -797,13 +798,9 @@ struct AnsCoder {
     __device__ int decodeMY() { return decodeF(sm->small.mvtab[1]); }
 };
 
-namespace {
-
-__global__ void __launch_bounds__(32)
-sp_ans_decode_kernel(const SpJob *__restrict__ jobs)
+// one frame of one rANS stream; `sm` = this warp's shared memory
+__device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm)
 {
-    __shared__ AnsShared sm;
-    const SpJob J = jobs[blockIdx.x];
     AnsState *st = reinterpret_cast<AnsState *>(J.state);
     const int lane = (int)lane_id();
     AnsCoder ec;
@@ -836,29 +833,6 @@ sp_ans_decode_kernel(const SpJob *__restrict__ jobs)
         for (int i = lane; i < (int)(sizeof(AnsSmall) / 16); i += 32) g[i] = s[i];
     }
     if (lane == 0) { st->gen = ec.gen; if (bits) atomicOr(J.status, bits); }
-}
-
-}  // namespace
-
-size_t sp_ans_state_bytes() { return (sizeof(AnsState) + 255) & ~(size_t)255; }
-size_t sp_ans_ctx_bytes() { return (size_t)ANS_NCTX * (ANS_HDR_BYTES + ANS_BODY_BYTES); }
-
-// host-side init of one stream's state: generation gen0 (headers are zeroed: generation 0 = "no context")
-void sp_ans_state_init(void *d_state, void *d_ctx, uint32_t gen0, cudaStream_t st)
-{
-    struct { uint32_t gen; uint32_t pad[3]; uint4 *hdrs; uint4 *bodies; } h;
-    memset(&h, 0, sizeof h);
-    h.gen = gen0;
-    h.hdrs = reinterpret_cast<uint4 *>(d_ctx);
-    h.bodies = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(d_ctx) + (size_t)ANS_NCTX * ANS_HDR_BYTES);
-    static_assert(sizeof(h) == sizeof(AnsState) - offsetof(AnsState, gen), "AnsState tail layout");
-    cudaStreamSynchronize(st);
-    cudaMemcpy(reinterpret_cast<char *>(d_state) + offsetof(AnsState, gen), &h, sizeof h, cudaMemcpyHostToDevice);
-}
-
-void launch_sp_ans(const SpJob *d_jobs, uint32_t n_jobs, cudaStream_t st)
-{
-    if (n_jobs) sp_ans_decode_kernel<<<n_jobs, 32, 0, st>>>(d_jobs);
 }
 
 }  // namespace jsp

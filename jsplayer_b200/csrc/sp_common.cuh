@@ -18,6 +18,7 @@ enum : uint32_t {
     SPJ_RENEW    = 1u << 1,   // flat I frame: only reset the models (RenewI, ScreenPressor.hx:108-115)
     SPJ_DIFF16   = 1u << 2,   // 16 bpp stream on the range coder: other context constants (:200-202, :316-318)
     SPJ_CXSHIFT0 = 1u << 3,   // SC_CXSHIFT == 0 (:59)
+    SPJ_ANS      = 1u << 5,   // rANS stream (v3 / v4): sp_ans.cuh, else the range coder of sp_rc.cuh
     SPJ_ANS_V3   = 1u << 4,   // rANS stream version 3: Cx6.f0 = 64 (v4: 32), ScreenPressor.hx:69-72
 };
 

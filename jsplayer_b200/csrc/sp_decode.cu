@@ -1,0 +1,60 @@
+// sp_decode.cu -- the ScreenPressor entropy-decode kernel: one warp (one 32-thread CTA) per frame of one stream.
+// Range-coder (v2, sp_rc.cuh) and rANS (v3 / v4, sp_ans.cuh) jobs share ONE launch, so that the streams of a level run
+// concurrently whatever their coder is (two launches would each wait for their own slowest warp).
+// Replaces the per-frame entry of reference src/ScreenPressor.hx (DecompressI :117-295, DecompressP :302-484).
+#include "sp_rc.cuh"
+#include "sp_ans.cuh"
+
+namespace jsp {
+namespace {
+
+constexpr size_t SP_SMEM = sizeof(AnsShared) > sizeof(RcSmall) ? sizeof(AnsShared) : sizeof(RcSmall);
+
+__global__ void __launch_bounds__(32)
+sp_decode_kernel(const SpJob *__restrict__ jobs)
+{
+    __shared__ alignas(16) uint8_t smem[SP_SMEM];
+    const SpJob J = jobs[blockIdx.x];
+    if (J.flags & SPJ_ANS) sp_ans_run(J, *reinterpret_cast<AnsShared *>(smem));
+    else sp_rc_run(J, *reinterpret_cast<RcSmall *>(smem));
+}
+
+}  // namespace
+
+size_t sp_rc_state_bytes() { return (sizeof(RcState) + 255) & ~(size_t)255; }
+size_t sp_rc_rows_bytes() { return (size_t)RC_ROWS * RC_ROW_STRIDE * 4; }
+
+// host-side init of one stream's state: generation gen0, tables irrelevant until the first I frame
+void sp_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t st)
+{
+    RcState h;
+    memset(&h, 0, sizeof h);
+    h.gen = gen0; h.rows = reinterpret_cast<uint32_t *>(d_rows);
+    // only the header fields matter; the small tables are rewritten by renewI before use
+    cudaStreamSynchronize(st);      // ordered after the memsets queued on st
+    cudaMemcpy(reinterpret_cast<char *>(d_state) + offsetof(RcState, gen), &h.gen, sizeof(RcState) - offsetof(RcState, gen),
+               cudaMemcpyHostToDevice);
+}
+
+size_t sp_ans_state_bytes() { return (sizeof(AnsState) + 255) & ~(size_t)255; }
+size_t sp_ans_ctx_bytes() { return (size_t)ANS_NCTX * (ANS_HDR_BYTES + ANS_BODY_BYTES); }
+
+// host-side init of one stream's state: generation gen0 (headers are zeroed: generation 0 = "no context")
+void sp_ans_state_init(void *d_state, void *d_ctx, uint32_t gen0, cudaStream_t st)
+{
+    struct { uint32_t gen; uint32_t pad[3]; uint4 *hdrs; uint4 *bodies; } h;
+    memset(&h, 0, sizeof h);
+    h.gen = gen0;
+    h.hdrs = reinterpret_cast<uint4 *>(d_ctx);
+    h.bodies = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(d_ctx) + (size_t)ANS_NCTX * ANS_HDR_BYTES);
+    static_assert(sizeof(h) == sizeof(AnsState) - offsetof(AnsState, gen), "AnsState tail layout");
+    cudaStreamSynchronize(st);
+    cudaMemcpy(reinterpret_cast<char *>(d_state) + offsetof(AnsState, gen), &h, sizeof h, cudaMemcpyHostToDevice);
+}
+
+void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, cudaStream_t st)
+{
+    if (n_jobs) sp_decode_kernel<<<n_jobs, 32, 0, st>>>(d_jobs);
+}
+
+}  // namespace jsp

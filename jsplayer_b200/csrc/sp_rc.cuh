@@ -1,4 +1,4 @@
-// sp_rc.cu -- ScreenPressor v2 entropy decode on sm_100a: 32-bit byte-wise range decoder with adaptive
+// sp_rc.cuh -- ScreenPressor v2 entropy decode on sm_100a: 32-bit byte-wise range decoder with adaptive
 // frequency tables.  Replaces reference src/RangeCoder.hx (whole file) and EntroCoderRC
 // (src/EntroCoders.hx:31-180) for one stream per warp.
 //
@@ -12,6 +12,7 @@
 //    search (RangeCoder.hx:58-65, :90-108) and a single division per symbol (see "table layout");
 //  * renewI (EntroCoders.hx:81-130) is O(1) for the 12288 colour rows: it bumps a generation number and rows
 //    with an older tag read as "all ones" (the reference also resets lazily, :85).
+#pragma once
 #include "sp_common.cuh"
 #include <cstddef>
 #include <cstring>
@@ -272,13 +273,9 @@ struct RcCoder {
     __device__ bool decodeBool() { return false; }
 };
 
-namespace {
-
-__global__ void __launch_bounds__(32)
-sp_rc_decode_kernel(const SpJob *__restrict__ jobs)
+// one frame of one range-coder stream; `sm` = this warp's shared memory
+__device__ __forceinline__ void sp_rc_run(const SpJob &J, RcSmall &sm)
 {
-    __shared__ RcSmall sm;
-    const SpJob J = jobs[blockIdx.x];
     RcState *st = reinterpret_cast<RcState *>(J.state);
     const int lane = (int)lane_id();
     RcCoder ec;
@@ -311,28 +308,6 @@ sp_rc_decode_kernel(const SpJob *__restrict__ jobs)
         for (int i = lane; i < (int)(sizeof(RcSmall) / 16); i += 32) g[i] = s[i];
     }
     if (lane == 0) { st->gen = ec.gen; if (bits) atomicOr(J.status, bits); }
-}
-
-}  // namespace
-
-size_t sp_rc_state_bytes() { return (sizeof(RcState) + 255) & ~(size_t)255; }
-size_t sp_rc_rows_bytes() { return (size_t)RC_ROWS * RC_ROW_STRIDE * 4; }
-
-// host-side init of one stream's state: generation 1, tables irrelevant until the first I frame
-void sp_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t st)
-{
-    RcState h;
-    memset(&h, 0, sizeof h);
-    h.gen = gen0; h.rows = reinterpret_cast<uint32_t *>(d_rows);
-    // only the header fields matter; the small tables are rewritten by renewI before use
-    cudaStreamSynchronize(st);      // ordered after the memsets queued on st
-    cudaMemcpy(reinterpret_cast<char *>(d_state) + offsetof(RcState, gen), &h.gen, sizeof(RcState) - offsetof(RcState, gen),
-               cudaMemcpyHostToDevice);
-}
-
-void launch_sp_rc(const SpJob *d_jobs, uint32_t n_jobs, cudaStream_t st)
-{
-    if (n_jobs) sp_rc_decode_kernel<<<n_jobs, 32, 0, st>>>(d_jobs);
 }
 
 }  // namespace jsp

@@ -3,7 +3,7 @@
  * adaptive table (FixedSizeRansCtx :54-145) and the escalating colour-context kinds (SymbList/Cx1-3 :155-208,
  * SmallContext/Cx4/Cx5 :210-392, Cx6 :394-704, Cx7 :706-772, Context :785-860, Sorter :862-872).
  * Used by the synthetic rANS encoder (sp_ans_enc.c); the CPU checker compiles the same models for its decoder.
- * Not part of libjsplayer_cuda (the CUDA decoder csrc/sp_ans.cu is an independent implementation).
+ * Not part of libjsplayer_cuda (the CUDA decoder csrc/sp_ans.cuh is an independent implementation).
  *
  * JavaScript typed-array semantics are explicit in the field types (Uint8Array -> uint8_t, Uint16Array -> uint16_t);
  * the reference's process-global statics (Context.rcv, SmallContext.totFr, Cx6.f0, Cx6._cnts/_freqs; ANS.hx:217,
