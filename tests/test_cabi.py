@@ -81,3 +81,22 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".c")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("oracle/msvideo1_oracle.c)", ""), f
+
+
+def test_header_is_plain_c_and_the_c_example_links(tmp_path):
+    """include/jsplayer_cuda.h must be consumable by a C compiler (the boundary other hosts bind), and the plain-C
+    example host must compile and link against the library.  Without a GPU it exits with the no-fallback message."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    probe = tmp_path / "probe.c"
+    probe.write_text('#include "jsplayer_cuda.h"\nint main(void) { return (int)sizeof(jsp_stream_desc) == 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", inc, "-c", str(probe), "-o", str(tmp_path / "probe.o")], check=True)
+    exe = str(tmp_path / "decode_avi")
+    libdir = os.path.join(ROOT, "jsplayer_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I", inc, os.path.join(ROOT, "examples", "decode_avi.c"), "-L", libdir,
+                    "-ljsplayer_cuda", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+    if _lib.load().jsp_device_count() <= 0:
+        r = subprocess.run([exe, "nonexistent.avi"], capture_output=True, text=True)
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr

@@ -92,3 +92,36 @@ def test_one_shot_multi_gpu_entry_matches(tmp_path):
         for f in range(lo, hi):
             assert (outs[i] == exp[fi][f]).all(), "file %d frame %d" % (fi, f)
             i += 1
+
+
+def test_plain_c_host_decodes_an_avi(tmp_path):
+    """examples/decode_avi.c (C99, links only libjsplayer_cuda): AVI file -> GOP segments -> jsp_batch_decode; its
+    per-frame checksums must equal the oracle's."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "decode_avi")
+    libdir = os.path.join(root, "jsplayer_b200")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "decode_avi.c"),
+                    "-L", libdir, "-ljsplayer_cuda", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    w, h = 128, 96
+    cases = []
+    frames, keys, _ = synth.sp_stream(w, h, 9, seed=31, version=4, gop=3, change_permille=60)
+    cases.append(("sp.avi", O.CODEC_SCREENPRESSOR, 24, b"SCPR", None, frames, keys))
+    pal = synth.random_palette(2)
+    frames = [synth.msv1_frame(True, w, h, 50 + f, skip_permille=0 if f % 4 == 0 else 300) for f in range(8)]
+    cases.append(("cram8.avi", O.CODEC_MSVC8, 8, b"CRAM", pal, frames, [1 if f % 4 == 0 else 0 for f in range(8)]))
+    for name, codec, bpp, four, pal, frames, keys in cases:
+        path = str(tmp_path / name)
+        write_avi(path, w, h, bpp, four, frames, keys, palette=pal)
+        r = subprocess.run([exe, path], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = [ln.split() for ln in r.stdout.splitlines() if ln.startswith("frame")]
+        exp = O.decode_stream(codec, w, h, bpp, frames, keys=keys, palette=pal)[0]
+        assert len(got) == len(frames)
+        for f, parts in enumerate(got):
+            s = 0
+            for v in exp[f].reshape(-1).astype(np.uint32).tolist():
+                s = (s * 31 + v) & 0xFFFFFFFF
+            assert int(parts[-1], 16) == s, "%s frame %d" % (name, f)
+            assert int(parts[parts.index("status") + 1]) == 0
