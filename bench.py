@@ -56,8 +56,11 @@ class C2(Workload):
     desc = "MSVideo1 RGB555 1920x1080 key frames, 25/50/25% 1/2/8-colour blocks, independent streams"
     dominant, dominant_name = 0, "msv1_decode_kernel<false>"
 
-    def __init__(self, frames=1024):
+    def __init__(self, frames=1024, mix=None):
         self.n = frames
+        if mix:
+            self.MIX = tuple(mix)
+            self.desc = "MSVideo1 RGB555 1920x1080 key frames, %d/%d/%d%% 1/2/8-colour blocks (sweep), independent streams" % self.MIX
 
     def frames(self, rank, n=None, threads=16):
         from jsplayer_b200 import synth
@@ -169,7 +172,7 @@ def make_workload(name, args):
     if name == "c5":
         return C5(args.files)
     if name == "c2":
-        return C2(args.frames)
+        return C2(args.frames, args.c2_mix)
     if name == "c3":
         return SPWorkload(args.streams or 256, 4, 1280, 720, 1, args.sp_versions, 32, 0xC0DEC3, 40, "c3",
                           "decoded Mpixel/s (ScreenPressor RGB24 720p key frames)",
@@ -365,6 +368,7 @@ def measure(wl, args, rank, local_rank, world, dist, torch, with_e2e=True, with_
     ms_total, kms, kcnt = bd.time_runs(warmup=0, iters=args.steps, flush_l2=flush)
     barrier()
     clocks = sampler.stop()
+    n_symbols = bd.symbols()
     t_local = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
@@ -423,6 +427,13 @@ def measure(wl, args, rank, local_rank, world, dist, torch, with_e2e=True, with_
                          "share_of_step": share},
             "clocks": clocks,
         }
+        if n_symbols:
+            # the entropy stage is latency-bound (one dependent chain per stream): its natural unit is symbols / s
+            ent_ms = sum(kms[i] for i in (2, 3, 6)) / args.steps
+            line["entropy"] = {"symbols_per_step": n_symbols, "symbols_per_pixel": n_symbols / st["pixels"],
+                               "msymbols_per_s": n_symbols / (ms_per_step * 1e-3) / 1e6,
+                               "entropy_kernel_ms_per_step": ent_ms,
+                               "note": "one warp per independent segment; a warp needs 0.5-0.8 us per symbol (DESIGN.md 4.3)"}
         line["e2e"] = e2e if e2e else {"value": None, "unit": "Mpixel/s", "skipped": "--e2e-steps 0 (pictures of this batch do not fit pinned host memory comfortably)"}
         if with_cpu and not args.no_cpu_baseline:
             n_s = sample_size(wl, cores, len(specs))
@@ -441,6 +452,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--files", type=int, default=8, help="c5: AVI files per GPU")
+    ap.add_argument("--c2-mix", type=lambda s: [int(x) for x in s.split(",")], default=None,
+                    help="c2 sweep: percentages of 1-/2-/8-colour blocks, e.g. 100,0,0 (default 25,50,25 = the quoted config)")
     ap.add_argument("--frames", type=int, default=1024, help="c2: frames (= independent streams) per GPU")
     ap.add_argument("--streams", type=int, default=0, help="c3/c4: streams per GPU (default 256 / 128)")
     ap.add_argument("--sp-versions", type=lambda s: [int(x) for x in s.split(",")], default=[2, 4],
@@ -498,7 +511,7 @@ def main():
             a2.streams, a2.steps, a2.e2e_steps = streams, min(args.steps, 5), 1
             try:
                 l2 = measure(make_workload(name, a2), a2, 0, local_rank, 1, dist, torch)
-                codecs[name] = {k: l2[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "kernels", "roofline", "e2e", "cpu_baseline") if k in l2}
+                codecs[name] = {k: l2[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "kernels", "roofline", "entropy", "e2e", "cpu_baseline") if k in l2}
             except (Exception, SystemExit) as e:       # a failed extra leg must not lose the headline line
                 codecs[name] = {"error": str(e)}
         line["codecs"] = codecs

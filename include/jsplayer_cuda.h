@@ -126,6 +126,10 @@ JSP_API int        jsp_batch_stats(jsp_batch *b, uint64_t *pixels, uint64_t *alg
  * writes (and previous pictures it copies) + compressed bytes it reads; intermediates excluded. */
 JSP_API int        jsp_batch_kernel_bytes(jsp_batch *b, uint64_t *bytes);
 
+/* Entropy-coded symbols the ScreenPressor kernels decoded in the last jsp_batch_run() (all frames); the entropy stage
+ * is latency-bound, so its throughput is reported in symbols / s rather than bytes / s. */
+JSP_API int64_t    jsp_batch_symbols(jsp_batch *b);
+
 /* One-shot convenience with the signature SURVEY.md 8b sketches; shards streams longest-first over
  * n_gpus devices of this process (no collectives: GOPs/streams are independent). */
 JSP_API int jsp_batch_decode(const jsp_stream_desc *streams, int n_streams, int n_gpus,

@@ -60,6 +60,7 @@ PROTOTYPES = {
     "jsp_batch_device_frame": (C.c_uint64, [C.c_void_p, C.c_int64]),
     "jsp_batch_time_runs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jsp_batch_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jsp_batch_symbols": (C.c_int64, [C.c_void_p]),
     "jsp_batch_kernel_bytes": (C.c_int, [C.c_void_p, C.c_void_p]),
     "jsp_avi_parse": (C.c_void_p, [C.c_void_p, C.c_uint64]),
     "jsp_avi_free": (None, [C.c_void_p]),

@@ -219,6 +219,10 @@ class BatchDecoder:
         self._lib.jsp_batch_stats(self._h, *[C.byref(x) for x in v])
         return dict(pixels=v[0].value, alg_bytes=v[1].value, in_bytes=v[2].value, out_bytes=v[3].value)
 
+    def symbols(self):
+        """Entropy-coded symbols the ScreenPressor kernels decoded in the last run (0 for MSVideo1-only batches)."""
+        return int(self._check(self._lib.jsp_batch_symbols(self._h), "jsp_batch_symbols"))
+
     def kernel_bytes(self):
         """Algorithmic bytes per run of every kernel class (index = JSP_K_*)."""
         v = (C.c_uint64 * _lib.JSP_N_KERNELS)()

@@ -257,6 +257,7 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             J.dst = b->d_out + R.out_off;
             J.prev = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
             J.status = b->d_status + f;
+            J.symbols = b->d_sp_symbols ? b->d_sp_symbols + f : nullptr;
             const size_t slot = R.sp_seg > 0 ? (size_t)(R.sp_seg % H.n_slots) : 0;
             J.state = b->d_sp_state + H.state_off + slot * H.state_stride;
             J.bts = b->d_sp_bts + H.bts_off + slot * H.bts_stride;
@@ -355,6 +356,8 @@ static bool run_plan(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *
     if (P.n_tickets && !JSP_CUDA(cudaMemsetAsync(b->d_tickets + P.ticket_off, 0, P.n_tickets * 4, st))) return false;
     if (P.frame_hi > P.frame_lo &&
         !JSP_CUDA(cudaMemsetAsync(b->d_status + P.frame_lo, 0, (size_t)(P.frame_hi - P.frame_lo) * 4, st))) return false;
+    if (b->d_sp_symbols && P.frame_hi > P.frame_lo &&
+        !JSP_CUDA(cudaMemsetAsync(b->d_sp_symbols + P.frame_lo, 0, (size_t)(P.frame_hi - P.frame_lo) * 4, st))) return false;
     int k = 0;
     for (const Launch &L : P.launches) {
         if (ev) { cudaEventRecord(ev[2 * k], st); ev_class->push_back(L.kclass); }
@@ -503,7 +506,7 @@ void jsp_batch_destroy(jsp_batch *b)
                     b->d_tile_cnt, b->d_tickets, b->d_sig_cur, b->d_sig_prev, b->d_sig_status, b->d_sig_first, b->d_sig_npx,
                     b->d_stream_first, b->d_stream_count, b->d_frame_codec, b->d_flush, b->d_spjobs, b->d_sp_state,
                     b->d_sp_rows, b->d_sp_bts, b->d_kd_cur, b->d_kd_prev, b->d_kd_status, b->d_kd_first, b->d_kd_npx,
-                    b->d_disp, b->d_disp_jobs};
+                    b->d_disp, b->d_disp_jobs, b->d_sp_symbols};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (b->h_status) cudaFreeHost(b->h_status);
     if (b->st_compute) cudaStreamDestroy(b->st_compute);
@@ -646,6 +649,7 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
             if (!grow(b->d_sp_state, b->sp_state_cap, st_cur)) return -1;
             if (!grow(b->d_sp_rows, b->sp_rows_cap, rows_cur)) return -1;
             if (!grow(b->d_sp_bts, b->sp_bts_cap, bts_cur)) return -1;
+            if (!grow(b->d_sp_symbols, b->sp_symbols_cap, (size_t)nf, true)) return -1;
             if (!keep || fresh_alloc) {
                 // generation tags of all rows to 0, generations start at 1: every row reads as "all ones"
                 if (!JSP_CUDA(cudaMemsetAsync(b->d_sp_rows, 0, rows_cur, b->st_compute))) return -1;
@@ -932,6 +936,19 @@ int jsp_batch_stats(jsp_batch *b, uint64_t *pixels, uint64_t *alg_bytes, uint64_
     if (in_bytes) *in_bytes = b->stat_in_bytes;
     if (out_bytes) *out_bytes = b->stat_out_bytes;
     return 0;
+}
+
+int64_t jsp_batch_symbols(jsp_batch *b)
+{
+    if (!b) return -1;
+    if (!b->d_sp_symbols) return 0;
+    if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
+    std::vector<uint32_t> h(b->frames.size());
+    if (!JSP_CUDA(cudaStreamSynchronize(b->st_compute))) return -1;
+    if (!JSP_CUDA(cudaMemcpy(h.data(), b->d_sp_symbols, h.size() * 4, cudaMemcpyDeviceToHost))) return -1;
+    int64_t n = 0;
+    for (uint32_t v : h) n += v;
+    return n;
 }
 
 int jsp_batch_kernel_bytes(jsp_batch *b, uint64_t *bytes)

@@ -129,6 +129,7 @@ struct jsp_batch {
     uint8_t *d_sp_state = nullptr; size_t sp_state_cap = 0;
     uint8_t *d_sp_rows = nullptr;  size_t sp_rows_cap = 0;
     uint8_t *d_sp_bts = nullptr;   size_t sp_bts_cap = 0;
+    uint32_t *d_sp_symbols = nullptr; size_t sp_symbols_cap = 0;   // per frame: entropy-coded symbols decoded (reporting)
     int persist_streams = 0;                       // per-stream drop-in: keep codec state across configure calls
     // significance post-pass tables
     const int32_t **d_sig_cur = nullptr; const int32_t **d_sig_prev = nullptr; uint32_t **d_sig_status = nullptr;

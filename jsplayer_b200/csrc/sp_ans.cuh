@@ -608,6 +608,7 @@ struct AnsCoder {
     const uint8_t *data;
     uint32_t len, pos, wbase;
     int nDec;
+    uint32_t nsym;                                                    // symbols decoded in this frame (reporting only)
     bool overrun, fail;
 
     __device__ __forceinline__ bool failed() const { return fail; }
@@ -661,7 +662,7 @@ struct AnsCoder {
     }
     __device__ __forceinline__ void count()                           // EntroCoders.hx:249-253
     {
-        nDec++;
+        nDec++; nsym++;
         if (nDec == ANS_B) { reinit(pos); nDec = 0; }
     }
 
@@ -806,7 +807,7 @@ __device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm)
     AnsCoder ec;
     ec.sm = &sm; ec.hdrs = st->hdrs; ec.bodies = st->bodies; ec.gen = st->gen;
     ec.f0 = (J.flags & SPJ_ANS_V3) ? 64 : 32;                         // Cx6.f0, EntroCoders.hx:210 / ScreenPressor.hx:69-72
-    ec.fail = false; ec.overrun = false; ec.x = 0; ec.data = J.src; ec.len = J.len; ec.pos = 0; ec.wbase = 0x80000000u; ec.nDec = 0;
+    ec.fail = false; ec.overrun = false; ec.x = 0; ec.data = J.src; ec.len = J.len; ec.pos = 0; ec.wbase = 0x80000000u; ec.nDec = 0; ec.nsym = 0;
     {
         const uint4 *g = reinterpret_cast<const uint4 *>(&st->small);
         uint4 *s = reinterpret_cast<uint4 *>(&sm.small);
@@ -832,7 +833,7 @@ __device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm)
         const uint4 *s = reinterpret_cast<const uint4 *>(&sm.small);
         for (int i = lane; i < (int)(sizeof(AnsSmall) / 16); i += 32) g[i] = s[i];
     }
-    if (lane == 0) { st->gen = ec.gen; if (bits) atomicOr(J.status, bits); }
+    if (lane == 0) { st->gen = ec.gen; if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
 }
 
 }  // namespace jsp

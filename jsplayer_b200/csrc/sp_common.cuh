@@ -32,6 +32,7 @@ struct SpJob {
     uint32_t len, X, Y, flags;
     uint32_t insign_blocks;   // nbx * ceil(insignificant_lines / 16) (ScreenPressor.hx:86-89)
     uint32_t pad;
+    uint32_t      *symbols;   // entropy-coded symbols this frame decoded (reporting: symbols / s), may be null
 };
 
 constexpr uint32_t FULLMASK = 0xffffffffu;

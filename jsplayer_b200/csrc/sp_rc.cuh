@@ -82,6 +82,7 @@ struct RcCoder {
     uint32_t range, code;
     const uint8_t *data;
     uint32_t len, pos, wbase;
+    uint32_t nsym;                                             // symbols decoded in this frame (reporting only)
     bool poisoned, fail;
 
     __device__ __forceinline__ bool failed() const { return fail; }
@@ -147,6 +148,7 @@ struct RcCoder {
     __device__ int decode_tiny(RcTiny &t, uint32_t step)
     {
         const int lane = (int)lane_id();
+        nsym++;
         uint32_t p = t.P[lane];
         uint32_t tot = __shfl_sync(FULLMASK, p, N - 1);
         if (poisoned) fail = true;
@@ -176,6 +178,7 @@ struct RcCoder {
     __device__ __forceinline__ int decode_big(uint32_t *tab, uint32_t step)
     {
         const int lane = (int)lane_id();
+        nsym++;
         uint32_t lp[K];
         uint32_t base, tot;
         bool fresh = false;
@@ -280,7 +283,7 @@ __device__ __forceinline__ void sp_rc_run(const SpJob &J, RcSmall &sm)
     const int lane = (int)lane_id();
     RcCoder ec;
     ec.sm = &sm; ec.rows = st->rows; ec.gen = st->gen;
-    ec.fail = false; ec.poisoned = false; ec.range = 0; ec.code = 0; ec.data = J.src; ec.len = J.len; ec.pos = 0; ec.wbase = 0x80000000u;
+    ec.fail = false; ec.poisoned = false; ec.range = 0; ec.code = 0; ec.data = J.src; ec.len = J.len; ec.pos = 0; ec.wbase = 0x80000000u; ec.nsym = 0;
     // models persist from frame to frame until the next I frame: restore the small tables
     {
         const uint4 *g = reinterpret_cast<const uint4 *>(&st->small);
@@ -307,7 +310,7 @@ __device__ __forceinline__ void sp_rc_run(const SpJob &J, RcSmall &sm)
         const uint4 *s = reinterpret_cast<const uint4 *>(&sm);
         for (int i = lane; i < (int)(sizeof(RcSmall) / 16); i += 32) g[i] = s[i];
     }
-    if (lane == 0) { st->gen = ec.gen; if (bits) atomicOr(J.status, bits); }
+    if (lane == 0) { st->gen = ec.gen; if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
 }
 
 }  // namespace jsp

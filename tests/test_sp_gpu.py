@@ -209,3 +209,25 @@ def test_16bpp_corrupt_stream_stays_in_bounds():
         for _ in range(3):
             badp[int(rng.integers(2, len(badp)))] ^= int(rng.integers(1, 256))
         check(w, h, 16, [frames[0], bytes(badp), frames[2]], keys)
+
+
+def test_symbol_count_matches_the_oracle():
+    """jsp_batch_symbols: the device-side count of entropy-coded symbols equals the oracle's (both coders)."""
+    import ctypes as C
+    lib = O.load()
+    lib.ora_symbol_count.restype = C.c_ulonglong
+    lib.ora_symbol_count.argtypes = [C.c_int]
+    for version in (2, 4):
+        w, h = 160, 120
+        frames, keys, pics = synth.sp_stream(w, h, 6, seed=40 + version, version=version, gop=3, change_permille=80)
+        lib.ora_symbol_count(1)
+        O.decode_stream(O.CODEC_SCREENPRESSOR, w, h, 24, frames, keys=keys)
+        want = lib.ora_symbol_count(1)
+        bd = BatchDecoder()
+        bd.configure([StreamSpec(SP, w, h, 24, frames=frames, keys=keys)])
+        bd.upload(); bd.run(); bd.sync()
+        got = bd.symbols()
+        bd.run(); bd.sync()
+        assert bd.symbols() == got                                  # per run, not cumulative
+        bd.close()
+        assert got == want and got > 0
