@@ -5,6 +5,8 @@
 
 nvcc cross-compiles without a GPU, so this runs on the CPU-only build container too.
 """
+import fcntl
+import hashlib
 import os
 import subprocess
 import sys
@@ -25,39 +27,84 @@ def _sources(d, exts):
     return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(exts))
 
 
-def _stale(target, deps):
+def _digest(deps, flags):
+    h = hashlib.sha256(" ".join(flags).encode())
+    for d in sorted(deps):
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def _stale(target, deps, flags=()):
+    """Content-based (not mtime-based): a snapshot copied to another machine keeps its built libraries valid."""
     if not os.path.exists(target):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        return open(target + ".srchash").read().strip() != _digest(deps, flags)
+    except OSError:
+        return True
+
+
+def _stamp(target, deps, flags=()):
+    with open(target + ".srchash", "w") as fh:
+        fh.write(_digest(deps, flags))
+
+
+class _Lock:
+    """One builder at a time (torchrun starts several ranks that may all find a stale library)."""
+
+    def __init__(self, target):
+        self.path = target + ".lock"
+
+    def __enter__(self):
+        self.fh = open(self.path, "w")
+        fcntl.flock(self.fh, fcntl.LOCK_EX)
+
+    def __exit__(self, *a):
+        fcntl.flock(self.fh, fcntl.LOCK_UN)
+        self.fh.close()
 
 
 def build_cuda(force=False, verbose=False):
     srcs = _sources(CSRC, (".cu", ".cpp"))
     deps = srcs + _sources(CSRC, (".cuh", ".h")) + [os.path.join(HERE, "..", "include", "jsplayer_cuda.h")]
-    if not force and not _stale(CUDA_LIB, deps):
+    if not force and not _stale(CUDA_LIB, deps, NVCC_FLAGS):
         return CUDA_LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", CUDA_LIB] + srcs
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libjsplayer_cuda.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+    with _Lock(CUDA_LIB):
+        if not force and not _stale(CUDA_LIB, deps, NVCC_FLAGS):      # another process built it while we waited
+            return CUDA_LIB
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        tmp = CUDA_LIB + ".tmp%d" % os.getpid()
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed building libjsplayer_cuda.so")
+        os.replace(tmp, CUDA_LIB)
+        _stamp(CUDA_LIB, deps, NVCC_FLAGS)
+        if verbose:
+            sys.stderr.write(r.stderr)
     return CUDA_LIB
 
 
 def build_synth(force=False):
     srcs = _sources(SYNTH, (".c",))
-    if not force and not _stale(SYNTH_LIB, srcs):
+    deps = srcs + _sources(SYNTH, (".h",))
+    if not force and not _stale(SYNTH_LIB, deps):
         return SYNTH_LIB
-    cc = os.environ.get("CC", "gcc")
-    cmd = [cc, "-O2", "-std=gnu11", "-fPIC", "-shared", "-Wall", "-o", SYNTH_LIB] + srcs + ["-lm"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("gcc failed building libjsplayer_synth.so")
+    with _Lock(SYNTH_LIB):
+        if not force and not _stale(SYNTH_LIB, deps):
+            return SYNTH_LIB
+        cc = os.environ.get("CC", "gcc")
+        tmp = SYNTH_LIB + ".tmp%d" % os.getpid()
+        cmd = [cc, "-O2", "-std=gnu11", "-fPIC", "-shared", "-Wall", "-o", tmp] + srcs + ["-lm"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("gcc failed building libjsplayer_synth.so")
+        os.replace(tmp, SYNTH_LIB)
+        _stamp(SYNTH_LIB, deps)
     return SYNTH_LIB
 
 

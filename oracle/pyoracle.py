@@ -4,6 +4,8 @@ TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.
 --impl reference legs.  Nothing in jsplayer_b200/ imports this module.
 """
 import ctypes as C
+import fcntl
+import hashlib
 import os
 import subprocess
 
@@ -24,10 +26,38 @@ class StreamDesc(C.Structure):
                 ("frame_key", C.c_void_p), ("out", C.c_void_p)]
 
 
+def _digest(srcs):
+    h = hashlib.sha256()
+    for s in sorted(srcs):
+        h.update(os.path.basename(s).encode())
+        with open(s, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build(force=False):
-    srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".c", ".h"))]
-    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
-        subprocess.run(["make", "-C", HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+    """Builds liboracle.so when its sources changed (content hash, not mtimes: the built file travels with a snapshot of
+    the repo); one builder at a time (torchrun ranks)."""
+    models = os.path.join(os.path.dirname(HERE), "jsplayer_b200", "synth")
+    srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
+    srcs += [os.path.join(models, f) for f in ("ans_models.c", "ans_models.h")]
+    stamp = LIB_PATH + ".srchash"
+
+    def stale():
+        try:
+            return not os.path.exists(LIB_PATH) or open(stamp).read().strip() != _digest(srcs)
+        except OSError:
+            return True
+    if force or stale():
+        with open(LIB_PATH + ".lock", "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or stale():
+                    subprocess.run(["make", "-C", HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+                    with open(stamp, "w") as fh:
+                        fh.write(_digest(srcs))
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
