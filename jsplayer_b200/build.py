@@ -69,20 +69,22 @@ class _Lock:
 def build_cuda(force=False, verbose=False):
     srcs = _sources(CSRC, (".cu", ".cpp"))
     deps = srcs + _sources(CSRC, (".cuh", ".h")) + [os.path.join(HERE, "..", "include", "jsplayer_cuda.h")]
-    if not force and not _stale(CUDA_LIB, deps, NVCC_FLAGS):
+    extra = os.environ.get("JSP_NVCC_EXTRA", "").split()          # e.g. -DJSP_PROFILE_SECTIONS (diagnostic builds)
+    flags = NVCC_FLAGS + extra
+    if not force and not _stale(CUDA_LIB, deps, flags):
         return CUDA_LIB
     with _Lock(CUDA_LIB):
-        if not force and not _stale(CUDA_LIB, deps, NVCC_FLAGS):      # another process built it while we waited
+        if not force and not _stale(CUDA_LIB, deps, flags):          # another process built it while we waited
             return CUDA_LIB
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         tmp = CUDA_LIB + ".tmp%d" % os.getpid()
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
+        cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("nvcc failed building libjsplayer_cuda.so")
         os.replace(tmp, CUDA_LIB)
-        _stamp(CUDA_LIB, deps, NVCC_FLAGS)
+        _stamp(CUDA_LIB, deps, flags)
         if verbose:
             sys.stderr.write(r.stderr)
     return CUDA_LIB

@@ -246,8 +246,11 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
                 plan.launches.push_back({JSP_K_FRAME_COPY, FK_COPY, first, (uint32_t)(T.jobs.size() - first), maxv, 0});
         }
         const size_t first = T.spjobs.size();
-        int n_rc = 0, n_ans = 0;
-        for (int64_t f : by_level[lv]) {
+        int n_rc = 0, n_ans = 0; uint32_t max_w = 0;
+        // longest frames first: when a launch has more warps than the device holds, the late starters are the short ones
+        std::vector<int64_t> order(by_level[lv]);
+        std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return b->frames[x].len > b->frames[y].len; });
+        for (int64_t f : order) {
             const FrameRec &R = b->frames[f];
             if (R.kind != FK_SP_I && R.kind != FK_SP_P && !(R.kind == FK_SP_FLAT && (R.sp_flags & SPJ_RENEW))) continue;
             const StreamRec &S = b->streams[R.stream];
@@ -264,11 +267,12 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             J.X = (uint32_t)S.w; J.Y = (uint32_t)S.h; J.flags = R.sp_flags | (H.version > 2 ? SPJ_ANS : 0u);
             J.insign_blocks = (uint32_t)(((S.w + 15) / 16) * ((std::max(0, b->insign_lines) + 15) / 16));
             (H.version > 2 ? n_ans : n_rc)++;
+            max_w = std::max(max_w, J.X);
             T.spjobs.push_back(J);
         }
         if (T.spjobs.size() > first) {
             const int kclass = n_ans == 0 ? JSP_K_SP_ENTROPY_RC : (n_rc == 0 ? JSP_K_SP_ENTROPY_ANS : JSP_K_SP_ENTROPY_MIXED);
-            plan.launches.push_back({kclass, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), 0, 0});
+            plan.launches.push_back({kclass, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), max_w, 0});
         }
     }
     plan.n_spjobs = T.spjobs.size() - plan.spjob_off;
@@ -370,7 +374,7 @@ static bool run_plan(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *
                                b->d_tile_map, b->d_tile_cnt, b->d_tickets + L.ticket, b->sm_count, st);
             break;
         case JSP_K_SP_ENTROPY_RC: case JSP_K_SP_ENTROPY_ANS: case JSP_K_SP_ENTROPY_MIXED:
-            launch_sp_decode(b->d_spjobs + L.first, L.count, st);
+            launch_sp_decode(b->d_spjobs + L.first, L.count, L.max_vec4, st);
             break;
         default: break;
         }

@@ -43,7 +43,7 @@ void sp_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t s
 size_t sp_ans_state_bytes();
 size_t sp_ans_ctx_bytes();
 void sp_ans_state_init(void *d_state, void *d_ctx, uint32_t gen0, cudaStream_t st);
-void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, cudaStream_t st);   // sp_decode.cu: both coders, one launch
+void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, cudaStream_t st);   // sp_decode.cu: both coders, one launch
 
 struct StreamRec {
     int codec, w, h, bpp;

@@ -718,6 +718,57 @@ struct AnsCoder {
         uint4 hv = make_uint4(0, 0, 0, 0);
         if (lane < 4) hv = gh[lane];
         const int f = get();
+        // ---- fast path: a Cx4 context (<= 4 symbols met: the common case on screen content) that HITS one of its
+        //      symbols.  SmallContext.decodeSC (ANS.hx:263-309) for S = 4, run by every lane from three broadcast
+        //      words -- no shared-memory staging, no divergence.  Anything else (a new symbol, other kinds) falls
+        //      through to the generic path below with nothing modified. ----
+        {
+            const uint32_t h_gen = __shfl_sync(FULLMASK, hv.x, 0), h_w1 = __shfl_sync(FULLMASK, hv.y, 0);
+            if (h_gen == gen && ((h_w1 >> 16) & 0xFFu) == CXK_4) {
+                const uint32_t symw = __shfl_sync(FULLMASK, bv.x, 0);                         // symbols[0..3]
+                const uint32_t f01 = __shfl_sync(FULLMASK, bv.x, 1), f23 = __shfl_sync(FULLMASK, bv.y, 1);   // freqs[0..3]
+                const int d = (int)(h_w1 & 0xFFFFu);
+                int mp = (int)(h_w1 >> 24);
+                uint32_t fq[4] = {f01 & 0xFFFFu, f01 >> 16, f23 & 0xFFFFu, f23 >> 16};
+                const int tot0 = (int)(fq[0] + fq[1] + fq[2] + fq[3]) + 256 - d;              // Cx4.decode, :320
+                int tot = tot0, shift = 0;
+                while (tot <= ANS_SCALE / 2 && tot > 0) { tot <<= 1; shift++; }
+                const int sf = f >> shift;
+                const int bonus = (ANS_SCALE - tot) >> shift;
+                int cumFr = 0, lastSymb = 0, hit = -1, hstart = 0, hfr = 0;
+                bool miss = false;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i < d && hit < 0 && !miss) {
+                        const int sy = (int)((symw >> (8 * i)) & 0xFFu);
+                        const int fr = (int)((fq[i] + (i == mp ? (uint32_t)bonus : 0u)) & 0xFFFFu);
+                        const int startFr = cumFr + sy - lastSymb;
+                        if (sf < startFr) miss = true;                                        // a symbol not met yet
+                        else if (startFr + fr > sf) { hit = i; hstart = startFr; hfr = fr; }
+                        else { cumFr += sy - lastSymb + fr; lastSymb = sy + 1; }
+                    }
+                }
+                if (hit >= 0) {
+                    const int c = (int)((symw >> (8 * hit)) & 0xFFu);
+                    uint32_t fh = 0, fm = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { if (i == hit) { fq[i] = (fq[i] + 50u) & 0xFFFFu; fh = fq[i]; } }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) if (i == mp) fm = fq[i];
+                    const int mp0 = mp;
+                    if (hit != mp && fh > fm) mp = hit;                                       // :291-292
+                    if (tot0 + 50 + 50 > ANS_SCALE) {                                         // rescale, :254-261
+#pragma unroll
+                        for (int i = 0; i < 4; i++) if (i < d) fq[i] = (fq[i] - (fq[i] >> 1)) & 0xFFFFu;
+                    }
+                    if (lane == 1) *reinterpret_cast<uint2 *>(gb + 1) = make_uint2(fq[0] | (fq[1] << 16), fq[2] | (fq[3] << 16));
+                    if (lane == 0 && mp != mp0) reinterpret_cast<uint32_t *>(gh)[1] = (h_w1 & 0x00FFFFFFu) | ((uint32_t)mp << 24);
+                    advance(hstart << shift, hfr << shift);
+                    count();
+                    return c;
+                }
+            }
+        }
         uint4 *sh4 = reinterpret_cast<uint4 *>(&sm->hdr), *sb4 = reinterpret_cast<uint4 *>(sm->body);
         sb4[lane] = bv;
         if (lane < 4) sh4[lane] = hv;
@@ -800,7 +851,7 @@ struct AnsCoder {
 };
 
 // one frame of one rANS stream; `sm` = this warp's shared memory
-__device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm)
+__device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm, uint32_t *ring)
 {
     AnsState *st = reinterpret_cast<AnsState *>(J.state);
     const int lane = (int)lane_id();
@@ -818,7 +869,7 @@ __device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm)
     if (J.flags & SPJ_RENEW) {
         ec.renewI();
     } else if (J.flags & SPJ_IFRAME) {
-        sp_decode_iframe(ec, J);
+        sp_decode_iframe(ec, J, ring);
         bits |= ST_CHANGED;
     } else {
         sp_decode_pframe(ec, J, bits);

@@ -79,6 +79,41 @@ __device__ __forceinline__ uint32_t sp_segment(int32_t *dst, const int32_t *prev
     return last;
 }
 
+// I frames: predictors 2 / 4 / 5 read the row above (ScreenPressor.hx:253-272).  Reading it back from global memory would
+// put an L2 round trip on the serial chain of every such run (stores do not stay in L1), so the last X + 1 pixels also
+// live in a shared-memory ring ("a ring of the last X+1 pixels is sufficient").
+__device__ __forceinline__ uint32_t sp_ring_size(uint32_t X) { return 1u << (32 - __clz(X + 65u)); }   // power of two > X + 65
+
+__device__ __forceinline__ uint32_t sp_segment_ring(int32_t *dst, uint32_t *ring, uint32_t rmask, long i, int m, int ptype,
+                                                    uint32_t clr, uint32_t left, long X, long end)
+{
+    const int lane = (int)lane_id();
+    const long idx = i + lane;
+    auto rd = [&](long j) -> uint32_t { return j >= 0 ? ring[(uint32_t)j & rmask] : 0u; };
+    uint32_t v = clr;
+    switch (ptype) {
+    case 1: v = left; break;
+    case 2: v = rd(idx - X); break;
+    case 5: v = rd(idx - X - 1); break;
+    case 4: {
+        uint32_t d = lane < m ? vsub4(rd(idx - X), rd(idx - X - 1)) : 0u;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULLMASK, d, s);
+            if (lane >= s) d = vadd4(d, o);
+        }
+        v = vadd4(left, d) & 0x00FFFFFFu;
+        break;
+    }
+    default: break;
+    }
+    __syncwarp();                                   // every lane has read the row above before its slots are reused
+    if (lane < m && idx < end) { dst[idx] = (int32_t)v; ring[(uint32_t)idx & rmask] = v; }
+    const uint32_t last = __shfl_sync(FULLMASK, v, (m - 1) & 31);
+    __syncwarp();
+    return last;
+}
+
 // A frame whose entropy decode failed shows the previous picture (a P frame returns the retained buffer) or
 // nothing (a failed I frame has already dropped prevFrame, ScreenPressor.hx:110): undo the partial writes.
 __device__ __forceinline__ void sp_undo_frame(const SpJob &J, bool iframe)
@@ -106,10 +141,26 @@ __device__ __forceinline__ int sp_ctx_index(Coder &ec, int channel, int cx, int 
 // a warp busy for ever.  No encoder emits them: a frame that needs more run-loop iterations than this is failed.
 __device__ __forceinline__ long sp_run_budget(long X, long Y) { return 2 * X * Y + 16 * ((X + 15) / 16) * ((Y + 15) / 16) + 4096; }
 
+// Optional section timing (build with JSP_NVCC_EXTRA=-DJSP_PROFILE_SECTIONS): cycles spent per warp in the pieces of the
+// I-frame loop, summed into g_sp_prof[] -- how the per-symbol latency was broken down.
+#ifdef JSP_PROFILE_SECTIONS
+__device__ unsigned long long g_sp_prof[8];
+#define JSP_T0 const long long _t0 = clock64();
+#define JSP_T1(k) _acc[k] += clock64() - _t0;
+#define JSP_PROF_DECL long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define JSP_PROF_FLUSH if (lane_id() == 0) { for (int _k = 0; _k < 8; _k++) atomicAdd(&g_sp_prof[_k], (unsigned long long)_acc[_k]); }
+#else
+#define JSP_T0
+#define JSP_T1(k)
+#define JSP_PROF_DECL
+#define JSP_PROF_FLUSH
+#endif
+
 // ---- the frame loops, generic over the entropy coder (EntroCoder interface, EntroCoders.hx:8-24) ----
 template <class Coder>
-__device__ void sp_decode_iframe(Coder &ec, const SpJob &J)
+__device__ void sp_decode_iframe(Coder &ec, const SpJob &J, uint32_t *ring)
 {
+    const uint32_t rmask = sp_ring_size(J.X) - 1u;
     const long X = J.X, end = (long)J.X * J.Y;
     int32_t *dst = J.dst;
     const int cxshift = (J.flags & SPJ_CXSHIFT0) ? 0 : 2;
@@ -140,30 +191,45 @@ __device__ void sp_decode_iframe(Coder &ec, const SpJob &J)
         k += n;
         for (int o = 0; o < n; o += 32) {
             const long idx = di + o + lane;
-            if (o + lane < n && idx < end) dst[idx] = (int32_t)clr;
+            if (o + lane < n && idx < end) { dst[idx] = (int32_t)clr; if (ring) ring[(uint32_t)idx & rmask] = clr; }
         }
         if (n > 0) lastval = clr;
         di += n;
     }
     __syncwarp();
     int ptype = 0;
+    JSP_PROF_DECL
+#ifdef JSP_PROFILE_SECTIONS
+    const long long _tall = clock64();
+#endif
     while (di < end) {                             // :218-286
         if (--budget < 0) ec.fail = true;
-        ptype = ec.decodeP(ptype);
-        if (ptype == 0) clr = decode_rgb();
-        int n = ec.decodeN(ptype);
+        { JSP_T0 ptype = ec.decodeP(ptype); JSP_T1(0) }
+        if (ptype == 0) { JSP_T0 clr = decode_rgb(); JSP_T1(1) }
+        int n;
+        { JSP_T0 n = ec.decodeN(ptype); JSP_T1(2) }
         if (ec.failed()) return;
         if (ptype == 3 || ptype > 5) n = 0;        // no such predictor in an I frame: nothing is written
         if (ptype == 1) clr = lastval;             // `clr = dst[lasti]` even for an empty run (:252)
+        { JSP_T0
         for (int o = 0; o < n; o += chunk) {
             const int m = n - o < chunk ? n - o : chunk;
-            lastval = sp_segment(dst, nullptr, di + o, m, ptype, clr, lastval, X, end);
+            lastval = ring ? sp_segment_ring(dst, ring, rmask, di + o, m, ptype, clr, lastval, X, end)
+                           : sp_segment(dst, nullptr, di + o, m, ptype, clr, lastval, X, end);
         }
+        JSP_T1(3) }
         if (n > 0 && ptype != 0) clr = lastval;
         di += n;
         cx1 = ((int)clr & maskcx1) >> shiftcx1;    // :274-275
         cx = (int)clr >> shiftcx;
+#ifdef JSP_PROFILE_SECTIONS
+        _acc[5]++;
+#endif
     }
+#ifdef JSP_PROFILE_SECTIONS
+    _acc[4] += clock64() - _tall;
+#endif
+    JSP_PROF_FLUSH
 }
 
 template <class Coder>

@@ -8,15 +8,17 @@
 namespace jsp {
 namespace {
 
-constexpr size_t SP_SMEM = sizeof(AnsShared) > sizeof(RcSmall) ? sizeof(AnsShared) : sizeof(RcSmall);
+constexpr size_t SP_SMEM = sizeof(AnsShared) > sizeof(RcShared) ? sizeof(AnsShared) : sizeof(RcShared);
 
 __global__ void __launch_bounds__(32)
-sp_decode_kernel(const SpJob *__restrict__ jobs)
+sp_decode_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
 {
     __shared__ alignas(16) uint8_t smem[SP_SMEM];
+    extern __shared__ uint32_t ring_mem[];          // the last X + 1 pixels of an I frame (sp_segment_ring)
     const SpJob J = jobs[blockIdx.x];
-    if (J.flags & SPJ_ANS) sp_ans_run(J, *reinterpret_cast<AnsShared *>(smem));
-    else sp_rc_run(J, *reinterpret_cast<RcSmall *>(smem));
+    uint32_t *ring = sp_ring_size(J.X) <= ring_words ? ring_mem : nullptr;     // pictures too wide for it read global memory
+    if (J.flags & SPJ_ANS) sp_ans_run(J, *reinterpret_cast<AnsShared *>(smem), ring);
+    else sp_rc_run(J, *reinterpret_cast<RcShared *>(smem), ring);
 }
 
 }  // namespace
@@ -52,9 +54,32 @@ void sp_ans_state_init(void *d_state, void *d_ctx, uint32_t gen0, cudaStream_t s
     cudaMemcpy(reinterpret_cast<char *>(d_state) + offsetof(AnsState, gen), &h, sizeof h, cudaMemcpyHostToDevice);
 }
 
-void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, cudaStream_t st)
+#ifdef JSP_PROFILE_SECTIONS
+extern "C" __attribute__((visibility("default"))) int jsp_debug_sp_profile(unsigned long long *out, int reset)
 {
-    if (n_jobs) sp_decode_kernel<<<n_jobs, 32, 0, st>>>(d_jobs);
+    unsigned long long z[8] = {0};
+    if (cudaMemcpyFromSymbol(out, g_sp_prof, sizeof z) != cudaSuccess) return -1;
+    if (reset) cudaMemcpyToSymbol(g_sp_prof, z, sizeof z);
+    return 0;
+}
+extern "C" __attribute__((visibility("default"))) int jsp_debug_rc_profile(unsigned long long *out, int reset)
+{
+    unsigned long long z[8] = {0};
+    if (cudaMemcpyFromSymbol(out, g_rc_prof, sizeof z) != cudaSuccess) return -1;
+    if (reset) cudaMemcpyToSymbol(g_rc_prof, z, sizeof z);
+    return 0;
+}
+#endif
+
+void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, cudaStream_t st)
+{
+    if (!n_jobs) return;
+    uint32_t words = 64;
+    while (words <= max_width + 65u) words <<= 1;                    // = sp_ring_size(max_width)
+    if (words > 16384u) words = 0;                                     // > 64 KB: such frames fall back to global reads
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(sp_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr_set = true; }
+    sp_decode_kernel<<<n_jobs, 32, (size_t)words * 4, st>>>(d_jobs, words);
 }
 
 }  // namespace jsp

@@ -51,6 +51,17 @@ struct RcSmall {
     alignas(16) uint8_t win[128];                              // bitstream window (not state; lives here to share the allocation)
 };
 
+// Shared memory of one warp: the small tables (saved to / restored from RcState) and a cache of colour rows.
+// A global store invalidates the L1 line it hits, and every symbol updates its row, so a row read straight from global
+// memory pays an L2 round trip (~500 cycles) on EVERY symbol.  Screen content keeps returning to a handful of contexts
+// (12 fully associative LRU slots catch 93-98 % of the accesses of the synthetic corpus), so rows are decoded in shared
+// memory like the small tables and written back when evicted and at the end of the frame.
+constexpr int RC_CACHE_ROWS = 12;
+struct RcShared {
+    RcSmall small;
+    RcBig<8> cache[RC_CACHE_ROWS];
+};
+
 struct RcState {                                               // per stream, in HBM
     RcSmall small;
     uint32_t gen;                                              // generation of the colour rows (bumped by renewI)
@@ -58,31 +69,62 @@ struct RcState {                                               // per stream, in
     uint32_t *rows;                                            // RC_ROWS * RC_ROW_STRIDE u32, separately allocated
 };
 
-// floor(a / b) for 5 <= b <= 2^17 (a table total), rb = fl(1 / b).  The float estimate is within 2^10 / b + 1 of the
-// quotient, so |rem| < 2^24 is exact in float and one refinement lands within one of the quotient; the two
-// predicated corrections make it exact (the trailing loops never run; they keep the result exact by construction).
-__device__ __forceinline__ uint32_t udiv_small(uint32_t a, uint32_t b, float rb)
+__device__ __forceinline__ float rcp_approx(float x)
 {
-    uint32_t q = __float2uint_rz(__uint2float_rz(a) * rb);
-    int32_t rem = (int32_t)(a - q * b);
-    const int32_t adj = __float2int_rd(__int2float_rn(rem) * rb);
-    q += (uint32_t)adj; rem -= adj * (int32_t)b;
-    if (rem < 0) { q--; rem += (int32_t)b; }
-    if (rem >= (int32_t)b) { q++; rem -= (int32_t)b; }
-    while (rem < 0) { q--; rem += (int32_t)b; }
-    while (rem >= (int32_t)b) { q++; rem -= (int32_t)b; }
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));    // one MUFU; the division below is exact by construction
+    return y;
+}
+
+// floor(a / b) for 5 <= b <= 2^17 (a table total).  The float pipeline (I2F / F2I conversions, a correctly rounded
+// reciprocal) costs ~260 cycles on the one warp that waits for it, so only the reciprocal of b -- which does not depend
+// on the coder state -- is formed in floating point (one MUFU); it is turned into a 32-bit fixed-point reciprocal that
+// is guaranteed not to exceed 2^32 / b, and the quotient comes from two multiply-highs plus exact corrections.
+struct RcRecip { uint32_t inv; };
+__device__ __forceinline__ RcRecip rc_recip(uint32_t b)
+{
+    // rb ~ 1 / b within 2^-22 relative; scale by 2^32 (b >= 5 keeps it below 2^30), then shave 2^-20 relative + 1 so that
+    // inv <= floor(2^32 / b) whatever the rounding of the approximation was
+    const uint32_t est = __float2uint_rz(rcp_approx(__uint2float_rn(b)) * 4294967296.0f);
+    RcRecip r; r.inv = est - (est >> 20) - 1u;
+    return r;
+}
+__device__ __forceinline__ uint32_t udiv_small(uint32_t a, uint32_t b, RcRecip rc)
+{
+    uint32_t q = __umulhi(a, rc.inv);                // <= a / b, short by at most a * 2^-19 / b + 1
+    uint32_t rem = a - q * b;
+    const uint32_t q2 = __umulhi(rem, rc.inv);       // the shortfall, again from below: now short by at most 2
+    q += q2; rem -= q2 * b;
+    if (rem >= b) { q++; rem -= b; }
+    if (rem >= b) { q++; rem -= b; }
+    while (rem >= b) { q++; rem -= b; }               // never runs; keeps the result exact by construction
     return q;
 }
 
+#ifdef JSP_PROFILE_SECTIONS
+__device__ unsigned long long g_rc_prof[8];
+#endif
+
 struct RcCoder {
     static constexpr bool kCanDecodeBool = false;              // EntroCoders.hx:178
-    RcSmall *sm;                                               // shared memory
+    RcSmall *sm;                                               // shared memory: small tables
+    RcBig<8> *cache;                                           // shared memory: colour-row cache
+    int my_tag;                                                // lane < RC_CACHE_ROWS: context index held by slot `lane`, -1 = empty
+    uint32_t my_age, tick;                                     // LRU stamps
     uint32_t *rows;
     uint32_t gen;
     uint32_t range, code;
     const uint8_t *data;
     uint32_t len, pos, wbase;
     uint32_t nsym;                                             // symbols decoded in this frame (reporting only)
+#ifdef JSP_PROFILE_SECTIONS
+    long long prof[8];
+#define JSP_PT(k) { const long long _n = clock64(); prof[k] += _n - _pt; _pt = _n; }
+#define JSP_PT0 long long _pt = clock64();
+#else
+#define JSP_PT(k)
+#define JSP_PT0
+#endif
     bool poisoned, fail;
 
     __device__ __forceinline__ bool failed() const { return fail; }
@@ -152,7 +194,7 @@ struct RcCoder {
         uint32_t p = t.P[lane];
         uint32_t tot = __shfl_sync(FULLMASK, p, N - 1);
         if (poisoned) fail = true;
-        const uint32_t r = udiv_small(range, tot, __frcp_rn(__uint2float_rn(tot)));
+        const uint32_t r = udiv_small(range, tot, rc_recip(tot));
         const uint32_t codev = poisoned ? 0u : code;
         const uint32_t pr = p * r;
         const int s = __popc(__ballot_sync(FULLMASK, lane < N && pr <= codev));
@@ -179,6 +221,7 @@ struct RcCoder {
     {
         const int lane = (int)lane_id();
         nsym++;
+        JSP_PT0
         uint32_t lp[K];
         uint32_t base, tot;
         bool fresh = false;
@@ -199,7 +242,9 @@ struct RcCoder {
             } else tot = tab[32 * K + 32];
         }
         if (poisoned) fail = true;
-        const uint32_t r = udiv_small(range, tot, __frcp_rn(__uint2float_rn(tot)));
+        JSP_PT(0)
+        const uint32_t r = udiv_small(range, tot, rc_recip(tot));
+        JSP_PT(1)
         const uint32_t codev = poisoned ? 0u : code;
         const uint32_t br = base * r;
         if (codev >= tot * r) { range = r; fail = true; return 32 * K - 1; }     // value >= total: not a valid stream
@@ -228,15 +273,19 @@ struct RcCoder {
                 else if (open) { hi = pr; open = false; }
             }
         }
+        JSP_PT(2)
         const int mL = __shfl_sync(FULLMASK, m, L);
         const uint32_t lo_abs = __shfl_sync(FULLMASK, br + lo, L), width = __shfl_sync(FULLMASK, hi - lo, L);
+        JSP_PT(3)
         consume(lo_abs, width);
+        JSP_PT(4)
         tot += step;
-        if (lane == L) {
+        {
+            const uint32_t add = lane == L ? step : 0u;        // branch-free: divergent regions cost ~50 cycles each here
 #pragma unroll
-            for (int q = 0; q < K; q++) if (q >= mL) lp[q] += step;
+            for (int q = 0; q < K; q++) lp[q] += q >= mL ? add : 0u;
+            base += lane > L ? step : 0u;
         }
-        if (lane > L) base += step;
         bool all = fresh;
         if (tot > RC_BOT) {                                    // :70-77 / :113-127
             uint32_t prev = 0, s = 0;
@@ -258,12 +307,75 @@ struct RcCoder {
         // every lane writes the (identical) total: a lane only ever reads back what it wrote itself, no barrier needed
         if (IS_ROW) *reinterpret_cast<uint2 *>(tab + 32 * K + 32) = make_uint2(tot, gen);
         else tab[32 * K + 32] = tot;
+        JSP_PT(5)
         return L * K + mL;
     }
 
-    __device__ int decodeClr(int cxi)                                            // DecodeValUni on a colour row in HBM/L2
+    // copies between a cache slot and the row's home in HBM: 73 x 16 bytes, three per lane
+    __device__ __forceinline__ void row_writeback(int slot, int tag)
     {
-        return decode_big<8, true>(rows + (size_t)cxi * RC_ROW_STRIDE, 400u);
+        const int lane = (int)lane_id();
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(&cache[slot]);
+        uint4 *g4 = reinterpret_cast<uint4 *>(rows + (size_t)tag * RC_ROW_STRIDE);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { const int i = lane + 32 * k; if (i < (int)(sizeof(RcBig<8>) / 16)) g4[i] = s4[i]; }
+    }
+    __device__ __forceinline__ void row_fill(int slot, int cxi)
+    {
+        const int lane = (int)lane_id();
+        uint4 *s4 = reinterpret_cast<uint4 *>(&cache[slot]);
+        const uint32_t *grow = rows + (size_t)cxi * RC_ROW_STRIDE;
+        const uint4 *g4 = reinterpret_cast<const uint4 *>(grow);
+        uint4 v[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { const int i = lane + 32 * k; v[k] = i < (int)(sizeof(RcBig<8>) / 16) ? g4[i] : make_uint4(0, 0, 0, 0); }
+        const bool fresh = grow[32 * 8 + 33] != gen;             // not touched since the last renewI: all counts are 1
+        if (fresh) {
+            RcBig<8> &t = cache[slot];
+#pragma unroll
+            for (int q = 0; q < 8; q++) t.lp[lane * 8 + q] = q + 1;
+            t.base[lane] = 8 * lane;
+            if (lane == 0) { t.total = 256; t.tag = gen; t.pad[0] = t.pad[1] = 0; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { const int i = lane + 32 * k; if (i < (int)(sizeof(RcBig<8>) / 16)) s4[i] = v[k]; }
+        }
+        __syncwarp();
+    }
+    // the shared-memory slot that holds colour row cxi (loading it, and evicting the least recently used row, if needed)
+    __device__ __forceinline__ uint32_t *row_slot(int cxi)
+    {
+        const int lane = (int)lane_id();
+        const uint32_t hit = __ballot_sync(FULLMASK, lane < RC_CACHE_ROWS && my_tag == cxi);
+        tick++;
+        int slot;
+        if (hit) {
+            slot = __ffs(hit) - 1;
+        } else {
+            const uint32_t key = lane < RC_CACHE_ROWS ? ((my_age << 4) | (uint32_t)lane) : 0xFFFFFFFFu;
+            slot = (int)(__reduce_min_sync(FULLMASK, key) & 15u);
+            const int old = __shfl_sync(FULLMASK, my_tag, slot);
+            if (old >= 0) row_writeback(slot, old);
+            __syncwarp();
+            row_fill(slot, cxi);
+            if (lane == slot) my_tag = cxi;
+        }
+        if (lane == slot) my_age = tick;
+        return cache[slot].lp;
+    }
+    __device__ void flush_rows()
+    {
+        for (int s = 0; s < RC_CACHE_ROWS; s++) {
+            const int t = __shfl_sync(FULLMASK, my_tag, s);
+            if (t >= 0) row_writeback(s, t);
+        }
+        my_tag = -1; my_age = 0;
+        __syncwarp();
+    }
+
+    __device__ int decodeClr(int cxi)                                            // DecodeValUni (RangeCoder.hx:82-130) on a cached colour row
+    {
+        return decode_big<8, false>(row_slot(cxi), 400u);
     }
     __device__ int decodeN(int ptype) { return decode_big<8, false>(sm->ntab[ptype].lp, 400u); }   // EntroCoders.hx:142-144
     __device__ int decodeP(int ptype) { return decode_tiny<6>(sm->ptypetab[ptype], 1000u); }
@@ -277,13 +389,18 @@ struct RcCoder {
 };
 
 // one frame of one range-coder stream; `sm` = this warp's shared memory
-__device__ __forceinline__ void sp_rc_run(const SpJob &J, RcSmall &sm)
+__device__ __forceinline__ void sp_rc_run(const SpJob &J, RcShared &shm, uint32_t *ring)
 {
     RcState *st = reinterpret_cast<RcState *>(J.state);
     const int lane = (int)lane_id();
+    RcSmall &sm = shm.small;
     RcCoder ec;
-    ec.sm = &sm; ec.rows = st->rows; ec.gen = st->gen;
+    ec.sm = &sm; ec.cache = shm.cache; ec.my_tag = -1; ec.my_age = 0; ec.tick = 0;
+    ec.rows = st->rows; ec.gen = st->gen;
     ec.fail = false; ec.poisoned = false; ec.range = 0; ec.code = 0; ec.data = J.src; ec.len = J.len; ec.pos = 0; ec.wbase = 0x80000000u; ec.nsym = 0;
+#ifdef JSP_PROFILE_SECTIONS
+    for (int k = 0; k < 8; k++) ec.prof[k] = 0;
+#endif
     // models persist from frame to frame until the next I frame: restore the small tables
     {
         const uint4 *g = reinterpret_cast<const uint4 *>(&st->small);
@@ -295,11 +412,12 @@ __device__ __forceinline__ void sp_rc_run(const SpJob &J, RcSmall &sm)
     if (J.flags & SPJ_RENEW) {
         ec.renewI();
     } else if (J.flags & SPJ_IFRAME) {
-        sp_decode_iframe(ec, J);
+        sp_decode_iframe(ec, J, ring);
         bits |= ST_CHANGED;
     } else {
         sp_decode_pframe(ec, J, bits);
     }
+    ec.flush_rows();
     if (ec.failed()) {
         bits = ST_ERROR;
         if (!(J.flags & SPJ_RENEW)) sp_undo_frame(J, (J.flags & SPJ_IFRAME) != 0);
@@ -311,6 +429,9 @@ __device__ __forceinline__ void sp_rc_run(const SpJob &J, RcSmall &sm)
         for (int i = lane; i < (int)(sizeof(RcSmall) / 16); i += 32) g[i] = s[i];
     }
     if (lane == 0) { st->gen = ec.gen; if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
+#ifdef JSP_PROFILE_SECTIONS
+    if (lane == 0) for (int k = 0; k < 6; k++) atomicAdd(&g_rc_prof[k], (unsigned long long)ec.prof[k]);
+#endif
 }
 
 }  // namespace jsp

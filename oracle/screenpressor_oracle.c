@@ -100,10 +100,16 @@ static inline int32_t px_get(const int32_t *p, long i, long end) { return (i >= 
 /* Defined behaviour (not in the reference): cx + cx1 stays below 4096 on every valid stream (cx < 64, cx1 <= 0xFC0;
  * 16 bpp v2: 5-bit channel values).  A corrupt stream can exceed it -- the reference would read outside cntab[] --
  * so the index wraps inside its channel and the frame is reported as failed. */
+/* test hook: when set, every colour-context index used is appended here (single-threaded callers only) */
+int32_t *g_ora_ctx_trace = 0; long g_ora_ctx_trace_cap = 0, g_ora_ctx_trace_n = 0;
+void ora_ctx_trace(int32_t *buf, long cap) { g_ora_ctx_trace = buf; g_ora_ctx_trace_cap = cap; g_ora_ctx_trace_n = 0; }
+long ora_ctx_trace_count(void) { return g_ora_ctx_trace_n; }
+
 static inline int ctx_index(sp_dec *s, int channel)
 {
     int i = s->cx + s->cx1;
     if (i < 0 || i >= CC_CXMAX) { s->ctx_fail = 1; i &= CC_CXMAX - 1; }
+    if (g_ora_ctx_trace && g_ora_ctx_trace_n < g_ora_ctx_trace_cap) g_ora_ctx_trace[g_ora_ctx_trace_n++] = channel * CC_CXMAX + i;
     return channel * CC_CXMAX + i;
 }
 

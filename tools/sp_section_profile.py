@@ -1,0 +1,30 @@
+import ctypes as C, numpy as np, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from jsplayer_b200 import synth, BatchDecoder, StreamSpec, CodecType, _lib
+lib = _lib.load()
+for ver in (2, 4):
+    specs = []
+    for i in range(32):
+        fr, k, _ = synth.sp_stream(1280, 720, 4, seed=0xC0DEC3 + i, version=ver, gop=1, change_permille=40)
+        specs.append(StreamSpec(CodecType.codec_screenpressor, 1280, 720, 24, frames=fr, keys=k))
+    bd = BatchDecoder(); bd.configure(specs); bd.upload(); bd.run(); bd.sync()
+    out = (C.c_ulonglong * 8)()
+    lib.jsp_debug_sp_profile(out, 1)
+    bd.run(); bd.sync()
+    lib.jsp_debug_sp_profile(out, 1)
+    nsym = bd.symbols()
+    v = [int(x) for x in out]
+    runs = v[5]
+    print("version", ver, "warps 128, symbols", nsym, "runs", runs)
+    names = ["decodeP", "decode_rgb(3 symbols)", "decodeN", "segment writes", "whole loop"]
+    for n, c in zip(names, v[:5]):
+        print("  %-24s %6.1f%% of loop   %7.0f cycles per run" % (n, 100.0 * c / v[4], c / runs))
+    print("  cycles per symbol (loop) %.0f" % (v[4] / nsym))
+    if ver == 2:
+        o2 = (C.c_ulonglong * 8)()
+        lib.jsp_debug_rc_profile(o2, 1)
+        w = [int(x) for x in o2]
+        nbig = nsym - runs          # decode_big calls = symbols - decodeP calls
+        for n, c in zip(["load table/row", "division", "ballot + search", "shuffles", "consume/renorm", "update + store"], w[:6]):
+            print("    decode_big %-18s %6.0f cycles per call" % (n, c / nbig / 2))   # two runs accumulated
+    bd.close()
