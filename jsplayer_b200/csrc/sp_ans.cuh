@@ -78,10 +78,19 @@ struct AnsState {                                  // per stream, in HBM
     uint4 *bodies;                                 // ANS_NCTX * 96 uint4
 };
 
+// A cached colour context of a small kind (None, Cx1..Cx6): header + the first 512 body bytes.  Global stores
+// invalidate the L1 lines they hit and every symbol updates its context, so a context read straight from global memory
+// costs an L2 round trip per symbol; screen content keeps returning to a handful of contexts (12 LRU slots catch
+// 93-98 %).  Cx7 contexts (1.5 KB) are rare there and stay in global memory.
+constexpr int ANS_CACHE_SLOTS = 12;
+struct alignas(16) AnsSlot {
+    CxHdr hdr;
+    uint8_t body[512];
+};
+
 struct AnsShared {
     AnsSmall small;
-    alignas(16) CxHdr hdr;
-    alignas(16) uint8_t body[512];
+    AnsSlot cache[ANS_CACHE_SLOTS];
     alignas(16) uint8_t big[ANS_BODY_BYTES];       // Cx7 under construction / Cx6 rescale temporaries
     alignas(16) uint8_t win[128];                  // bitstream window
     int res_c, res_freq, res_cum, res_wb;          // lane 0 -> warp
@@ -598,10 +607,19 @@ __device__ __noinline__ int update_raw(CxHdr &H, uint8_t *B, uint8_t *big, int c
 
 }  // namespace cx
 
+#ifdef JSP_PROFILE_SECTIONS
+__device__ unsigned long long g_ans_prof[16];
+#define JSP_AT(k) { const long long _n = clock64(); aprof[k] += _n - _at; aprof[8 + (k)]++; _at = _n; }
+#else
+#define JSP_AT(k)
+#endif
+
 struct AnsCoder {
     static constexpr bool kCanDecodeBool = true;                      // EntroCoders.hx:257
     AnsShared *sm;
     uint4 *hdrs, *bodies;
+    int my_tag;                                                       // lane < ANS_CACHE_SLOTS: context held by slot `lane`, -1 = empty
+    uint32_t my_age, tick;                                            // LRU stamps
     uint32_t gen;
     int f0;
     uint32_t x;                                                       // rANS state (low 32 bits; ANS.hx:6)
@@ -609,6 +627,9 @@ struct AnsCoder {
     uint32_t len, pos, wbase;
     int nDec;
     uint32_t nsym;                                                    // symbols decoded in this frame (reporting only)
+#ifdef JSP_PROFILE_SECTIONS
+    long long aprof[16];
+#endif
     bool overrun, fail;
 
     __device__ __forceinline__ bool failed() const { return fail; }
@@ -652,6 +673,17 @@ struct AnsCoder {
     __device__ __forceinline__ void advance(int start, int freq)      // decAdvance, ANS.hx:37-44
     {
         const int32_t r = (int32_t)x;
+        if (r >= 0 && (uint32_t)freq <= (uint32_t)ANS_SCALE && (r & 4095) >= start) {
+            // every state a valid stream reaches: the product fits 32 bits (freq <= 2^12, r >> 12 < 2^19)
+            uint32_t v = (uint32_t)freq * ((uint32_t)r >> 12) + (uint32_t)((r & 4095) - start);
+            int guard = 0;
+            while (v < ANS_L) {
+                if (overrun || ++guard > 8) { fail = true; break; }
+                v = (v << 8) | rbyte();
+            }
+            x = v;
+            return;
+        }
         long long v = (long long)freq * (r >> 12) + (r & 4095) - start;
         int guard = 0;
         while (v < (long long)ANS_L) {
@@ -689,143 +721,240 @@ struct AnsCoder {
         __syncwarp();
     }
 
+    // FixedSizeRansCtx.decode + incrCnt on a shared-memory table (decodeF, EntroCoders.hx:271-280).  Only the cumFreq
+    // vector is searched (a lane owns K consecutive symbols); the symbol's freq / cumFreq / count are then three
+    // scalar shared-memory reads and the update one scalar write.  The periodic rebuild (ANS.hx:89-102, every ~128
+    // symbols) takes the full register path of fx_core.
     template <int N>
-    __device__ int decodeF(FxTab<N> &t)                               // decodeF, EntroCoders.hx:271-280
+    __device__ int decodeF(FxTab<N> &t)
     {
         constexpr int K = FxTab<N>::K;
-        const int lane = (int)lane_id();
-        uint32_t cum[K], fr[K], cnt[K];
-        ld_u16<K>(t.cum + lane * K, cum); ld_u16<K>(t.fr + lane * K, fr); ld_u16<K>(t.cnt + lane * K, cnt);
-        uint32_t cntsum = t.cntsum;
-        int freq, cumf, owner; bool rebuilt;
+        const int lane = (int)lane_id(), j0 = lane * K;
         const int f = get();
-        const int c = fx_core<N, K>(cum, fr, cnt, t.dec, cntsum, f, freq, cumf, rebuilt, owner);
-        if (rebuilt) { st_u16<K>(t.cum + lane * K, cum); st_u16<K>(t.fr + lane * K, fr); st_u16<K>(t.cnt + lane * K, cnt); }
-        else if (lane == owner) st_u16<K>(t.cnt + lane * K, cnt);
-        if (lane == 0) t.cntsum = cntsum;
+        uint32_t cum[K];
+        ld_u16<K>(t.cum + j0, cum);
+        const uint32_t cntsum = t.cntsum + 16u;
+        if (cntsum + 16u > (uint32_t)ANS_SCALE) {                      // this symbol triggers the rebuild: slow path
+            uint32_t fr[K], cnt[K];
+            ld_u16<K>(t.fr + j0, fr); ld_u16<K>(t.cnt + j0, cnt);
+            uint32_t cs = t.cntsum;
+            int freq, cumf, owner; bool rebuilt;
+            const int c = fx_core<N, K>(cum, fr, cnt, t.dec, cs, f, freq, cumf, rebuilt, owner);
+            __syncwarp();
+            st_u16<K>(t.cum + j0, cum); st_u16<K>(t.fr + j0, fr); st_u16<K>(t.cnt + j0, cnt);
+            t.cntsum = cs;                                             // every lane stores the same value
+            __syncwarp();
+            advance(cumf, freq);
+            count();
+            return c;
+        }
+        const int c0 = t.dec[(f >> 7) & 31];
+        const uint32_t nxt = __shfl_down_sync(FULLMASK, cum[0], 1);
+        uint32_t mask = 0;
+#pragma unroll
+        for (int q = 0; q < K; q++) {
+            const int j = j0 + q;
+            const uint32_t cn = q + 1 < K ? cum[(q + 1) % K] : nxt;
+            if (j >= c0 && j < N - 1 && (int)cn > f) mask |= 1u << q;
+        }
+        const uint32_t ball = __ballot_sync(FULLMASK, mask != 0);
+        int c = N - 1;
+        if (ball) {
+            const int lw = __ffs(ball) - 1;
+            const uint32_t m = __shfl_sync(FULLMASK, mask, lw);
+            c = lw * K + __ffs(m) - 1;
+        }
+        const int freq = t.fr[c], cumf = t.cum[c];
+        const uint32_t cn = t.cnt[c];
+        __syncwarp();                                                  // every lane has read the table
+        t.cnt[c] = (uint16_t)(cn + 16u);                               // every lane stores the same values: no divergence
+        t.cntsum = cntsum;
         __syncwarp();
         advance(cumf, freq);
         count();
         return c;
     }
 
+    __device__ __forceinline__ void slot_writeback(int slot, int tag)
+    {
+        const int lane = (int)lane_id();
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(&sm->cache[slot]);
+        uint4 *gh = hdrs + (size_t)tag * (ANS_HDR_BYTES / 16);
+        uint4 *gb = bodies + (size_t)tag * (ANS_BODY_BYTES / 16);
+        if (lane < 4) gh[lane] = s4[lane];
+        gb[lane] = s4[4 + lane];
+    }
+    __device__ void flush_slots()
+    {
+        for (int k = 0; k < ANS_CACHE_SLOTS; k++) {
+            const int t = __shfl_sync(FULLMASK, my_tag, k);
+            if (t >= 0) slot_writeback(k, t);
+        }
+        my_tag = -1; my_age = 0;
+        __syncwarp();
+    }
+
+    // Cx7 = FixedSizeRansCtx(256) in global memory: the register path of the fixed tables.  hv / bv = the header words
+    // (lanes 0-3) and the first 512 body bytes (cumFreq, 8 per lane) already loaded by the caller.
+    __device__ __forceinline__ int decode_cx7(uint4 *gh, uint4 *gb, const uint4 &hv, const uint4 &bv, int f)
+    {
+        const int lane = (int)lane_id();
+        uint4 *sh4 = reinterpret_cast<uint4 *>(sm->big);               // the header's working copy (decTable lives in it)
+        if (lane < 4) sh4[lane] = hv;
+        __syncwarp();
+        CxHdr &H = *reinterpret_cast<CxHdr *>(sm->big);
+        uint32_t cum[8], fr[8], cnt[8];
+        {
+            const uint4 fv = gb[32 + lane], cv = gb[64 + lane];
+            auto unpack = [&](const uint4 &w, uint32_t (&o)[8]) {
+                o[0] = w.x & 0xFFFFu; o[1] = w.x >> 16; o[2] = w.y & 0xFFFFu; o[3] = w.y >> 16;
+                o[4] = w.z & 0xFFFFu; o[5] = w.z >> 16; o[6] = w.w & 0xFFFFu; o[7] = w.w >> 16;
+            };
+            unpack(bv, cum); unpack(fv, fr); unpack(cv, cnt);
+        }
+        uint32_t cntsum = H.cntsum;
+        int freq, cumf, owner; bool rebuilt;
+        const int c = fx_core<256, 8>(cum, fr, cnt, H.dec, cntsum, f, freq, cumf, rebuilt, owner);
+        auto pack = [&](const uint32_t (&v)[8]) {
+            return make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+        };
+        if (rebuilt) { gb[lane] = pack(cum); gb[32 + lane] = pack(fr); gb[64 + lane] = pack(cnt); }
+        else if (lane == owner) gb[64 + lane] = pack(cnt);
+        if (lane == 0) H.cntsum = cntsum;
+        __syncwarp();
+        if (lane < (rebuilt ? 4 : 1)) gh[lane] = sh4[lane];
+        __syncwarp();
+        advance(cumf, freq);
+        return c;
+    }
+
     __device__ int decodeClr(int cxi)                                 // EntroCoders.hx:235-255
     {
         const int lane = (int)lane_id();
-        uint4 *gh = hdrs + (size_t)cxi * (ANS_HDR_BYTES / 16);
-        uint4 *gb = bodies + (size_t)cxi * (ANS_BODY_BYTES / 16);
-        const uint4 bv = gb[lane];
-        uint4 hv = make_uint4(0, 0, 0, 0);
-        if (lane < 4) hv = gh[lane];
+#ifdef JSP_PROFILE_SECTIONS
+        long long _at = clock64();
+#endif
         const int f = get();
-        // ---- fast path: a Cx4 context (<= 4 symbols met: the common case on screen content) that HITS one of its
-        //      symbols.  SmallContext.decodeSC (ANS.hx:263-309) for S = 4, run by every lane from three broadcast
-        //      words -- no shared-memory staging, no divergence.  Anything else (a new symbol, other kinds) falls
-        //      through to the generic path below with nothing modified. ----
-        {
+        // ---- find the context in the shared-memory cache, or bring it in ----
+        const uint32_t hit = __ballot_sync(FULLMASK, lane < ANS_CACHE_SLOTS && my_tag == cxi);
+        tick++;
+        int slot;
+        if (hit) {
+            slot = __ffs(hit) - 1;
+        } else {
+            uint4 *gh = hdrs + (size_t)cxi * (ANS_HDR_BYTES / 16);
+            uint4 *gb = bodies + (size_t)cxi * (ANS_BODY_BYTES / 16);
+            const uint4 bv = gb[lane];
+            uint4 hv = make_uint4(0, 0, 0, 0);
+            if (lane < 4) hv = gh[lane];
             const uint32_t h_gen = __shfl_sync(FULLMASK, hv.x, 0), h_w1 = __shfl_sync(FULLMASK, hv.y, 0);
-            if (h_gen == gen && ((h_w1 >> 16) & 0xFFu) == CXK_4) {
-                const uint32_t symw = __shfl_sync(FULLMASK, bv.x, 0);                         // symbols[0..3]
-                const uint32_t f01 = __shfl_sync(FULLMASK, bv.x, 1), f23 = __shfl_sync(FULLMASK, bv.y, 1);   // freqs[0..3]
-                const int d = (int)(h_w1 & 0xFFFFu);
-                int mp = (int)(h_w1 >> 24);
-                uint32_t fq[4] = {f01 & 0xFFFFu, f01 >> 16, f23 & 0xFFFFu, f23 >> 16};
-                const int tot0 = (int)(fq[0] + fq[1] + fq[2] + fq[3]) + 256 - d;              // Cx4.decode, :320
-                int tot = tot0, shift = 0;
-                while (tot <= ANS_SCALE / 2 && tot > 0) { tot <<= 1; shift++; }
-                const int sf = f >> shift;
-                const int bonus = (ANS_SCALE - tot) >> shift;
-                int cumFr = 0, lastSymb = 0, hit = -1, hstart = 0, hfr = 0;
-                bool miss = false;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (i < d && hit < 0 && !miss) {
-                        const int sy = (int)((symw >> (8 * i)) & 0xFFu);
-                        const int fr = (int)((fq[i] + (i == mp ? (uint32_t)bonus : 0u)) & 0xFFFFu);
-                        const int startFr = cumFr + sy - lastSymb;
-                        if (sf < startFr) miss = true;                                        // a symbol not met yet
-                        else if (startFr + fr > sf) { hit = i; hstart = startFr; hfr = fr; }
-                        else { cumFr += sy - lastSymb + fr; lastSymb = sy + 1; }
-                    }
-                }
-                if (hit >= 0) {
-                    const int c = (int)((symw >> (8 * hit)) & 0xFFu);
-                    uint32_t fh = 0, fm = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) { if (i == hit) { fq[i] = (fq[i] + 50u) & 0xFFFFu; fh = fq[i]; } }
-#pragma unroll
-                    for (int i = 0; i < 4; i++) if (i == mp) fm = fq[i];
-                    const int mp0 = mp;
-                    if (hit != mp && fh > fm) mp = hit;                                       // :291-292
-                    if (tot0 + 50 + 50 > ANS_SCALE) {                                         // rescale, :254-261
-#pragma unroll
-                        for (int i = 0; i < 4; i++) if (i < d) fq[i] = (fq[i] - (fq[i] >> 1)) & 0xFFFFu;
-                    }
-                    if (lane == 1) *reinterpret_cast<uint2 *>(gb + 1) = make_uint2(fq[0] | (fq[1] << 16), fq[2] | (fq[3] << 16));
-                    if (lane == 0 && mp != mp0) reinterpret_cast<uint32_t *>(gh)[1] = (h_w1 & 0x00FFFFFFu) | ((uint32_t)mp << 24);
-                    advance(hstart << shift, hfr << shift);
-                    count();
-                    return c;
-                }
+            if (h_gen == gen && ((h_w1 >> 16) & 0xFFu) == CXK_7) {     // big contexts are decoded where they live
+                const int c7 = decode_cx7(gh, gb, hv, bv, f);
+                JSP_AT(4)
+                count();
+                return c7;
             }
+            const uint32_t key = lane < ANS_CACHE_SLOTS ? ((my_age << 4) | (uint32_t)lane) : 0xFFFFFFFFu;
+            slot = (int)(__reduce_min_sync(FULLMASK, key) & 15u);
+            const int old = __shfl_sync(FULLMASK, my_tag, slot);
+            if (old >= 0) slot_writeback(slot, old);
+            __syncwarp();
+            uint4 *s4 = reinterpret_cast<uint4 *>(&sm->cache[slot]);
+            if (lane < 4) s4[lane] = hv;
+            s4[4 + lane] = bv;
+            if (lane == slot) my_tag = cxi;
+            __syncwarp();
         }
-        uint4 *sh4 = reinterpret_cast<uint4 *>(&sm->hdr), *sb4 = reinterpret_cast<uint4 *>(sm->body);
-        sb4[lane] = bv;
-        if (lane < 4) sh4[lane] = hv;
-        __syncwarp();
-        CxHdr &H = sm->hdr;
+        if (lane == slot) my_age = tick;
+        if (hit) { JSP_AT(0) } else { JSP_AT(5) }
+        AnsSlot &S = sm->cache[slot];
+        CxHdr &H = S.hdr;
         const int kind = H.gen == gen ? H.kind : CXK_NONE;
         int c;
-        if (kind == CXK_7) {                                          // Cx7 = FixedSizeRansCtx(256), register path
-            uint32_t cum[8], fr[8], cnt[8];
-            {
-                uint32_t t[8];
-                const uint4 fv = gb[32 + lane], cv = gb[64 + lane];
-                auto unpack = [&](const uint4 &w, uint32_t (&o)[8]) {
-                    o[0] = w.x & 0xFFFFu; o[1] = w.x >> 16; o[2] = w.y & 0xFFFFu; o[3] = w.y >> 16;
-                    o[4] = w.z & 0xFFFFu; o[5] = w.z >> 16; o[6] = w.w & 0xFFFFu; o[7] = w.w >> 16;
-                };
-                unpack(bv, cum); unpack(fv, fr); unpack(cv, cnt);
-                (void)t;
-            }
-            uint32_t cntsum = H.cntsum;
-            int freq, cumf, owner; bool rebuilt;
-            c = fx_core<256, 8>(cum, fr, cnt, H.dec, cntsum, f, freq, cumf, rebuilt, owner);
-            auto pack = [&](const uint32_t (&v)[8]) {
-                return make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
-            };
-            if (rebuilt) { gb[lane] = pack(cum); gb[32 + lane] = pack(fr); gb[64 + lane] = pack(cnt); }
-            else if (lane == owner) gb[64 + lane] = pack(cnt);
-            if (lane == 0) H.cntsum = cntsum;
-            __syncwarp();
-            if (lane < (rebuilt ? 4 : 1)) gh[lane] = sh4[lane];
-            __syncwarp();
-            advance(cumf, freq);
-        } else {
-            int wb;
-            if (kind >= CXK_4) {
+        // ---- fast path: a Cx4 context (<= 4 symbols met: the common case on screen content) that HITS one of its
+        //      symbols.  SmallContext.decodeSC (ANS.hx:263-309) for S = 4, run by every lane from three shared-memory
+        //      words -- no divergence; lane 0 stores the two words that change. ----
+        if (kind == CXK_4) {
+            const uint32_t *bw = reinterpret_cast<const uint32_t *>(S.body);
+            const uint32_t symw = bw[0], f01 = bw[B_SC_FR / 4], f23 = bw[B_SC_FR / 4 + 1];
+            const int d = H.d, mp = H.maxpos;
+            const int q0 = (int)(f01 & 0xFFFFu), q1 = (int)(f01 >> 16), q2 = (int)(f23 & 0xFFFFu), q3 = (int)(f23 >> 16);
+            const int tot0 = q0 + q1 + q2 + q3 + 256 - d;                                      // Cx4.decode, :320
+            // `while (tot <= PROB_SCALE / 2) { tot <<= 1; shift++; }` in closed form (tot0 is 257 .. 4096 + 3 * 50)
+            const int hb = 31 - __clz(tot0);
+            const int shift = max(0, 11 - hb + ((tot0 & (tot0 - 1)) == 0 ? 1 : 0));
+            const int tot = tot0 << shift;
+            const int sf = f >> shift;
+            const int bonus = (ANS_SCALE - tot) >> shift;
+            // symbols (unused slots: 256, which nothing reaches) and this call's frequencies (the bonus goes to maxpos)
+            const int s0 = (int)(symw & 0xFFu), s1 = d > 1 ? (int)((symw >> 8) & 0xFFu) : 256,
+                      s2 = d > 2 ? (int)((symw >> 16) & 0xFFu) : 256, s3 = d > 3 ? (int)(symw >> 24) : 256;
+            const int r0 = (q0 + (mp == 0 ? bonus : 0)) & 0xFFFF, r1 = (q1 + (mp == 1 ? bonus : 0)) & 0xFFFF,
+                      r2 = (q2 + (mp == 2 ? bonus : 0)) & 0xFFFF, r3 = (q3 + (mp == 3 ? bonus : 0)) & 0xFFFF;
+            // interval starts: every symbol below s_i that has not been met owns one unit (decodeSC, :274-299)
+            const int a0 = s0, e0 = a0 + r0;
+            const int a1 = e0 + s1 - s0 - 1, e1 = a1 + r1;
+            const int a2 = e1 + s2 - s1 - 1, e2 = a2 + r2;
+            const int a3 = e2 + s3 - s2 - 1, e3 = a3 + r3;
+            const bool h0 = sf >= a0 && sf < e0, h1 = d > 1 && sf >= a1 && sf < e1,
+                       h2 = d > 2 && sf >= a2 && sf < e2, h3 = d > 3 && sf >= a3 && sf < e3;
+            if (h0 || h1 || h2 || h3) {
+                const int hitpos = h0 ? 0 : (h1 ? 1 : (h2 ? 2 : 3));
+                c = h0 ? s0 : (h1 ? s1 : (h2 ? s2 : s3));
+                const int hstart = h0 ? a0 : (h1 ? a1 : (h2 ? a2 : a3));
+                const int hfr = h0 ? r0 : (h1 ? r1 : (h2 ? r2 : r3));
+                int n0 = (q0 + (h0 ? 50 : 0)) & 0xFFFF, n1 = (q1 + (h1 ? 50 : 0)) & 0xFFFF,
+                    n2 = (q2 + (h2 ? 50 : 0)) & 0xFFFF, n3 = (q3 + (h3 ? 50 : 0)) & 0xFFFF;
+                const int fh = h0 ? n0 : (h1 ? n1 : (h2 ? n2 : n3));
+                const int fm = mp == 0 ? n0 : (mp == 1 ? n1 : (mp == 2 ? n2 : n3));
+                const int nmp = (hitpos != mp && fh > fm) ? hitpos : mp;                      // :291-292
+                if (tot0 + 50 + 50 > ANS_SCALE) {                                             // rescale, :254-261
+                    n0 = d > 0 ? (n0 - (n0 >> 1)) & 0xFFFF : n0; n1 = d > 1 ? (n1 - (n1 >> 1)) & 0xFFFF : n1;
+                    n2 = d > 2 ? (n2 - (n2 >> 1)) & 0xFFFF : n2; n3 = d > 3 ? (n3 - (n3 >> 1)) & 0xFFFF : n3;
+                }
+                __syncwarp();                                          // every lane has read the slot
                 if (lane == 0) {
-                    CxRes r; r.c = 0; r.freq = 1; r.cum = 0;
-                    sm->res_wb = cx::decode_small(H, sm->body, sm->big, f, r);
-                    sm->res_c = r.c; sm->res_freq = r.freq; sm->res_cum = r.cum;
+                    uint32_t *bwr = reinterpret_cast<uint32_t *>(S.body);
+                    bwr[B_SC_FR / 4] = (uint32_t)n0 | ((uint32_t)n1 << 16); bwr[B_SC_FR / 4 + 1] = (uint32_t)n2 | ((uint32_t)n3 << 16);
+                    H.maxpos = (uint8_t)nmp;
                 }
                 __syncwarp();
-                c = sm->res_c; wb = sm->res_wb;
-                const int freq = sm->res_freq, cumf = sm->res_cum;
-                advance(cumf, freq);
-                if (c > 255) { fail = true; c &= 255; }               // escape interval past symbol 255: not a valid stream
-            } else {
-                c = (int)rbyte();                                     // Rans.raw, ANS.hx:46-48
-                if (lane == 0) sm->res_wb = cx::update_raw(H, sm->body, sm->big, c, f0, gen);
-                __syncwarp();
-                wb = sm->res_wb;
+                advance(hstart << shift, hfr << shift);
+                JSP_AT(1)
+                count();
+                return c;
             }
-            // write the slab back: header always, the live part of the body (or the freshly built Cx7)
-            if (wb < 0) {
-                const uint4 *big4 = reinterpret_cast<const uint4 *>(sm->big);
-                gb[lane] = big4[lane]; gb[32 + lane] = big4[32 + lane]; gb[64 + lane] = big4[64 + lane];
-            } else if (lane * 16 < wb) gb[lane] = sb4[lane];
-            if (lane < 4) gh[lane] = sh4[lane];
+        }
+        // ---- generic path: lane 0 does the bookkeeping of the small kinds in place on the cached slot ----
+        int wb;
+        if (kind >= CXK_4) {
+            if (lane == 0) {
+                CxRes r; r.c = 0; r.freq = 1; r.cum = 0;
+                sm->res_wb = cx::decode_small(H, S.body, sm->big, f, r);
+                sm->res_c = r.c; sm->res_freq = r.freq; sm->res_cum = r.cum;
+            }
+            __syncwarp();
+            c = sm->res_c; wb = sm->res_wb;
+            const int freq = sm->res_freq, cumf = sm->res_cum;
+            advance(cumf, freq);
+            if (c > 255) { fail = true; c &= 255; }                   // escape interval past symbol 255: not a valid stream
+            JSP_AT(2)
+        } else {
+            c = (int)rbyte();                                         // Rans.raw, ANS.hx:46-48
+            if (lane == 0) sm->res_wb = cx::update_raw(H, S.body, sm->big, c, f0, gen);
+            __syncwarp();
+            wb = sm->res_wb;
+            JSP_AT(3)
+        }
+        if (wb < 0) {
+            // the context has just become a Cx7 (built in `big`): it moves out to global memory and leaves the cache
+            uint4 *gh = hdrs + (size_t)cxi * (ANS_HDR_BYTES / 16);
+            uint4 *gb = bodies + (size_t)cxi * (ANS_BODY_BYTES / 16);
+            const uint4 *big4 = reinterpret_cast<const uint4 *>(sm->big);
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(&S);
+            gb[lane] = big4[lane]; gb[32 + lane] = big4[32 + lane]; gb[64 + lane] = big4[64 + lane];
+            if (lane < 4) gh[lane] = s4[lane];
+            if (lane == slot) { my_tag = -1; my_age = 0; }
             __syncwarp();
         }
         count();
@@ -859,6 +988,10 @@ __device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm, uint32
     ec.sm = &sm; ec.hdrs = st->hdrs; ec.bodies = st->bodies; ec.gen = st->gen;
     ec.f0 = (J.flags & SPJ_ANS_V3) ? 64 : 32;                         // Cx6.f0, EntroCoders.hx:210 / ScreenPressor.hx:69-72
     ec.fail = false; ec.overrun = false; ec.x = 0; ec.data = J.src; ec.len = J.len; ec.pos = 0; ec.wbase = 0x80000000u; ec.nDec = 0; ec.nsym = 0;
+    ec.my_tag = -1; ec.my_age = 0; ec.tick = 0;
+#ifdef JSP_PROFILE_SECTIONS
+    for (int k = 0; k < 16; k++) ec.aprof[k] = 0;
+#endif
     {
         const uint4 *g = reinterpret_cast<const uint4 *>(&st->small);
         uint4 *s = reinterpret_cast<uint4 *>(&sm.small);
@@ -874,6 +1007,7 @@ __device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm, uint32
     } else {
         sp_decode_pframe(ec, J, bits);
     }
+    ec.flush_slots();
     if (ec.failed()) {
         bits = ST_ERROR;
         if (!(J.flags & SPJ_RENEW)) sp_undo_frame(J, (J.flags & SPJ_IFRAME) != 0);
@@ -885,6 +1019,9 @@ __device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm, uint32
         for (int i = lane; i < (int)(sizeof(AnsSmall) / 16); i += 32) g[i] = s[i];
     }
     if (lane == 0) { st->gen = ec.gen; if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
+#ifdef JSP_PROFILE_SECTIONS
+    if (lane == 0) for (int k = 0; k < 16; k++) atomicAdd(&g_ans_prof[k], (unsigned long long)ec.aprof[k]);
+#endif
 }
 
 }  // namespace jsp

@@ -62,6 +62,13 @@ extern "C" __attribute__((visibility("default"))) int jsp_debug_sp_profile(unsig
     if (reset) cudaMemcpyToSymbol(g_sp_prof, z, sizeof z);
     return 0;
 }
+extern "C" __attribute__((visibility("default"))) int jsp_debug_ans_profile(unsigned long long *out, int reset)
+{
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyFromSymbol(out, g_ans_prof, sizeof z) != cudaSuccess) return -1;
+    if (reset) cudaMemcpyToSymbol(g_ans_prof, z, sizeof z);
+    return 0;
+}
 extern "C" __attribute__((visibility("default"))) int jsp_debug_rc_profile(unsigned long long *out, int reset)
 {
     unsigned long long z[8] = {0};

@@ -20,6 +20,13 @@ for ver in (2, 4):
     for n, c in zip(names, v[:5]):
         print("  %-24s %6.1f%% of loop   %7.0f cycles per run" % (n, 100.0 * c / v[4], c / runs))
     print("  cycles per symbol (loop) %.0f" % (v[4] / nsym))
+    if ver != 2:
+        o3 = (C.c_ulonglong * 16)()
+        lib.jsp_debug_ans_profile(o3, 1)
+        a = [int(x) for x in o3]
+        for k, n in enumerate(["cache hit lookup", "Cx4 hit fast path", "kinds 4-6 generic (lane 0)", "raw kinds (None, Cx1-3)", "Cx7 (global)", "cache miss fill"]):
+            if a[8 + k]:
+                print("    decodeClr %-28s %9d calls  %6.0f cycles per call" % (n, a[8 + k] // 2, a[k] / a[8 + k]))
     if ver == 2:
         o2 = (C.c_ulonglong * 8)()
         lib.jsp_debug_rc_profile(o2, 1)
