@@ -6,10 +6,12 @@
 //  * the non-colour tables (ntab 6x257, ptypetab 6x7, xxtab, ntab2, bttab, sxytab 4x17, mvtab 2x513 -- 15 KB in
 //    the prefix layout below) live in shared memory for the whole frame and are saved to / restored from the
 //    stream's state in HBM; the bitstream is read through a 128-byte shared-memory window;
-//  * a colour context is one 1280-byte row in HBM/L2 (lane-local prefix sums of 256 counts + 32 lane bases +
-//    total + generation tag; the reference's 16 group sums are derived data and are not stored).  The warp loads
-//    the row with one coalesced access and finds the symbol with ONE __ballot_sync -- no prefix scan, no linear
-//    search (RangeCoder.hx:58-65, :90-108) and a single division per symbol (see "table layout");
+//  * a colour context is one 1280-byte row in HBM (lane-local prefix sums of 256 counts + 32 lane bases + total +
+//    generation tag; the reference's 16 group sums are derived data and are not stored).  Rows are DECODED in a
+//    12-slot LRU cache in shared memory, exactly like the small tables: a global store invalidates the L1 line it
+//    hits and every symbol updates its row, so decoding rows in place would pay an L2 round trip per symbol.
+//    The symbol search is ONE __ballot_sync plus a 3-probe binary search in registers -- no prefix scan, no linear
+//    search (RangeCoder.hx:58-65, :90-108) -- and a single division per symbol (see "table layout");
 //  * renewI (EntroCoders.hx:81-130) is O(1) for the 12288 colour rows: it bumps a generation number and rows
 //    with an older tag read as "all ones" (the reference also resets lazily, :85).
 #pragma once
@@ -215,8 +217,9 @@ struct RcCoder {
         return s;                                              // a lane reads back only its own P[lane]: no barrier needed
     }
 
-    // RangeCoder.hx:51-80 (256 / 512 symbols) and :82-130 (colour rows; the 16 group sums are derived data)
-    template <int K, bool IS_ROW>
+    // RangeCoder.hx:51-80 (256 / 512 symbols) and :82-130 (colour rows, cached in shared memory; the reference's 16 group
+    // sums are derived data and are not kept), on a table in shared memory
+    template <int K>
     __device__ __forceinline__ int decode_big(uint32_t *tab, uint32_t step)
     {
         const int lane = (int)lane_id();
@@ -224,22 +227,12 @@ struct RcCoder {
         JSP_PT0
         uint32_t lp[K];
         uint32_t base, tot;
-        bool fresh = false;
         {
             const uint4 *t4 = reinterpret_cast<const uint4 *>(tab) + lane * (K / 4);
 #pragma unroll
             for (int q = 0; q < K / 4; q++) { const uint4 v = t4[q]; lp[4 * q] = v.x; lp[4 * q + 1] = v.y; lp[4 * q + 2] = v.z; lp[4 * q + 3] = v.w; }
             base = tab[32 * K + lane];
-            if (IS_ROW) {
-                const uint2 meta = *reinterpret_cast<const uint2 *>(tab + 32 * K + 32);   // total, generation tag
-                tot = meta.x;
-                fresh = meta.y != gen;                         // not touched since the last renewI: all counts are 1
-                if (fresh) {
-#pragma unroll
-                    for (int q = 0; q < K; q++) lp[q] = q + 1;
-                    base = K * lane; tot = 32 * K;
-                }
-            } else tot = tab[32 * K + 32];
+            tot = tab[32 * K + 32];
         }
         if (poisoned) fail = true;
         JSP_PT(0)
@@ -286,7 +279,7 @@ struct RcCoder {
             for (int q = 0; q < K; q++) lp[q] += q >= mL ? add : 0u;
             base += lane > L ? step : 0u;
         }
-        bool all = fresh;
+        bool all = false;
         if (tot > RC_BOT) {                                    // :70-77 / :113-127
             uint32_t prev = 0, s = 0;
 #pragma unroll
@@ -305,8 +298,7 @@ struct RcCoder {
         }
         if (all || lane > L) tab[32 * K + lane] = base;
         // every lane writes the (identical) total: a lane only ever reads back what it wrote itself, no barrier needed
-        if (IS_ROW) *reinterpret_cast<uint2 *>(tab + 32 * K + 32) = make_uint2(tot, gen);
-        else tab[32 * K + 32] = tot;
+        tab[32 * K + 32] = tot;
         JSP_PT(5)
         return L * K + mL;
     }
@@ -375,16 +367,16 @@ struct RcCoder {
 
     __device__ int decodeClr(int cxi)                                            // DecodeValUni (RangeCoder.hx:82-130) on a cached colour row
     {
-        return decode_big<8, false>(row_slot(cxi), 400u);
+        return decode_big<8>(row_slot(cxi), 400u);
     }
-    __device__ int decodeN(int ptype) { return decode_big<8, false>(sm->ntab[ptype].lp, 400u); }   // EntroCoders.hx:142-144
+    __device__ int decodeN(int ptype) { return decode_big<8>(sm->ntab[ptype].lp, 400u); }   // EntroCoders.hx:142-144
     __device__ int decodeP(int ptype) { return decode_tiny<6>(sm->ptypetab[ptype], 1000u); }
-    __device__ int decodeX() { return decode_big<8, false>(sm->xxtab.lp, 1u); }
+    __device__ int decodeX() { return decode_big<8>(sm->xxtab.lp, 1u); }
     __device__ int decodeBT() { return decode_tiny<5>(sm->bttab, 10u); }
-    __device__ int decodeBN() { return decode_big<8, false>(sm->ntab2.lp, 20u); }
+    __device__ int decodeBN() { return decode_big<8>(sm->ntab2.lp, 20u); }
     __device__ int decodeSXY(int n) { return decode_tiny<16>(sm->sxytab[n], 100u); }
-    __device__ int decodeMX() { return decode_big<16, false>(sm->mvtab[0].lp, 100u); }
-    __device__ int decodeMY() { return decode_big<16, false>(sm->mvtab[1].lp, 100u); }
+    __device__ int decodeMX() { return decode_big<16>(sm->mvtab[0].lp, 100u); }
+    __device__ int decodeMY() { return decode_big<16>(sm->mvtab[1].lp, 100u); }
     __device__ bool decodeBool() { return false; }
 };
 
