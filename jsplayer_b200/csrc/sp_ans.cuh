@@ -676,6 +676,7 @@ struct AnsCoder {
         if (r >= 0 && (uint32_t)freq <= (uint32_t)ANS_SCALE && (r & 4095) >= start) {
             // every state a valid stream reaches: the product fits 32 bits (freq <= 2^12, r >> 12 < 2^19)
             uint32_t v = (uint32_t)freq * ((uint32_t)r >> 12) + (uint32_t)((r & 4095) - start);
+            if (v >= ANS_L) { x = v; return; }                          // most symbols cost less than a byte
             int guard = 0;
             while (v < ANS_L) {
                 if (overrun || ++guard > 8) { fail = true; break; }

@@ -107,9 +107,10 @@ __device__ __forceinline__ uint32_t sp_segment_ring(int32_t *dst, uint32_t *ring
     }
     default: break;
     }
-    __syncwarp();                                   // every lane has read the row above before its slots are reused
+    if (ptype > 1) __syncwarp();                    // every lane has read the row above before its slots are reused
     if (lane < m && idx < end) { dst[idx] = (int32_t)v; ring[(uint32_t)idx & rmask] = v; }
-    const uint32_t last = __shfl_sync(FULLMASK, v, (m - 1) & 31);
+    // predictors 0 / 1 write one value everywhere: no broadcast needed for "the run's last pixel"
+    const uint32_t last = ptype > 1 ? __shfl_sync(FULLMASK, v, (m - 1) & 31) : v;
     __syncwarp();
     return last;
 }
