@@ -553,7 +553,7 @@ __device__ int find_or_add(CxHdr &H, uint8_t *B, int c, int cap)      // SymbLis
 
 // Context.decode for kinds 4-6 (ANS.hx:795-810). Returns the number of body bytes to write back, or -1 when a
 // Cx7 was built in `big`.
-__device__ __noinline__ int decode_small(CxHdr &H, uint8_t *B, uint8_t *big, int someFreq, CxRes &r)
+__device__ __forceinline__ int decode_small(CxHdr &H, uint8_t *B, uint8_t *big, int someFreq, CxRes &r)
 {
     int tf;
     switch (H.kind) {
@@ -576,7 +576,7 @@ __device__ __noinline__ int decode_small(CxHdr &H, uint8_t *B, uint8_t *big, int
 }
 
 // Context.update for kinds None-3 after a raw symbol (ANS.hx:812-859). Same return convention.
-__device__ __noinline__ int update_raw(CxHdr &H, uint8_t *B, uint8_t *big, int c, int f0, uint32_t gen)
+__device__ __forceinline__ int update_raw(CxHdr &H, uint8_t *B, uint8_t *big, int c, int f0, uint32_t gen)
 {
     int kind = H.gen == gen ? H.kind : CXK_NONE;
     switch (kind) {

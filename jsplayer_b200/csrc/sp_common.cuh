@@ -174,14 +174,17 @@ __device__ void sp_decode_iframe(Coder &ec, const SpJob &J, uint32_t *ring)
     int cx = 0, cx1 = 0;
     long di = 0, k = 0;
     uint32_t clr = 0, lastval = 0;
-    auto decode_rgb = [&]() -> uint32_t {       // ScreenPressor.hx:173-183
-        const int r = ec.decodeClr(sp_ctx_index(ec, 0, cx, cx1));
-        cx1 = (cx << 6) & 0xFC0; cx = r >> cxshift;
-        const int g = ec.decodeClr(sp_ctx_index(ec, 1, cx, cx1));
-        cx1 = (cx << 6) & 0xFC0; cx = g >> cxshift;
-        const int b = ec.decodeClr(sp_ctx_index(ec, 2, cx, cx1));
-        cx1 = (cx << 6) & 0xFC0; cx = b >> cxshift;
-        return ((uint32_t)b << 16) + ((uint32_t)g << 8) + (uint32_t)r;
+    // ScreenPressor.hx:173-183.  A rolled loop on purpose: one copy of the colour decoder per call site instead of three
+    // keeps the hot loop's code small (several warps share an SM's instruction cache).
+    auto decode_rgb = [&]() -> uint32_t {
+        uint32_t px = 0;
+#pragma unroll 1
+        for (int ch = 0; ch < 3; ch++) {
+            const int v = ec.decodeClr(sp_ctx_index(ec, ch, cx, cx1));
+            cx1 = (cx << 6) & 0xFC0; cx = v >> cxshift;
+            px += (uint32_t)v << (8 * ch);
+        }
+        return px;
     };
     long budget = sp_run_budget(X, J.Y);
     while (k < X + 1) {                            // first X+1 pixels: (colour, run) pairs, :170-197
@@ -275,13 +278,14 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
     uint32_t clr = 0;
     int lastmx = 0, lastmy = 0;
     auto decode_rgb = [&]() -> uint32_t {
-        const int r = ec.decodeClr(sp_ctx_index(ec, 0, cx, cx1));
-        cx1 = (cx << 6) & 0xFC0; cx = r >> cxshift;
-        const int g = ec.decodeClr(sp_ctx_index(ec, 1, cx, cx1));
-        cx1 = (cx << 6) & 0xFC0; cx = g >> cxshift;
-        const int b = ec.decodeClr(sp_ctx_index(ec, 2, cx, cx1));
-        cx1 = (cx << 6) & 0xFC0; cx = b >> cxshift;
-        return ((uint32_t)b << 16) + ((uint32_t)g << 8) + (uint32_t)r;
+        uint32_t px = 0;
+#pragma unroll 1
+        for (int ch = 0; ch < 3; ch++) {
+            const int v = ec.decodeClr(sp_ctx_index(ec, ch, cx, cx1));
+            cx1 = (cx << 6) & 0xFC0; cx = v >> cxshift;
+            px += (uint32_t)v << (8 * ch);
+        }
+        return px;
     };
     for (int bi = 0; bi < nb; bi++) {
         // skip unchanged blocks 32 at a time: they already hold the previous picture
