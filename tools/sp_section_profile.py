@@ -1,7 +1,17 @@
+"""Per-section cycle counts (clock64) of the ScreenPressor entropy kernels: where a symbol's ~800-1000 cycles go.
+
+ncu's stall sampling is flat for these kernels (one warp per scheduler, every instruction waits a little), so the I-frame
+loop and the decoders carry optional timers (JSP_PROFILE_SECTIONS).  Workload: 32 streams x 4 I frames, 1280x720, both
+coders.  Results of round 1: profiles/r01_sp_section_profile.txt, discussion in DESIGN.md 4.3.
+"""
 import ctypes as C, numpy as np, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from jsplayer_b200 import synth, BatchDecoder, StreamSpec, CodecType, _lib
 lib = _lib.load()
+if not hasattr(lib, "jsp_debug_sp_profile"):
+    raise SystemExit("build the library with section timers first:\n"
+                     "  JSP_NVCC_EXTRA=-DJSP_PROFILE_SECTIONS python jsplayer_b200/build.py --force\n"
+                     "(and rebuild without the flag afterwards: the timers cost ~40 cycles per section)")
 for ver in (2, 4):
     specs = []
     for i in range(32):
