@@ -154,7 +154,7 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
                        bool secondary = false)
 {
     const uint32_t mframe_base = secondary ? (uint32_t)b->frames.size() : 0u;   // chunk plans use their own frame descriptors
-    plan.launches.clear(); plan.uploads.clear();
+    plan.launches.clear(); plan.finished.clear(); plan.uploads.clear();
     plan.frame_lo = b->streams[s_lo].first_frame;
     plan.frame_hi = b->streams[s_hi - 1].first_frame + b->streams[s_hi - 1].n_frames;
     plan.tile_tab_off = T.tile_tab.size();
@@ -172,11 +172,13 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
         // whole-picture copies (unchanged frames)
         {
             const size_t first = T.jobs.size(); uint32_t maxv = 0;
+            std::vector<int64_t> fin;
             for (int64_t f : by_level[lv]) {
                 FrameRec &R = b->frames[f];
                 if (R.kind != FK_COPY && R.kind != FK_SP_P && R.kind != FK_SP_FLAT) continue;
                 const StreamRec &S = b->streams[R.stream];
                 if (S.codec == JSP_CODEC_SCREENPRESSOR) continue;          // ScreenPressor levels are planned below
+                fin.push_back(f);
                 CopyJob J;
                 J.dst = b->d_out + R.out_off;
                 J.src = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
@@ -186,8 +188,10 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
                 maxv = std::max(maxv, J.n_vec4);
                 T.jobs.push_back(J);
             }
-            if (T.jobs.size() > first)
+            if (T.jobs.size() > first) {
                 plan.launches.push_back({JSP_K_FRAME_COPY, FK_COPY, first, (uint32_t)(T.jobs.size() - first), maxv, 0});
+                plan.finished.push_back(std::move(fin));
+            }
         }
         // MSVideo1, one launch per pixel format; tiles are listed tile-major so that a tile's
         // predecessors in its frame were handed out a whole "row" of frames earlier
@@ -218,6 +222,7 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
                 }
             }
             plan.launches.push_back({JSP_K_MSV1_DECODE, kind, first, (uint32_t)(T.tile_tab.size() - first), 0, (uint32_t)ticket_cursor});
+            plan.finished.push_back(fr);
             ticket_cursor++;
         }
     }
@@ -228,11 +233,13 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
     for (int lv = 0; lv <= max_level; lv++) {
         {
             const size_t first = T.jobs.size(); uint32_t maxv = 0;
+            std::vector<int64_t> fin;
             for (int64_t f : by_level[lv]) {
                 const FrameRec &R = b->frames[f];
                 const StreamRec &S = b->streams[R.stream];
                 if (S.codec != JSP_CODEC_SCREENPRESSOR) continue;
                 if (R.kind != FK_COPY && R.kind != FK_SP_P && R.kind != FK_SP_FLAT) continue;
+                if (R.kind != FK_SP_P) fin.push_back(f);                   // a P frame's picture is final after its decode
                 CopyJob J;
                 J.dst = b->d_out + R.out_off;
                 J.src = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
@@ -242,10 +249,13 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
                 maxv = std::max(maxv, J.n_vec4);
                 T.jobs.push_back(J);
             }
-            if (T.jobs.size() > first)
+            if (T.jobs.size() > first) {
                 plan.launches.push_back({JSP_K_FRAME_COPY, FK_COPY, first, (uint32_t)(T.jobs.size() - first), maxv, 0});
+                plan.finished.push_back(std::move(fin));
+            }
         }
         const size_t first = T.spjobs.size();
+        std::vector<int64_t> fin;
         int n_rc = 0, n_ans = 0; uint32_t max_w = 0;
         // longest frames first: when a launch has more warps than the device holds, the late starters are the short ones
         std::vector<int64_t> order(by_level[lv]);
@@ -269,10 +279,12 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             (H.version > 2 ? n_ans : n_rc)++;
             max_w = std::max(max_w, J.X);
             T.spjobs.push_back(J);
+            if (R.kind != FK_SP_FLAT) fin.push_back(f);
         }
         if (T.spjobs.size() > first) {
             const int kclass = n_ans == 0 ? JSP_K_SP_ENTROPY_RC : (n_rc == 0 ? JSP_K_SP_ENTROPY_ANS : JSP_K_SP_ENTROPY_MIXED);
             plan.launches.push_back({kclass, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), max_w, 0});
+            plan.finished.push_back(std::move(fin));
         }
     }
     plan.n_spjobs = T.spjobs.size() - plan.spjob_off;
@@ -351,7 +363,14 @@ static bool upload_tables(jsp_batch *b, HostTables &T, size_t n_states, size_t n
     return true;
 }
 
+template <class F> static bool run_plan_with(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *ev, std::vector<int> *ev_class, F &&after_launch);
 static bool run_plan(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *ev = nullptr, std::vector<int> *ev_class = nullptr)
+{
+    return run_plan_with(b, P, st, ev, ev_class, [](int) { return true; });
+}
+
+// Enqueues the plan's launches on `st`; after_launch(k) runs on the host right after launch k has been enqueued.
+template <class F> static bool run_plan_with(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *ev, std::vector<int> *ev_class, F &&after_launch)
 {
     if (P.n_states) {
         if (!JSP_CUDA(cudaMemsetAsync(b->d_tile_map + P.state_off, 0, P.n_states * 8, st))) return false;
@@ -379,6 +398,7 @@ static bool run_plan(jsp_batch *b, const Plan &P, cudaStream_t st, cudaEvent_t *
         default: break;
         }
         if (ev) cudaEventRecord(ev[2 * k + 1], st);
+        if (!after_launch(k)) return false;
         k++;
     }
     return JSP_CUDA(cudaGetLastError());
@@ -887,11 +907,56 @@ int jsp_batch_download_display(jsp_batch *b, int32_t *const *out_frames, uint8_t
     return JSP_CUDA(cudaStreamSynchronize(b->st_compute)) ? 0 : -1;
 }
 
+// true when the first destination picture is page-locked memory (an asynchronous D2H into pageable memory would
+// block the host inside the launch loop)
+static bool outputs_pinned(jsp_batch *b, int32_t *const *out_frames)
+{
+    for (size_t i = 0; i < b->frames.size(); i++) {
+        if (!out_frames[i]) continue;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, out_frames[i]) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    }
+    return false;
+}
+
+// Multi-level batches (inter-frame chains): the pictures a launch finishes are copied out on the download stream
+// while the later levels still decode, so the D2H of level L overlaps the decode of levels L+1...
+static int decode_host_streamed(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags)
+{
+    if (jsp_batch_upload(b)) return -1;
+    const Plan &P = b->whole;
+    while (b->ev_sync.size() < P.launches.size() + 1) { cudaEvent_t e; if (!JSP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming))) return -1; b->ev_sync.push_back(e); }
+    cudaEvent_t ev0 = b->ev_sync[P.launches.size()];
+    if (!JSP_CUDA(cudaEventRecord(ev0, b->st_compute)) || !JSP_CUDA(cudaStreamWaitEvent(b->st_out, ev0, 0))) return -1;
+    std::vector<uint8_t> sent(b->frames.size(), 0);
+    const int reruns = b->rerun_count;
+    const bool ok = run_plan_with(b, P, b->st_compute, nullptr, nullptr, [&](int k) {
+        const std::vector<int64_t> &fin = P.finished[(size_t)k];
+        if (fin.empty()) return true;
+        if (!JSP_CUDA(cudaEventRecord(b->ev_sync[(size_t)k], b->st_compute))) return false;
+        if (!JSP_CUDA(cudaStreamWaitEvent(b->st_out, b->ev_sync[(size_t)k], 0))) return false;
+        for (int64_t f : fin) {
+            if (!download_range(b, f, f + 1, out_frames, b->st_out)) return false;
+            sent[(size_t)f] = 1;
+        }
+        return true;
+    });
+    if (!ok) return -1;
+    if (!run_status(b, b->st_compute)) return -1;
+    if (jsp_batch_results(b, flags)) return -1;                              // syncs the compute stream
+    if (b->rerun_count != reruns) std::fill(sent.begin(), sent.end(), 0);    // a demoted key frame: everything was decoded again
+    for (size_t f = 0; f < sent.size(); f++)
+        if (!sent[f] && !download_range(b, (int64_t)f, (int64_t)f + 1, out_frames, b->st_out)) return -1;
+    return JSP_CUDA(cudaStreamSynchronize(b->st_out)) ? 0 : -1;
+}
+
 int jsp_batch_decode_host(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags)
 {
     if (!b) return -1;
     if (b->chunks.empty() || !out_frames) {
-        // latency-bound batches (ScreenPressor) and single frames: upload, decode, download back to back
+        if (out_frames && b->whole.launches.size() > 1 && outputs_pinned(b, out_frames)) return decode_host_streamed(b, out_frames, flags);
+        // single launches and pageable destinations: upload, decode, download back to back
         if (jsp_batch_upload(b)) return -1;
         if (jsp_batch_run(b)) return -1;
         return jsp_batch_download(b, out_frames, flags);

@@ -88,6 +88,7 @@ struct CopyRange { const uint8_t *h; size_t d_off; size_t bytes; };
 struct Plan {
     int64_t frame_lo = 0, frame_hi = 0;        // global frame range covered (streams are contiguous)
     std::vector<Launch> launches;
+    std::vector<std::vector<int64_t>> finished;   // per launch: frames whose picture is final once it completes
     std::vector<CopyRange> uploads;
     size_t tile_tab_off = 0, n_tile_entries = 0;   // slice of d_tile_tab
     size_t job_off = 0, n_jobs = 0;                // slice of d_jobs
