@@ -260,6 +260,8 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
         // longest frames first: when a launch has more warps than the device holds, the late starters are the short ones
         std::vector<int64_t> order(by_level[lv]);
         std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return b->frames[x].len > b->frames[y].len; });
+        // range-coder frames first (the kernel deals the two coders to different SMs when both are present)
+        std::stable_partition(order.begin(), order.end(), [&](int64_t x) { return b->sp_hosts[b->frames[x].stream].version <= 2; });
         for (int64_t f : order) {
             const FrameRec &R = b->frames[f];
             if (R.kind != FK_SP_I && R.kind != FK_SP_P && !(R.kind == FK_SP_FLAT && (R.sp_flags & SPJ_RENEW))) continue;
@@ -283,7 +285,10 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
         }
         if (T.spjobs.size() > first) {
             const int kclass = n_ans == 0 ? JSP_K_SP_ENTROPY_RC : (n_rc == 0 ? JSP_K_SP_ENTROPY_ANS : JSP_K_SP_ENTROPY_MIXED);
-            plan.launches.push_back({kclass, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), max_w, 0});
+            Launch L{kclass, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), max_w, (uint32_t)ticket_cursor};
+            L.n_rc = (uint32_t)n_rc;
+            ticket_cursor += 2;
+            plan.launches.push_back(L);
             plan.finished.push_back(std::move(fin));
         }
     }
@@ -393,7 +398,7 @@ template <class F> static bool run_plan_with(jsp_batch *b, const Plan &P, cudaSt
                                b->d_tile_map, b->d_tile_cnt, b->d_tickets + L.ticket, b->sm_count, st);
             break;
         case JSP_K_SP_ENTROPY_RC: case JSP_K_SP_ENTROPY_ANS: case JSP_K_SP_ENTROPY_MIXED:
-            launch_sp_decode(b->d_spjobs + L.first, L.count, L.max_vec4, st);
+            launch_sp_decode(b->d_spjobs + L.first, L.count, L.max_vec4, L.n_rc, b->d_tickets + L.ticket, st);
             break;
         default: break;
         }

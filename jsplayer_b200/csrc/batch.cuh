@@ -43,7 +43,7 @@ void sp_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t s
 size_t sp_ans_state_bytes();
 size_t sp_ans_ctx_bytes();
 void sp_ans_state_init(void *d_state, void *d_ctx, uint32_t gen0, cudaStream_t st);
-void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, cudaStream_t st);   // sp_decode.cu: both coders, one launch
+void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, uint32_t n_rc, uint32_t *d_queue, cudaStream_t st);   // sp_decode.cu: both coders, one launch
 
 struct StreamRec {
     int codec, w, h, bpp;
@@ -79,7 +79,8 @@ struct Launch {
     size_t first;                   // offset into the plan's tile table / job table
     uint32_t count;                 // CTAs / jobs
     uint32_t max_vec4;              // copy jobs: largest job
-    uint32_t ticket;                // ticket counter slot
+    uint32_t ticket;                // ticket counter slot (MSVideo1 tiles; two job queues of a mixed ScreenPressor launch)
+    uint32_t n_rc = 0;              // ScreenPressor: the first n_rc jobs are range-coder frames
 };
 
 struct CopyRange { const uint8_t *h; size_t d_off; size_t bytes; };

@@ -11,11 +11,29 @@ namespace {
 constexpr size_t SP_SMEM = sizeof(AnsShared) > sizeof(RcShared) ? sizeof(AnsShared) : sizeof(RcShared);
 
 __global__ void __launch_bounds__(32)
-sp_decode_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
+sp_decode_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words, uint32_t n_rc, uint32_t *__restrict__ queue)
 {
     __shared__ alignas(16) uint8_t smem[SP_SMEM];
     extern __shared__ uint32_t ring_mem[];          // the last X + 1 pixels of an I frame (sp_segment_ring)
-    const SpJob J = jobs[blockIdx.x];
+    uint32_t idx = blockIdx.x;
+    if (queue) {
+        // Both coders in one launch: jobs [0, n_rc) are range-coder frames, the rest rANS frames.  The warps that share
+        // an SM share its instruction cache, and the two decoders together do not fit it -- so an SM prefers one
+        // coder: the low SM ids take from the range-coder queue, the others from the rANS queue, each falling back to
+        // the other queue once its own is empty (gridDim.x == number of jobs, so every warp gets exactly one).
+        if ((threadIdx.x & 31) == 0) {
+            uint32_t smid, nsm;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+            const uint32_t n = gridDim.x, n_ans = n - n_rc;
+            const bool want_rc = (uint64_t)smid * n < (uint64_t)n_rc * nsm;
+            uint32_t t = atomicAdd(&queue[want_rc ? 0 : 1], 1u);
+            if (want_rc) idx = t < n_rc ? t : n_rc + atomicAdd(&queue[1], 1u);
+            else idx = t < n_ans ? n_rc + t : atomicAdd(&queue[0], 1u);
+        }
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+    }
+    const SpJob J = jobs[idx];
     uint32_t *ring = sp_ring_size(J.X) <= ring_words ? ring_mem : nullptr;     // pictures too wide for it read global memory
     if (J.flags & SPJ_ANS) sp_ans_run(J, *reinterpret_cast<AnsShared *>(smem), ring);
     else sp_rc_run(J, *reinterpret_cast<RcShared *>(smem), ring);
@@ -78,7 +96,7 @@ extern "C" __attribute__((visibility("default"))) int jsp_debug_rc_profile(unsig
 }
 #endif
 
-void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, cudaStream_t st)
+void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, uint32_t n_rc, uint32_t *d_queue, cudaStream_t st)
 {
     if (!n_jobs) return;
     uint32_t words = 64;
@@ -86,7 +104,8 @@ void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, 
     if (words > 16384u) words = 0;                                     // > 64 KB: such frames fall back to global reads
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(sp_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr_set = true; }
-    sp_decode_kernel<<<n_jobs, 32, (size_t)words * 4, st>>>(d_jobs, words);
+    const bool mixed = n_rc != 0 && n_rc != n_jobs && d_queue;
+    sp_decode_kernel<<<n_jobs, 32, (size_t)words * 4, st>>>(d_jobs, words, n_rc, mixed ? d_queue : nullptr);
 }
 
 }  // namespace jsp
