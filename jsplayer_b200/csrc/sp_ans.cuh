@@ -731,6 +731,7 @@ struct AnsCoder {
     {
         constexpr int K = FxTab<N>::K;
         const int lane = (int)lane_id(), j0 = lane * K;
+        if (fail) return 0;                                            // a failed frame decodes nothing more: the models stay as they were
         const int f = get();
         uint32_t cum[K];
         ld_u16<K>(t.cum + j0, cum);
@@ -832,6 +833,7 @@ struct AnsCoder {
     __device__ int decodeClr(int cxi)                                 // EntroCoders.hx:235-255
     {
         const int lane = (int)lane_id();
+        if (fail) return 0;                                            // as in decodeF
 #ifdef JSP_PROFILE_SECTIONS
         long long _at = clock64();
 #endif
@@ -964,6 +966,7 @@ struct AnsCoder {
 
     __device__ bool decodeBool()                                      // EntroCoders.hx:259-269
     {
+        if (fail) return false;
         const int f = get();
         const bool flag = f >= (ANS_SCALE >> 1);
         advance(flag ? ANS_SCALE >> 1 : 0, ANS_SCALE >> 1);
@@ -981,7 +984,7 @@ struct AnsCoder {
 };
 
 // one frame of one rANS stream; `sm` = this warp's shared memory
-__device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm, uint32_t *ring)
+__device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm, uint32_t *ring, uint32_t *ptile)
 {
     AnsState *st = reinterpret_cast<AnsState *>(J.state);
     const int lane = (int)lane_id();
@@ -1006,7 +1009,7 @@ __device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm, uint32
         sp_decode_iframe(ec, J, ring);
         bits |= ST_CHANGED;
     } else {
-        sp_decode_pframe(ec, J, bits);
+        sp_decode_pframe(ec, J, bits, ptile);
     }
     ec.flush_slots();
     if (ec.failed()) {

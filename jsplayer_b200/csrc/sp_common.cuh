@@ -146,6 +146,10 @@ __device__ __forceinline__ long sp_run_budget(long X, long Y) { return 2 * X * Y
 // I-frame loop, summed into g_sp_prof[] -- how the per-symbol latency was broken down.
 #ifdef JSP_PROFILE_SECTIONS
 __device__ unsigned long long g_sp_prof[8];
+__device__ unsigned long long g_spp_prof[10];     // P frames: block types, symbol decodes, run writes, motion, whole, runs, row pieces, frames
+#define JSP_PT0 const long long _pt0 = clock64();
+#define JSP_PT1(k) _pacc[k] += clock64() - _pt0;
+#define JSP_PCOUNT(k) _pacc[k]++;
 #define JSP_T0 const long long _t0 = clock64();
 #define JSP_T1(k) _acc[k] += clock64() - _t0;
 #define JSP_PROF_DECL long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -155,6 +159,9 @@ __device__ unsigned long long g_sp_prof[8];
 #define JSP_T1(k)
 #define JSP_PROF_DECL
 #define JSP_PROF_FLUSH
+#define JSP_PT0
+#define JSP_PT1(k)
+#define JSP_PCOUNT(k)
 #endif
 
 // ---- the frame loops, generic over the entropy coder (EntroCoder interface, EntroCoders.hx:8-24) ----
@@ -236,8 +243,15 @@ __device__ void sp_decode_iframe(Coder &ec, const SpJob &J, uint32_t *ring)
     JSP_PROF_FLUSH
 }
 
+// P-frame data blocks are decoded against a shared-memory copy of the rectangle and its upper / left neighbours: every
+// row piece of a run reads the pixel to its left or the row above, and from global memory each of those reads is an L2
+// round trip on the serial chain (~550 cycles per row piece measured, tools/sp_pframe_profile.py).
+constexpr int SP_PT_STRIDE = 17;                                   // (16 + 1) x (16 + 1) pixels of the output picture ...
+constexpr int SP_PT_PREV = 320;                                   // ... then 16 x 16 of the previous picture
+constexpr uint32_t SP_PTILE_WORDS = SP_PT_PREV + 16 * 16 + 32;     // + slack for the reads of inactive lanes
+
 template <class Coder>
-__device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bits)
+__device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bits, uint32_t *ptile)
 {
     const long X = J.X, Y = J.Y, end = X * Y;
     const int nbx = (int)((J.X + 15) / 16), nby = (int)((J.Y + 15) / 16), nb = nbx * nby;
@@ -248,6 +262,13 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
     const int cxshift = (J.flags & SPJ_CXSHIFT0) ? 0 : 2;
     int maskcx1 = 0xFC00, shiftcx1 = 4, shiftcx = 18;
     if (J.flags & SPJ_DIFF16) { maskcx1 = 0xFF00; shiftcx1 = 2; shiftcx = 16; }
+#ifdef JSP_PROFILE_SECTIONS
+    long long _pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long _pall = clock64();
+    struct PFlush { long long *a; long long t0; __device__ ~PFlush() { a[4] += clock64() - t0; a[7]++;
+        if (lane_id() == 0) { for (int k = 0; k < 8; k++) atomicAdd(&g_spp_prof[k], (unsigned long long)a[k]);
+                              atomicMax(&g_spp_prof[8], (unsigned long long)a[4]); } } } _pflush{_pacc, _pall};
+#endif
     ec.decodeBegin(J.src, J.len, 1);
     int t = ec.decodeX();
     int xx1 = ec.decodeX(); xx1 = (xx1 << 8) + t;
@@ -272,6 +293,9 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
         x += n;
     }
     __syncwarp();
+#ifdef JSP_PROFILE_SECTIONS
+    _pacc[0] += clock64() - _pall;
+#endif
     if (signif) status_bits |= ST_SIGNIFICANT;
     status_bits |= ST_CHANGED;
     int cx = 0, cx1 = 0;
@@ -301,6 +325,7 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
         int x1 = x16, x2 = x16 + 16, y1 = y16, y2 = y16 + 16;
         if (x2 > X) x2 = (int)X;
         if (y2 > Y) y2 = (int)Y;
+        JSP_PT0
         if (((bt - 1) & 1) > 0) {                  // sub-rectangle (:375-386); the block itself is already copied
             x1 = ec.decodeSXY(0) + x16;
             y1 = ec.decodeSXY(1) + y16;
@@ -322,15 +347,46 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
                 }
             }
             __syncwarp();
+            JSP_PT1(3)
         } else {                                   // data (:406-467): runs in raster order inside the rectangle
+            JSP_PT1(3)
             int xq = x1, y = y1, ptype = 0;
+            // well-formed rectangle: stage it (rows y1-1 .. y2-1, columns x1-1 .. x2-1, by linear pixel index) in shared memory
+            // (not when the rectangle spans the picture's width: the pixel "left" of column 0 is the previous row's last
+            // pixel, which the block itself rewrites)
+            const bool tiled = ptile != nullptr && x2 > x1 && x2 <= X && y2 > y1 && y2 <= Y && !(x1 == 0 && x2 == X);
+            if (tiled) {
+                const int w = x2 - x1, h = y2 - y1;
+                // all loads first, then the stores: the warp waits for one L2 round trip, not for eighteen
+                uint32_t ra[10], rb[8];
+#pragma unroll
+                for (int it = 0; it < 10; it++) {
+                    const int k = lane + 32 * it, ry = k / 17, rx = k - ry * 17;
+                    ra[it] = (ry <= h && rx <= w) ? px_load(dst, (long)(y1 - 1 + ry) * X + (x1 - 1 + rx), end) : 0u;
+                }
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int k = lane + 32 * it, ry = k >> 4, rx = k & 15;
+                    rb[it] = (ry < h && rx < w) ? px_load(prev, (long)(y1 + ry) * X + (x1 + rx), end) : 0u;
+                }
+#pragma unroll
+                for (int it = 0; it < 10; it++) ptile[lane + 32 * it] = ra[it];       // 320 words: up to SP_PT_PREV
+#pragma unroll
+                for (int it = 0; it < 8; it++) ptile[SP_PT_PREV + lane + 32 * it] = rb[it];
+                __syncwarp();
+            }
             while (y < y2) {
                 if (--budget < 0) ec.fail = true;
+                int n;
+                { JSP_PT0
                 ptype = ec.decodeP(ptype);
                 if (ptype == 0) clr = decode_rgb();
-                int n = ec.decodeN(ptype);
+                n = ec.decodeN(ptype);
+                JSP_PT1(1) JSP_PCOUNT(5) }
                 if (ec.failed()) return;
-                while (n > 0) {                    // one row piece at a time: later rows may read this one
+                JSP_PT0
+                while (n > 0) {
+                    JSP_PCOUNT(6)                    // one row piece at a time: later rows may read this one
                     int m = x2 - xq; if (m > n) m = n; if (m > 32) m = 32;
                     if (m <= 0) {                  // degenerate rectangle (x2 <= x1): the reference steps one pixel per row
                         const long i = (long)y * X + xq;
@@ -344,12 +400,59 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
                         continue;
                     }
                     const long i = (long)y * X + xq;
-                    const uint32_t left = (ptype == 1 || ptype == 4) ? px_load(dst, i - 1, end) : 0u;
-                    const uint32_t last = sp_segment(dst, prev, i, m, ptype, clr, left, X, end);
+                    uint32_t last;
+                    if (tiled && y < y2) {
+                        uint32_t *row = ptile + (y - y1 + 1) * SP_PT_STRIDE + (xq - x1 + 1);      // &tile[y][xq]
+                        uint32_t v = clr;
+                        switch (ptype) {
+                        case 1: v = row[-1]; break;
+                        case 2: v = row[lane - SP_PT_STRIDE]; break;
+                        case 3: v = ptile[SP_PT_PREV + (y - y1) * 16 + (xq - x1) + lane]; break;
+                        case 5: v = row[lane - SP_PT_STRIDE - 1]; break;
+                        case 4: {
+                            uint32_t d = lane < m ? vsub4(row[lane - SP_PT_STRIDE], row[lane - SP_PT_STRIDE - 1]) : 0u;
+#pragma unroll
+                            for (int sft = 1; sft < 16; sft <<= 1) {           // m <= 16 here
+                                const uint32_t o = __shfl_up_sync(FULLMASK, d, sft);
+                                if (lane >= sft) d = vadd4(d, o);
+                            }
+                            v = vadd4(row[-1], d) & 0x00FFFFFFu;
+                            break;
+                        }
+                        default: break;
+                        }
+                        if (lane < m) { row[lane] = v; dst[i + lane] = (int32_t)v; }
+                        last = __shfl_sync(FULLMASK, v, (m - 1) & 31);
+                        __syncwarp();
+                    } else if (i + m > end || m >= X) {
+                        // a piece that leaves the picture (or is wider than a picture row): only a corrupt stream gets
+                        // here.  Pixels outside the picture are not written and read as 0, so the left-to-right chain
+                        // the parallel segment assumes does not hold: one pixel at a time, as the reference does it
+                        // (every lane runs the same loop and reads back its own stores)
+                        uint32_t v = clr;
+                        for (int k = 0; k < m; k++) {
+                            const long p = i + k;
+                            switch (ptype) {
+                            case 1: v = px_load(dst, p - 1, end); break;
+                            case 2: v = px_load(dst, p - X, end); break;
+                            case 3: v = px_load(prev, p, end); break;
+                            case 4: v = vadd4(px_load(dst, p - 1, end), vsub4(px_load(dst, p - X, end), px_load(dst, p - X - 1, end))) & 0x00FFFFFFu; break;
+                            case 5: v = px_load(dst, p - X - 1, end); break;
+                            default: break;
+                            }
+                            if (p >= 0 && p < end) dst[p] = (int32_t)v;
+                        }
+                        last = v;
+                        __syncwarp();
+                    } else {
+                        const uint32_t left = (ptype == 1 || ptype == 4) ? px_load(dst, i - 1, end) : 0u;
+                        last = sp_segment(dst, prev, i, m, ptype, clr, left, X, end);
+                    }
                     if (ptype != 0) clr = last;
                     n -= m; xq += m;
                     if (xq >= x2) { xq = x1; y++; }
                 }
+                JSP_PT1(2)
                 cx1 = ((int)clr & maskcx1) >> shiftcx1;    // :462-463
                 cx = (int)clr >> shiftcx;
             }

@@ -35,8 +35,12 @@ sp_decode_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words, uint32_t n
     }
     const SpJob J = jobs[idx];
     uint32_t *ring = sp_ring_size(J.X) <= ring_words ? ring_mem : nullptr;     // pictures too wide for it read global memory
-    if (J.flags & SPJ_ANS) sp_ans_run(J, *reinterpret_cast<AnsShared *>(smem), ring);
-    else sp_rc_run(J, *reinterpret_cast<RcShared *>(smem), ring);
+    uint32_t *ptile = ring_words >= SP_PTILE_WORDS ? ring_mem : nullptr;       // P frames use the same memory for their block tile
+#ifdef JSP_NO_PTILE
+    ptile = nullptr;
+#endif
+    if (J.flags & SPJ_ANS) sp_ans_run(J, *reinterpret_cast<AnsShared *>(smem), ring, ptile);
+    else sp_rc_run(J, *reinterpret_cast<RcShared *>(smem), ring, ptile);
 }
 
 }  // namespace
@@ -80,6 +84,13 @@ extern "C" __attribute__((visibility("default"))) int jsp_debug_sp_profile(unsig
     if (reset) cudaMemcpyToSymbol(g_sp_prof, z, sizeof z);
     return 0;
 }
+extern "C" __attribute__((visibility("default"))) int jsp_debug_spp_profile(unsigned long long *out, int reset)
+{
+    unsigned long long z[10] = {0};
+    if (cudaMemcpyFromSymbol(out, g_spp_prof, sizeof z) != cudaSuccess) return -1;
+    if (reset) cudaMemcpyToSymbol(g_spp_prof, z, sizeof z);
+    return 0;
+}
 extern "C" __attribute__((visibility("default"))) int jsp_debug_ans_profile(unsigned long long *out, int reset)
 {
     unsigned long long z[16] = {0};
@@ -99,9 +110,10 @@ extern "C" __attribute__((visibility("default"))) int jsp_debug_rc_profile(unsig
 void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, uint32_t n_rc, uint32_t *d_queue, cudaStream_t st)
 {
     if (!n_jobs) return;
-    uint32_t words = 64;
-    while (words <= max_width + 65u) words <<= 1;                    // = sp_ring_size(max_width)
-    if (words > 16384u) words = 0;                                     // > 64 KB: such frames fall back to global reads
+    uint32_t words = 1024;                                             // at least the P-frame block tile (SP_PTILE_WORDS)
+    while (words <= max_width + 65u) words <<= 1;                    // >= sp_ring_size(max_width)
+    if (words > 16384u) words = 1024;                                  // > 64 KB: such I frames fall back to global reads
+    static_assert(SP_PTILE_WORDS <= 1024, "P-frame tile fits the minimum dynamic shared memory");
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(sp_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr_set = true; }
     const bool mixed = n_rc != 0 && n_rc != n_jobs && d_queue;

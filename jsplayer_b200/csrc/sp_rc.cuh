@@ -192,6 +192,7 @@ struct RcCoder {
     __device__ int decode_tiny(RcTiny &t, uint32_t step)
     {
         const int lane = (int)lane_id();
+        if (fail) return 0;                                    // a failed frame decodes nothing more: the models stay as they were
         nsym++;
         uint32_t p = t.P[lane];
         uint32_t tot = __shfl_sync(FULLMASK, p, N - 1);
@@ -223,6 +224,7 @@ struct RcCoder {
     __device__ __forceinline__ int decode_big(uint32_t *tab, uint32_t step)
     {
         const int lane = (int)lane_id();
+        if (fail) return 0;                                    // as in decode_tiny
         nsym++;
         JSP_PT0
         uint32_t lp[K];
@@ -381,7 +383,7 @@ struct RcCoder {
 };
 
 // one frame of one range-coder stream; `sm` = this warp's shared memory
-__device__ __forceinline__ void sp_rc_run(const SpJob &J, RcShared &shm, uint32_t *ring)
+__device__ __forceinline__ void sp_rc_run(const SpJob &J, RcShared &shm, uint32_t *ring, uint32_t *ptile)
 {
     RcState *st = reinterpret_cast<RcState *>(J.state);
     const int lane = (int)lane_id();
@@ -407,7 +409,7 @@ __device__ __forceinline__ void sp_rc_run(const SpJob &J, RcShared &shm, uint32_
         sp_decode_iframe(ec, J, ring);
         bits |= ST_CHANGED;
     } else {
-        sp_decode_pframe(ec, J, bits);
+        sp_decode_pframe(ec, J, bits, ptile);
     }
     ec.flush_rows();
     if (ec.failed()) {

@@ -91,6 +91,7 @@ static inline void ea_count(entro_ans *a)
 static int ea_clr(entro *e, int cxi)                       /* :235-255 */
 {
     entro_ans *a = (entro_ans *)e;
+    if (a->rans.failed) return 0;                          /* a failed frame decodes nothing more (sp_entro.h) */
     color_ctx *dcx = &a->cntab[cxi];
     dec_receiver rcv; int c;
     if (cctx_decode(dcx, rans_get(&a->rans), &rcv, a->f0)) {
@@ -109,6 +110,7 @@ static int ea_clr(entro *e, int cxi)                       /* :235-255 */
 static int ea_bool(entro *e)                               /* :259-269 */
 {
     entro_ans *a = (entro_ans *)e;
+    if (a->rans.failed) return 0;
     const int f = rans_get(&a->rans);
     const int flag = f >= (ANS_PROB_SCALE >> 1);
     rans_advance(&a->rans, flag ? ANS_PROB_SCALE >> 1 : 0, ANS_PROB_SCALE >> 1);
@@ -118,6 +120,7 @@ static int ea_bool(entro *e)                               /* :259-269 */
 static int ea_f(entro_ans *a, fixed_ctx *t)                /* decodeF, :271-280 */
 {
     dec_receiver rcv;
+    if (a->rans.failed) return 0;
     fx_decode(t, rans_get(&a->rans), &rcv);
     rans_advance(&a->rans, rcv.cumFreq, rcv.freq);
     ea_count(a);
@@ -134,6 +137,7 @@ static int ea_my(entro *e) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->m
 static int ea_canbool(entro *e) { (void)e; return 1; }
 static int ea_diff16(entro *e) { (void)e; return 0; }      /* EntroCoders.hx:214 */
 static int ea_failed(entro *e) { return ((entro_ans *)e)->rans.failed; }
+static void ea_fail(entro *e) { ((entro_ans *)e)->rans.failed = 1; }
 
 entro *entro_ans_new(int f0val)
 {
@@ -149,7 +153,7 @@ entro *entro_ans_new(int f0val)
     a->base.decodeClr = ea_clr; a->base.decodeN = ea_n; a->base.decodeP = ea_p; a->base.decodeX = ea_x; a->base.decodeBT = ea_bt;
     a->base.decodeBN = ea_bn; a->base.decodeSXY = ea_sxy; a->base.decodeMX = ea_mx; a->base.decodeMY = ea_my;
     a->base.canDecodeBool = ea_canbool; a->base.decodeBool = ea_bool; a->base.differentConstantsFor16bpp = ea_diff16;
-    a->base.failed = ea_failed;
+    a->base.failed = ea_failed; a->base.fail = ea_fail;
     return &a->base;
 }
 

@@ -8,6 +8,10 @@
  * yields `undefined`, which turns `code` into NaN for good; `Std.int(NaN / range)` is 0 from then on
  * (RangeCoder.hx:41,48).  That state is kept as `poisoned`; asking for another symbol in it is reported
  * through failed() (defined behaviour; the reference would go on decoding symbol 0 for ever).
+ *
+ * After the first failed symbol of a frame no further symbol is decoded (every later call returns 0 and touches
+ * nothing): a failed symbol leaves `range` un-normalised, and what JavaScript's doubles would compute from there
+ * (code >= 2^32, division by a zero range) is not something a 32-bit decoder should have to reproduce.
  */
 #include "sp_entro.h"
 #include <stdlib.h>
@@ -52,6 +56,10 @@ static inline uint32_t rc_get_freq(rangecoder *rc, uint32_t tot)
     g_ora_symbols++;
     if (rc->poisoned) rc->failed = 1;
     rc->range = rc->range / tot;
+    /* Only after a failed symbol (whose range stays un-normalised until the frame loop looks at failed()) can the range
+     * drop below a table total.  JavaScript would go on with code / 0 = Infinity; defined behaviour here: the value lies
+     * above every cumulative count, i.e. the symbol fails again and no table is touched. */
+    if (rc->range == 0) { rc->failed = 1; return 0xFFFFFFFFu; }
     if (rc->poisoned) return 0;
     uint64_t v = rc->code / rc->range;
     return v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v;
@@ -68,6 +76,7 @@ static inline void rc_decode(rangecoder *rc, uint32_t cum, uint32_t freq)
 /* RangeCoder.hx:51-80 */
 static int rc_decode_val(rangecoder *rc, uint32_t *cnt, int maxc, uint32_t step)
 {
+    if (rc->failed) return 0;                                /* defined behaviour: a failed frame decodes nothing more */
     uint32_t totfr = cnt[maxc];
     uint32_t value = rc_get_freq(rc, totfr);
     int c = 0; uint32_t cumfr = 0, cnt_c = 0;
@@ -91,6 +100,7 @@ static int rc_decode_val(rangecoder *rc, uint32_t *cnt, int maxc, uint32_t step)
 /* RangeCoder.hx:82-130: 16 group sums at [off..off+15], total at [off+16], 256 counts at [off+17..] */
 static int rc_decode_val_uni(rangecoder *rc, uint32_t *cnt, uint32_t step)
 {
+    if (rc->failed) return 0;                                /* as above */
     uint32_t totfr = cnt[16];
     uint32_t value = rc_get_freq(rc, totfr);
     int x = 0; uint32_t cumfr = 0, cnt_x = 0;
@@ -186,6 +196,7 @@ static int erc_canbool(entro *e) { (void)e; return 0; }
 static int erc_bool(entro *e) { (void)e; return 0; }
 static int erc_diff16(entro *e) { (void)e; return 1; }       /* EntroCoders.hx:72 */
 static int erc_failed(entro *e) { return ((entro_rc *)e)->rc.failed; }
+static void erc_fail(entro *e) { ((entro_rc *)e)->rc.failed = 1; }
 
 entro *entro_rc_new(void)
 {
@@ -195,7 +206,7 @@ entro *entro_rc_new(void)
     r->base.decodeBegin = erc_begin; r->base.decodeClr = erc_clr; r->base.decodeN = erc_n; r->base.decodeP = erc_p;
     r->base.decodeX = erc_x; r->base.decodeBT = erc_bt; r->base.decodeBN = erc_bn; r->base.decodeSXY = erc_sxy;
     r->base.decodeMX = erc_mx; r->base.decodeMY = erc_my; r->base.canDecodeBool = erc_canbool; r->base.decodeBool = erc_bool;
-    r->base.differentConstantsFor16bpp = erc_diff16; r->base.failed = erc_failed;
+    r->base.differentConstantsFor16bpp = erc_diff16; r->base.failed = erc_failed; r->base.fail = erc_fail;
     return &r->base;
 }
 

@@ -95,7 +95,7 @@ static inline int32_t px_get(const int32_t *p, long i, long end) { return (i >= 
  * has adapted, so a hostile stream can keep a decoder busy for ever.  No encoder emits them; a frame that needs more
  * run-loop iterations than 2 per pixel + 16 per block + 4096 is reported as failed (ctx_fail doubles as the flag). */
 #define SP_RUN_BUDGET(X, Y) (2L * (X) * (Y) + 16L * (((X) + 15) / 16) * (((Y) + 15) / 16) + 4096)
-#define SP_SPEND(s) do { if (--(s)->budget < 0) (s)->ctx_fail = 1; } while (0)
+#define SP_SPEND(s) do { if (--(s)->budget < 0) { (s)->ctx_fail = 1; (s)->ec->fail((s)->ec); } } while (0)
 
 /* Defined behaviour (not in the reference): cx + cx1 stays below 4096 on every valid stream (cx < 64, cx1 <= 0xFC0;
  * 16 bpp v2: 5-bit channel values).  A corrupt stream can exceed it -- the reference would read outside cntab[] --
@@ -108,7 +108,7 @@ long ora_ctx_trace_count(void) { return g_ora_ctx_trace_n; }
 static inline int ctx_index(sp_dec *s, int channel)
 {
     int i = s->cx + s->cx1;
-    if (i < 0 || i >= CC_CXMAX) { s->ctx_fail = 1; i &= CC_CXMAX - 1; }
+    if (i < 0 || i >= CC_CXMAX) { s->ctx_fail = 1; s->ec->fail(s->ec); i &= CC_CXMAX - 1; }
     if (g_ora_ctx_trace && g_ora_ctx_trace_n < g_ora_ctx_trace_cap) g_ora_ctx_trace[g_ora_ctx_trace_n++] = channel * CC_CXMAX + i;
     return channel * CC_CXMAX + i;
 }
@@ -313,6 +313,8 @@ int sp_decompress_p(sp_dec *s, const uint8_t *src, int len, int32_t *dst, const 
                 }
             }
         }
+    /* a symbol that failed after the last in-loop check (e.g. the sub-rectangle of a block that then holds no rows) */
+    if ((ec->failed(ec) || s->ctx_fail)) return ORA_ERROR_OCCURED;
     s->prevFrame = dst;
     *data_pnt = dst; *signif_out = signif;
     return ORA_ZERO_STATE;

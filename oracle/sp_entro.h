@@ -25,6 +25,10 @@ struct entro {
     /* not in the reference: set when the coder was asked for a symbol after it had already read past the
      * end of the data, or when a symbol search ran off its table (both impossible on a valid stream) */
     int  (*failed)(entro *);
+    /* not in the reference: the frame loop reports a failure of its own (colour-context index out of range, run budget
+     * spent).  Defined behaviour for every kind of failure: after the first one no further symbol of the frame is
+     * decoded -- each decode call returns 0 and leaves the models alone. */
+    void (*fail)(entro *);
 };
 
 entro *entro_rc_new(void);            /* EntroCoderRC, EntroCoders.hx:31-180 */

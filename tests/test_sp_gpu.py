@@ -231,3 +231,55 @@ def test_symbol_count_matches_the_oracle():
         assert bd.symbols() == got                                  # per run, not cumulative
         bd.close()
         assert got == want and got > 0
+
+
+@pytest.mark.parametrize("version", [2, 3, 4])
+def test_corrupt_p_frames_match_the_oracle(version):
+    """Bit flips in P frames: rectangles that degenerate or leave the picture, runs that overflow their rectangle,
+    motion vectors pointing outside -- whatever the decoder then does must equal the oracle, frame by frame (the
+    shared-memory block tile of well-formed rectangles and the global-memory path of the others mix freely)."""
+    rng = np.random.default_rng(100 + version)
+    for (w, h) in ((100, 60), (33, 17), (64, 48), (16, 16), (250, 130)):
+        frames, keys, pics = synth.sp_stream(w, h, 4, seed=w + version, version=version, change_permille=250)
+        for trial in range(12):
+            bad = [frames[0]]
+            for f in frames[1:]:
+                b = bytearray(f)
+                if len(b) > 4:
+                    for _ in range(1 + trial % 3):
+                        b[int(rng.integers(1, len(b)))] ^= int(1 << rng.integers(0, 8))
+                bad.append(bytes(b))
+            check(w, h, 24, bad, keys)
+
+
+@pytest.mark.parametrize("version,bpp", [(2, 24), (3, 24), (4, 24), (2, 16)])
+def test_fuzzed_batches_match_the_oracle(version, bpp):
+    """tools/sp_fuzz.py in small: corrupted I and P frames (bit flips, truncation), narrow and odd picture sizes, many
+    corrupted copies decoded as one batch."""
+    rng = np.random.default_rng(4242 + version + bpp)
+    for (w, h) in ((33, 17), (16, 16), (9, 20), (96, 32)):
+        frames, keys, pics = synth.sp_stream(w, h, 6, seed=w + version, version=version, gop=4, change_permille=200, bpp=bpp)
+        specs, cases = [], []
+        for trial in range(16):
+            bad = []
+            for fi, f in enumerate(frames):
+                b = bytearray(f)
+                hit = (fi > 0) if trial % 4 < 2 else (rng.random() < 0.5)
+                if hit and len(b) > 6:
+                    for _ in range(1 + trial % 5):
+                        b[int(rng.integers(1, len(b)))] ^= int(1 << rng.integers(0, 8))
+                    if trial % 4 == 3 and rng.random() < 0.3:
+                        b = b[: int(rng.integers(2, len(b)))]
+                bad.append(bytes(b))
+            specs.append(StreamSpec(SP, w, h, bpp, frames=bad, keys=keys)); cases.append(bad)
+        outs, flags = gpu_decode(specs, insign=16)
+        k = 0
+        for trial, bad in enumerate(cases):
+            exp, ch, sg, st = O.decode_stream(O.CODEC_SCREENPRESSOR, w, h, bpp, bad, keys=keys, insignificant_lines=16)
+            for i in range(len(bad)):
+                err = bool(flags[k] & _lib.JSP_FRAME_ERROR)
+                assert err == (st[i] != 0), (w, h, trial, i)
+                assert (outs[k] == exp[i]).all(), (w, h, trial, i)
+                if not err:
+                    assert bool(flags[k] & _lib.JSP_FRAME_CHANGED) == bool(ch[i]), (w, h, trial, i)
+                k += 1
