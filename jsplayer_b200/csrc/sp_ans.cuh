@@ -633,6 +633,9 @@ struct AnsCoder {
     bool overrun, fail;
 
     __device__ __forceinline__ bool failed() const { return fail; }
+    // a failure found by the frame loop.  (rANS arithmetic stays well defined on garbage -- 32-bit state, bounded tables --
+    // so this coder simply goes on until the loop's next check, exactly as the oracle does.)
+    __device__ __forceinline__ void fail_frame() { fail = true; }
 
     __device__ __forceinline__ uint32_t rbyte()                       // data[pos++]; out of bounds reads as 0 after `|`
     {
@@ -731,7 +734,6 @@ struct AnsCoder {
     {
         constexpr int K = FxTab<N>::K;
         const int lane = (int)lane_id(), j0 = lane * K;
-        if (fail) return 0;                                            // a failed frame decodes nothing more: the models stay as they were
         const int f = get();
         uint32_t cum[K];
         ld_u16<K>(t.cum + j0, cum);
@@ -833,7 +835,6 @@ struct AnsCoder {
     __device__ int decodeClr(int cxi)                                 // EntroCoders.hx:235-255
     {
         const int lane = (int)lane_id();
-        if (fail) return 0;                                            // as in decodeF
 #ifdef JSP_PROFILE_SECTIONS
         long long _at = clock64();
 #endif
@@ -966,7 +967,6 @@ struct AnsCoder {
 
     __device__ bool decodeBool()                                      // EntroCoders.hx:259-269
     {
-        if (fail) return false;
         const int f = get();
         const bool flag = f >= (ANS_SCALE >> 1);
         advance(flag ? ANS_SCALE >> 1 : 0, ANS_SCALE >> 1);

@@ -134,7 +134,7 @@ template <class Coder>
 __device__ __forceinline__ int sp_ctx_index(Coder &ec, int channel, int cx, int cx1)
 {
     int i = cx + cx1;
-    if (i < 0 || i >= 4096) { ec.fail = true; i &= 4095; }
+    if (i < 0 || i >= 4096) { ec.fail_frame(); i &= 4095; }
     return channel * 4096 + i;
 }
 
@@ -195,7 +195,7 @@ __device__ void sp_decode_iframe(Coder &ec, const SpJob &J, uint32_t *ring)
     };
     long budget = sp_run_budget(X, J.Y);
     while (k < X + 1) {                            // first X+1 pixels: (colour, run) pairs, :170-197
-        if (--budget < 0) ec.fail = true;
+        if (--budget < 0) ec.fail_frame();
         clr = decode_rgb();
         const int n = ec.decodeN(0);
         if (ec.failed()) return;
@@ -214,7 +214,7 @@ __device__ void sp_decode_iframe(Coder &ec, const SpJob &J, uint32_t *ring)
     const long long _tall = clock64();
 #endif
     while (di < end) {                             // :218-286
-        if (--budget < 0) ec.fail = true;
+        if (--budget < 0) ec.fail_frame();
         { JSP_T0 ptype = ec.decodeP(ptype); JSP_T1(0) }
         if (ptype == 0) { JSP_T0 clr = decode_rgb(); JSP_T1(1) }
         int n;
@@ -241,6 +241,26 @@ __device__ void sp_decode_iframe(Coder &ec, const SpJob &J, uint32_t *ring)
     _acc[4] += clock64() - _tall;
 #endif
     JSP_PROF_FLUSH
+}
+
+// A row piece decoded one pixel at a time by every lane (each reads back its own stores): for pieces that leave the
+// picture, where pixels are not written and read as 0.  Cold: only corrupt streams get here.
+static __device__ __noinline__ uint32_t sp_piece_pixelwise(int32_t *dst, const int32_t *prev, long i, int m, int ptype, uint32_t clr, long X, long end)
+{
+    uint32_t v = clr;
+    for (int k = 0; k < m; k++) {
+        const long p = i + k;
+        switch (ptype) {
+        case 1: v = px_load(dst, p - 1, end); break;
+        case 2: v = px_load(dst, p - X, end); break;
+        case 3: v = px_load(prev, p, end); break;
+        case 4: v = vadd4(px_load(dst, p - 1, end), vsub4(px_load(dst, p - X, end), px_load(dst, p - X - 1, end))) & 0x00FFFFFFu; break;
+        case 5: v = px_load(dst, p - X - 1, end); break;
+        default: break;
+        }
+        if (p >= 0 && p < end) dst[p] = (int32_t)v;
+    }
+    return v;
 }
 
 // P-frame data blocks are decoded against a shared-memory copy of the rectangle and its upper / left neighbours: every
@@ -280,7 +300,7 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
     long x = xx1;
     long budget = sp_run_budget(X, Y);
     while (x <= xx2) {                             // block types, run-length coded (:336-344)
-        if (--budget < 0) ec.fail = true;
+        if (--budget < 0) ec.fail_frame();
         const int bt = ec.decodeBT();
         const int n = ec.decodeBN();
         if (ec.failed()) return;
@@ -376,7 +396,7 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
                 __syncwarp();
             }
             while (y < y2) {
-                if (--budget < 0) ec.fail = true;
+                if (--budget < 0) ec.fail_frame();
                 int n;
                 { JSP_PT0
                 ptype = ec.decodeP(ptype);
@@ -429,20 +449,7 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
                         // here.  Pixels outside the picture are not written and read as 0, so the left-to-right chain
                         // the parallel segment assumes does not hold: one pixel at a time, as the reference does it
                         // (every lane runs the same loop and reads back its own stores)
-                        uint32_t v = clr;
-                        for (int k = 0; k < m; k++) {
-                            const long p = i + k;
-                            switch (ptype) {
-                            case 1: v = px_load(dst, p - 1, end); break;
-                            case 2: v = px_load(dst, p - X, end); break;
-                            case 3: v = px_load(prev, p, end); break;
-                            case 4: v = vadd4(px_load(dst, p - 1, end), vsub4(px_load(dst, p - X, end), px_load(dst, p - X - 1, end))) & 0x00FFFFFFu; break;
-                            case 5: v = px_load(dst, p - X - 1, end); break;
-                            default: break;
-                            }
-                            if (p >= 0 && p < end) dst[p] = (int32_t)v;
-                        }
-                        last = v;
+                        last = sp_piece_pixelwise(dst, prev, i, m, ptype, clr, X, end);
                         __syncwarp();
                     } else {
                         const uint32_t left = (ptype == 1 || ptype == 4) ? px_load(dst, i - 1, end) : 0u;

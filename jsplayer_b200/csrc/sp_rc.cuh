@@ -130,6 +130,7 @@ struct RcCoder {
     bool poisoned, fail;
 
     __device__ __forceinline__ bool failed() const { return fail; }
+    __device__ __forceinline__ void fail_frame() { fail = true; range = 0; }   // a failure found by the frame loop; see decode_tiny
 
     __device__ __forceinline__ void next_byte()
     {
@@ -192,16 +193,18 @@ struct RcCoder {
     __device__ int decode_tiny(RcTiny &t, uint32_t step)
     {
         const int lane = (int)lane_id();
-        if (fail) return 0;                                    // a failed frame decodes nothing more: the models stay as they were
         nsym++;
         uint32_t p = t.P[lane];
         uint32_t tot = __shfl_sync(FULLMASK, p, N - 1);
-        if (poisoned) fail = true;
+        // A failed frame decodes nothing more (the models stay as they were), at no cost to the symbol chain: failing
+        // zeroes `range`, a zero range gives r = 0, every product is then 0 <= code and the search runs off the table
+        // again.  A symbol asked for after the data ran out (`poisoned`) fails the same way.
+        if (poisoned) range = 0;
         const uint32_t r = udiv_small(range, tot, rc_recip(tot));
-        const uint32_t codev = poisoned ? 0u : code;
+        const uint32_t codev = code;
         const uint32_t pr = p * r;
         const int s = __popc(__ballot_sync(FULLMASK, lane < N && pr <= codev));
-        if (s >= N) { range = r; fail = true; return N - 1; }
+        if (s >= N) { range = 0; fail = true; return N - 1; }
         const uint32_t below = __shfl_sync(FULLMASK, pr, (s + 31) & 31), hi = __shfl_sync(FULLMASK, pr, s);
         const uint32_t lo = s ? below : 0u;
         consume(lo, hi - lo);
@@ -224,7 +227,6 @@ struct RcCoder {
     __device__ __forceinline__ int decode_big(uint32_t *tab, uint32_t step)
     {
         const int lane = (int)lane_id();
-        if (fail) return 0;                                    // as in decode_tiny
         nsym++;
         JSP_PT0
         uint32_t lp[K];
@@ -236,13 +238,13 @@ struct RcCoder {
             base = tab[32 * K + lane];
             tot = tab[32 * K + 32];
         }
-        if (poisoned) fail = true;
+        if (poisoned) range = 0;                               // as in decode_tiny: fails below, touches nothing
         JSP_PT(0)
         const uint32_t r = udiv_small(range, tot, rc_recip(tot));
         JSP_PT(1)
-        const uint32_t codev = poisoned ? 0u : code;
+        const uint32_t codev = code;
         const uint32_t br = base * r;
-        if (codev >= tot * r) { range = r; fail = true; return 32 * K - 1; }     // value >= total: not a valid stream
+        if (codev >= tot * r) { range = 0; fail = true; return 32 * K - 1; }     // value >= total: not a valid stream
         const int L = __popc(__ballot_sync(FULLMASK, br <= codev)) - 1;          // lane 0 has base 0: L >= 0
         const uint32_t t = codev - br;                                           // meaningful in lane L only
         // in lane L the symbol's inclusive prefix exceeds t (the next lane's base is above the value), so

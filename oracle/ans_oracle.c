@@ -91,7 +91,6 @@ static inline void ea_count(entro_ans *a)
 static int ea_clr(entro *e, int cxi)                       /* :235-255 */
 {
     entro_ans *a = (entro_ans *)e;
-    if (a->rans.failed) return 0;                          /* a failed frame decodes nothing more (sp_entro.h) */
     color_ctx *dcx = &a->cntab[cxi];
     dec_receiver rcv; int c;
     if (cctx_decode(dcx, rans_get(&a->rans), &rcv, a->f0)) {
@@ -110,7 +109,6 @@ static int ea_clr(entro *e, int cxi)                       /* :235-255 */
 static int ea_bool(entro *e)                               /* :259-269 */
 {
     entro_ans *a = (entro_ans *)e;
-    if (a->rans.failed) return 0;
     const int f = rans_get(&a->rans);
     const int flag = f >= (ANS_PROB_SCALE >> 1);
     rans_advance(&a->rans, flag ? ANS_PROB_SCALE >> 1 : 0, ANS_PROB_SCALE >> 1);
@@ -120,7 +118,6 @@ static int ea_bool(entro *e)                               /* :259-269 */
 static int ea_f(entro_ans *a, fixed_ctx *t)                /* decodeF, :271-280 */
 {
     dec_receiver rcv;
-    if (a->rans.failed) return 0;
     fx_decode(t, rans_get(&a->rans), &rcv);
     rans_advance(&a->rans, rcv.cumFreq, rcv.freq);
     ea_count(a);

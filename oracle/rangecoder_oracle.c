@@ -51,16 +51,19 @@ static void rc_begin(rangecoder *rc, const uint8_t *src, int len, int pos0)
 __thread unsigned long long g_ora_symbols = 0;
 unsigned long long ora_symbol_count(int reset) { unsigned long long v = g_ora_symbols; if (reset) g_ora_symbols = 0; return v; }
 
-static inline uint32_t rc_get_freq(rangecoder *rc, uint32_t tot)
+/* Defined behaviour: a failed frame decodes nothing more -- every later call returns 0 and leaves the models alone.
+ * Asking for a symbol after the data has run out (poisoned) is such a failure.  Calls are still counted. */
+static inline int rc_frozen(rangecoder *rc)
 {
     g_ora_symbols++;
     if (rc->poisoned) rc->failed = 1;
-    rc->range = rc->range / tot;
-    /* Only after a failed symbol (whose range stays un-normalised until the frame loop looks at failed()) can the range
-     * drop below a table total.  JavaScript would go on with code / 0 = Infinity; defined behaviour here: the value lies
-     * above every cumulative count, i.e. the symbol fails again and no table is touched. */
-    if (rc->range == 0) { rc->failed = 1; return 0xFFFFFFFFu; }
-    if (rc->poisoned) return 0;
+    return rc->failed;
+}
+
+static inline uint32_t rc_get_freq(rangecoder *rc, uint32_t tot)
+{
+    rc->range = rc->range / tot;                           /* >= 2^24 / (2^16 + step) on every path that gets here */
+    if (rc->range == 0) { rc->failed = 1; return 0xFFFFFFFFu; }   /* (unreachable: a failed symbol freezes the coder) */
     uint64_t v = rc->code / rc->range;
     return v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v;
 }
@@ -76,7 +79,7 @@ static inline void rc_decode(rangecoder *rc, uint32_t cum, uint32_t freq)
 /* RangeCoder.hx:51-80 */
 static int rc_decode_val(rangecoder *rc, uint32_t *cnt, int maxc, uint32_t step)
 {
-    if (rc->failed) return 0;                                /* defined behaviour: a failed frame decodes nothing more */
+    if (rc_frozen(rc)) return 0;
     uint32_t totfr = cnt[maxc];
     uint32_t value = rc_get_freq(rc, totfr);
     int c = 0; uint32_t cumfr = 0, cnt_c = 0;
@@ -100,7 +103,7 @@ static int rc_decode_val(rangecoder *rc, uint32_t *cnt, int maxc, uint32_t step)
 /* RangeCoder.hx:82-130: 16 group sums at [off..off+15], total at [off+16], 256 counts at [off+17..] */
 static int rc_decode_val_uni(rangecoder *rc, uint32_t *cnt, uint32_t step)
 {
-    if (rc->failed) return 0;                                /* as above */
+    if (rc_frozen(rc)) return 0;
     uint32_t totfr = cnt[16];
     uint32_t value = rc_get_freq(rc, totfr);
     int x = 0; uint32_t cumfr = 0, cnt_x = 0;

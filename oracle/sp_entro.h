@@ -26,8 +26,9 @@ struct entro {
      * end of the data, or when a symbol search ran off its table (both impossible on a valid stream) */
     int  (*failed)(entro *);
     /* not in the reference: the frame loop reports a failure of its own (colour-context index out of range, run budget
-     * spent).  Defined behaviour for every kind of failure: after the first one no further symbol of the frame is
-     * decoded -- each decode call returns 0 and leaves the models alone. */
+     * spent).  Defined behaviour: the range coder decodes nothing more after a frame's first failure of any kind (each
+     * later call returns 0 and leaves the models alone -- its arithmetic has no defined meaning from there); the rANS
+     * coder, whose 32-bit state stays well defined on garbage, goes on until the frame loop's next check. */
     void (*fail)(entro *);
 };
 
