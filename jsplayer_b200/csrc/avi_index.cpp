@@ -172,14 +172,21 @@ jsp_avi *jsp_avi_parse(const uint8_t *file, uint64_t size)
         snprintf(g_avi_err, sizeof g_avi_err, "not a RIFF AVI file");
         return nullptr;
     }
-    jsp_avi *a = new jsp_avi();
-    a->info.fps = 15.0;
-    size_t cursor = SIZE_MAX;             // collect index entries while walking ...
-    // top level: RIFF 'AVI ' followed by optional RIFF 'AVIX' extension segments (OpenDML)
-    walk(a, file, size, 0, size, 0, false, cursor);
-    cursor = 0;                           // ... and apply them now that every frame chunk is known
-    for (const jsp_avi::IdxEntry &e : a->pending) apply_index_entry(a, cursor, e.data_off, e.size, e.key);
-    a->pending.clear();
+    jsp_avi *a = nullptr;
+    try {                                 // no C++ exception may cross the C ABI
+        a = new jsp_avi();
+        a->info.fps = 15.0;
+        size_t cursor = SIZE_MAX;         // collect index entries while walking ...
+        // top level: RIFF 'AVI ' followed by optional RIFF 'AVIX' extension segments (OpenDML)
+        walk(a, file, size, 0, size, 0, false, cursor);
+        cursor = 0;                       // ... and apply them now that every frame chunk is known
+        for (const jsp_avi::IdxEntry &e : a->pending) apply_index_entry(a, cursor, e.data_off, e.size, e.key);
+        a->pending.clear();
+    } catch (...) {
+        delete a;
+        snprintf(g_avi_err, sizeof g_avi_err, "out of memory while indexing");
+        return nullptr;
+    }
     a->info.n_frames = (int32_t)a->frames.size();
     a->info.has_index = a->have_index ? 1 : 0;
     if (a->info.width <= 0 || a->info.height <= 0 || a->info.bpp == 0) {

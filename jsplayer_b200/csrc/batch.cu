@@ -14,6 +14,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <string>
 #include <thread>
 
 namespace jsp {
@@ -544,7 +546,17 @@ void jsp_batch_destroy(jsp_batch *b)
     delete b;
 }
 
+static int64_t batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_streams);
+
+// No C++ exception may cross the C ABI: a descriptor table too large for host memory is an error return, not a terminate().
 int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_streams)
+{
+    try { return batch_configure(b, sd, n_streams); }
+    catch (const std::exception &e) { set_error("jsp_batch_configure: %s", e.what()); return -1; }
+    catch (...) { set_error("jsp_batch_configure: unknown failure"); return -1; }
+}
+
+static int64_t batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_streams)
 {
     if (!b || !sd || n_streams <= 0) { set_error("jsp_batch_configure: bad arguments"); return -1; }
     if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
@@ -564,6 +576,10 @@ int64_t jsp_batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_strea
         const jsp_stream_desc &D = sd[s];
         if (D.width <= 0 || D.height <= 0 || D.n_frames < 0 || (D.n_frames > 0 && (!D.frame_off || !D.frame_len || !D.frame_key))) {
             set_error("stream %d: bad descriptor", s); return -1;
+        }
+        // AVI headers carry 32-bit sizes; block counts, tile counts and pixel indices here are sized for real pictures
+        if (D.width > 32768 || D.height > 32768 || (int64_t)D.width * D.height > ((int64_t)1 << 28)) {
+            set_error("stream %d: picture size %d x %d out of range", s, D.width, D.height); return -1;
         }
         if (D.codec != JSP_CODEC_MSVC16 && D.codec != JSP_CODEC_MSVC8 && D.codec != JSP_CODEC_SCREENPRESSOR) {
             set_error("stream %d: unknown codec %d", s, D.codec); return -1;
@@ -1109,6 +1125,7 @@ int jsp_batch_decode(const jsp_stream_desc *streams, int n_streams, int n_gpus, 
     std::vector<int> rc(n_gpus, 0);
     std::vector<std::string> errs(n_gpus);
     auto work = [&](int g) {
+      try {
         std::sort(shard[g].begin(), shard[g].end());
         std::vector<jsp_stream_desc> sd; std::vector<int32_t *> outs; std::vector<int64_t> gidx;
         for (int s : shard[g]) {
@@ -1128,6 +1145,8 @@ int jsp_batch_decode(const jsp_stream_desc *streams, int n_streams, int n_gpus, 
             }
         }
         jsp_batch_destroy(b);
+      } catch (const std::exception &e) { rc[g] = -1; errs[g] = e.what(); }
+        catch (...) { rc[g] = -1; errs[g] = "unknown failure"; }
     };
     std::vector<std::thread> th;
     for (int g = 1; g < n_gpus; g++) th.emplace_back(work, g);

@@ -105,6 +105,51 @@ def test_bad_files():
     assert 0 < a.n_frames <= 6
 
 
+def test_mutated_files_never_leave_the_buffer():
+    """Bit flips, random / extreme 32-bit fields and truncation anywhere in the file (headers, chunk sizes, both index
+    kinds): the indexer either refuses the file or returns a frame table that lies inside it."""
+    rng = np.random.default_rng(5)
+    fr = [synth.msv1_frame(True, 64, 48, s, skip_permille=100 if s else 0) for s in range(6)]
+    seeds = [avi_bytes(64, 48, 8, b"MSVC", fr, keys=[1, 0, 0, 1, 0, 0], palette=synth.random_palette(3))]
+    fr2, k2 = sp_frames()
+    plain = avi_bytes(64, 48, 24, b"SCPR", fr2, k2)
+    movi = plain.find(b"movi")
+    pos, ents = movi + 4, []
+    while plain[pos:pos + 4] == b"00dc":
+        ln = struct.unpack("<I", plain[pos + 4:pos + 8])[0]
+        ents.append((pos + 8, ln)); pos += 8 + ((ln + 1) & ~1)
+    ix = struct.pack("<HBBI4sQI", 2, 0, 1, len(ents), b"00dc", 0, 0) + b"".join(
+        struct.pack("<II", o, l | (0x80000000 if i % 3 else 0)) for i, (o, l) in enumerate(ents))
+    seeds.append(plain[:pos] + _chunk(b"ix00", ix) + plain[pos:])          # stale LIST size: also a malformed file
+    for base in seeds:
+        base = np.frombuffer(base, dtype=np.uint8)
+        accepted = 0
+        for it in range(400):
+            m = base.copy()
+            for _ in range(1 + it % 7):
+                at = int(rng.integers(0, m.size))
+                if it % 4 == 0:
+                    m[at] ^= 1 << int(rng.integers(0, 8))
+                elif it % 4 == 1:
+                    m[at:at + 4] = rng.integers(0, 256, min(4, m.size - at), dtype=np.uint8)
+                elif it % 4 == 2:
+                    v = 0xFFFFFFFF if rng.random() < 0.3 else int(rng.integers(0, 64))
+                    a4 = at & ~3
+                    if a4 + 4 <= m.size:
+                        m[a4:a4 + 4] = np.frombuffer(np.uint32(v).tobytes(), dtype=np.uint8)
+                else:
+                    m = m[: 12 + int(rng.integers(0, m.size - 12))]
+                    break
+            try:
+                a = avi.parse_avi(m)
+            except ValueError:
+                continue
+            accepted += 1
+            assert all(int(a.frame_off[i]) + int(a.frame_len[i]) <= m.size for i in range(a.n_frames))
+            a.gops(); a.spec()
+        assert accepted > 100
+
+
 def test_shard_is_a_balanced_partition():
     w = [5, 3, 8, 1, 9, 2, 7, 7]
     for n in (1, 2, 3, 8):

@@ -226,3 +226,13 @@ def test_persistent_mode_large_batch():
     for first, e in exp:
         for f in range(2):
             assert (outs[first + f] == e[f]).all(), "frame %d" % (first + f)
+
+
+def test_absurd_picture_sizes_are_refused():
+    """A corrupt AVI header can claim any 32-bit size: the batcher refuses it instead of sizing tables from it."""
+    frame = synth.msv1_frame(False, 64, 48, 1)
+    for (w, h) in ((1 << 20, 1 << 20), (40000, 16), (16, 40000), (32768, 16384)):
+        bd = BatchDecoder()
+        with pytest.raises(RuntimeError, match="out of range"):
+            bd.configure([StreamSpec(CodecType.codec_msvc16, w, h, 16, frames=[frame], keys=[1])])
+        bd.close()
