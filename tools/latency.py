@@ -47,10 +47,8 @@ for name, mk, frames, keys, codec, bpp in (("MSVideo1 RGB555 1080p", lambda: MSV
                                            ("ScreenPressor v4 1080p", lambda: ScreenPressor(w, h, 24), sp4, skeys4, O.CODEC_SCREENPRESSOR, 24)):
     for pinned in (False, True):
         dec = mk(); dec.Preinit(36)
-        timed(dec, frames, keys, w, h, pinned)                      # warm-up pass (allocations, first-touch)
-        dec.StopAndClean()
-        dec = mk(); dec.Preinit(36)
-        t = timed(dec, frames, keys, w, h, pinned)
+        timed(dec, frames, keys, w, h, pinned)                      # warm-up pass (device allocations, first-touch)
+        t = timed(dec, frames, keys, w, h, pinned)                  # the same stream again, from its key frame
         dec.StopAndClean()
         print("%-24s %-8s key frame %7.2f ms   inter frames median %6.2f ms  max %6.2f ms" % (name, "pinned" if pinned else "pageable", t[0], np.median(t[1:]), t[1:].max()))
     print("%-24s CPU oracle, 1 thread: %6.2f ms per frame (stream average)" % (name, oracle_ms(codec, w, h, bpp, frames, keys)))
