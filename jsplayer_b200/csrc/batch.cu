@@ -275,6 +275,7 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             J.prev = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
             J.status = b->d_status + f;
             J.symbols = b->d_sp_symbols ? b->d_sp_symbols + f : nullptr;
+            J.done = b->d_done ? b->d_done + f : nullptr;
             const size_t slot = R.sp_seg > 0 ? (size_t)(R.sp_seg % H.n_slots) : 0;
             J.state = b->d_sp_state + H.state_off + slot * H.state_stride;
             J.bts = b->d_sp_bts + H.bts_off + slot * H.bts_stride;
@@ -540,6 +541,7 @@ void jsp_batch_destroy(jsp_batch *b)
                     b->d_disp, b->d_disp_jobs, b->d_sp_symbols};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (b->h_status) cudaFreeHost(b->h_status);
+    if (b->h_done) cudaFreeHost(b->h_done);
     if (b->st_compute) cudaStreamDestroy(b->st_compute);
     if (b->st_in) cudaStreamDestroy(b->st_in);
     if (b->st_out) cudaStreamDestroy(b->st_out);
@@ -695,6 +697,14 @@ static int64_t batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_st
             if (!grow(b->d_sp_rows, b->sp_rows_cap, rows_cur)) return -1;
             if (!grow(b->d_sp_bts, b->sp_bts_cap, bts_cur)) return -1;
             if (!grow(b->d_sp_symbols, b->sp_symbols_cap, (size_t)nf, true)) return -1;
+            if ((size_t)nf > b->done_cap) {
+                if (b->h_done) cudaFreeHost(b->h_done);
+                b->h_done = b->d_done = nullptr; b->done_cap = 0;
+                if (!JSP_CUDA(cudaHostAlloc((void **)&b->h_done, (size_t)nf * 4, cudaHostAllocMapped))) return -1;
+                if (!JSP_CUDA(cudaHostGetDevicePointer((void **)&b->d_done, b->h_done, 0))) return -1;
+                b->done_cap = (size_t)nf;
+            }
+            memset(b->h_done, 0, (size_t)nf * 4);
             if (!keep || fresh_alloc) {
                 // generation tags of all rows to 0, generations start at 1: every row reads as "all ones"
                 if (!JSP_CUDA(cudaMemsetAsync(b->d_sp_rows, 0, rows_cur, b->st_compute))) return -1;
@@ -952,9 +962,19 @@ static int decode_host_streamed(jsp_batch *b, int32_t *const *out_frames, uint8_
     if (!JSP_CUDA(cudaEventRecord(ev0, b->st_compute)) || !JSP_CUDA(cudaStreamWaitEvent(b->st_out, ev0, 0))) return -1;
     std::vector<uint8_t> sent(b->frames.size(), 0);
     const int reruns = b->rerun_count;
+    // ScreenPressor pictures are not taken per launch but per FRAME: a launch lasts as long as its longest frame, and the
+    // kernel raises a flag in mapped memory when a picture is complete (sp_signal_done) -- the host polls the flags and
+    // copies pictures out while the launch is still running
+    std::vector<int64_t> polled;
+    if (b->h_done) memset(b->h_done, 0, b->frames.size() * 4);
     const bool ok = run_plan_with(b, P, b->st_compute, nullptr, nullptr, [&](int k) {
         const std::vector<int64_t> &fin = P.finished[(size_t)k];
         if (fin.empty()) return true;
+        const int kc = P.launches[(size_t)k].kclass;
+        if (b->h_done && (kc == JSP_K_SP_ENTROPY_RC || kc == JSP_K_SP_ENTROPY_ANS || kc == JSP_K_SP_ENTROPY_MIXED)) {
+            polled.insert(polled.end(), fin.begin(), fin.end());
+            return true;
+        }
         if (!JSP_CUDA(cudaEventRecord(b->ev_sync[(size_t)k], b->st_compute))) return false;
         if (!JSP_CUDA(cudaStreamWaitEvent(b->st_out, b->ev_sync[(size_t)k], 0))) return false;
         for (int64_t f : fin) {
@@ -965,6 +985,27 @@ static int decode_host_streamed(jsp_batch *b, int32_t *const *out_frames, uint8_
     });
     if (!ok) return -1;
     if (!run_status(b, b->st_compute)) return -1;
+    {
+        const volatile uint32_t *done = b->h_done;
+        size_t left = polled.size();
+        while (left > 0) {
+            size_t kept = 0;
+            for (size_t i = 0; i < left; i++) {
+                const int64_t f = polled[i];
+                if (done[f]) {
+                    if (!download_range(b, f, f + 1, out_frames, b->st_out)) return -1;
+                    sent[(size_t)f] = 1;
+                } else polled[kept++] = f;
+            }
+            if (kept == left) {
+                // nothing new: stop polling once the compute stream has drained (every flag is up by then -- or the
+                // launch failed, which the calls below report)
+                if (cudaStreamQuery(b->st_compute) != cudaErrorNotReady) break;
+                std::this_thread::yield();
+            }
+            left = kept;
+        }
+    }
     if (jsp_batch_results(b, flags)) return -1;                              // syncs the compute stream
     if (b->rerun_count != reruns) std::fill(sent.begin(), sent.end(), 0);    // a demoted key frame: everything was decoded again
     for (size_t f = 0; f < sent.size(); f++)
@@ -976,7 +1017,9 @@ int jsp_batch_decode_host(jsp_batch *b, int32_t *const *out_frames, uint8_t *fla
 {
     if (!b) return -1;
     if (b->chunks.empty() || !out_frames) {
-        if (out_frames && b->whole.launches.size() > 1 && outputs_pinned(b, out_frames)) return decode_host_streamed(b, out_frames, flags);
+        bool sp_launch = false;                  // a ScreenPressor launch streams its pictures out frame by frame
+        for (const Launch &L : b->whole.launches) sp_launch = sp_launch || L.kclass == JSP_K_SP_ENTROPY_RC || L.kclass == JSP_K_SP_ENTROPY_ANS || L.kclass == JSP_K_SP_ENTROPY_MIXED;
+        if (out_frames && (b->whole.launches.size() > 1 || (sp_launch && b->h_done)) && outputs_pinned(b, out_frames)) return decode_host_streamed(b, out_frames, flags);
         // single launches and pageable destinations: upload, decode, download back to back
         if (jsp_batch_upload(b)) return -1;
         if (jsp_batch_run(b)) return -1;

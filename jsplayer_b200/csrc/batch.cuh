@@ -147,6 +147,7 @@ struct jsp_batch {
     jsp::DisplayJob *d_disp_jobs = nullptr; size_t disp_jobs_cap = 0;
 
     uint32_t *h_status = nullptr; size_t h_status_cap = 0;   // pinned
+    uint32_t *h_done = nullptr, *d_done = nullptr; size_t done_cap = 0;   // mapped pinned: per-frame completion flags of ScreenPressor frames
 
     const int32_t *ext_prev = nullptr;   // previous picture held outside the batch (per-stream drop-in)
     int ext_has_prev = 0;                // codec's prevFrame was non-null before the batch's first frame

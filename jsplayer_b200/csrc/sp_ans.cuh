@@ -1023,6 +1023,7 @@ __device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm, uint32
         for (int i = lane; i < (int)(sizeof(AnsSmall) / 16); i += 32) g[i] = s[i];
     }
     if (lane == 0) { st->gen = ec.gen; if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
+    sp_signal_done(J);
 #ifdef JSP_PROFILE_SECTIONS
     if (lane == 0) for (int k = 0; k < 16; k++) atomicAdd(&g_ans_prof[k], (unsigned long long)ec.aprof[k]);
 #endif

@@ -33,6 +33,7 @@ struct SpJob {
     uint32_t insign_blocks;   // nbx * ceil(insignificant_lines / 16) (ScreenPressor.hx:86-89)
     uint32_t pad;
     uint32_t      *symbols;   // entropy-coded symbols this frame decoded (reporting: symbols / s), may be null
+    uint32_t      *done;      // set to 1 (host-mapped memory) when the picture is complete and visible system-wide; may be null
 };
 
 constexpr uint32_t FULLMASK = 0xffffffffu;
@@ -113,6 +114,16 @@ __device__ __forceinline__ uint32_t sp_segment_ring(int32_t *dst, uint32_t *ring
     const uint32_t last = ptype > 1 ? __shfl_sync(FULLMASK, v, (m - 1) & 31) : v;
     __syncwarp();
     return last;
+}
+
+// The host may copy a picture out while the launch that produced it is still running (other warps of the launch decode
+// longer frames): every lane makes its stores visible system-wide, then one lane raises the frame's flag in mapped memory.
+__device__ __forceinline__ void sp_signal_done(const SpJob &J)
+{
+    if (!J.done) return;
+    __threadfence_system();
+    __syncwarp();
+    if (lane_id() == 0) *reinterpret_cast<volatile uint32_t *>(J.done) = 1u;
 }
 
 // A frame whose entropy decode failed shows the previous picture (a P frame returns the retained buffer) or

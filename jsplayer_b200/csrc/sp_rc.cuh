@@ -425,6 +425,7 @@ __device__ __forceinline__ void sp_rc_run(const SpJob &J, RcShared &shm, uint32_
         for (int i = lane; i < (int)(sizeof(RcSmall) / 16); i += 32) g[i] = s[i];
     }
     if (lane == 0) { st->gen = ec.gen; if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
+    sp_signal_done(J);
 #ifdef JSP_PROFILE_SECTIONS
     if (lane == 0) for (int k = 0; k < 6; k++) atomicAdd(&g_rc_prof[k], (unsigned long long)ec.prof[k]);
 #endif

@@ -98,3 +98,19 @@ def test_demoted_key_frame_is_downloaded_again():
     for i in range(6):
         assert (outs[i] == (exp_a if i < 3 else exp_b)[i % 3]).all(), i
         assert not (flags[i] & _lib.JSP_FRAME_ERROR)
+
+
+@pytest.mark.parametrize("version", [2, 4])
+def test_single_launch_pictures_leave_while_the_launch_runs(version):
+    """Key frames only: one launch, whose pictures the host copies out frame by frame as the kernel flags them complete
+    (short frames long before the longest one ends).  Repeated, to give an ordering bug a chance to show."""
+    specs, exp = [], []
+    for s, (w, h) in enumerate([(320, 240), (64, 48), (640, 360), (33, 17), (1280, 720), (100, 60)]):
+        frames, keys, pics = synth.sp_stream(w, h, 3, seed=50 + s, version=version, gop=1, change_permille=60)
+        specs.append(StreamSpec(SP, w, h, 24, frames=frames, keys=keys))
+        exp += pics
+    for rep in range(3):
+        outs, flags = decode_pinned(specs)
+        for i, e in enumerate(exp):
+            assert (outs[i] == e).all(), (rep, i)
+            assert not (flags[i] & _lib.JSP_FRAME_ERROR)
