@@ -966,7 +966,11 @@ static int decode_host_streamed(jsp_batch *b, int32_t *const *out_frames, uint8_
     // kernel raises a flag in mapped memory when a picture is complete (sp_signal_done) -- the host polls the flags and
     // copies pictures out while the launch is still running
     std::vector<int64_t> polled;
-    if (b->h_done) memset(b->h_done, 0, b->frames.size() * 4);
+    if (b->h_done) {
+        // flags still being raised by an earlier, asynchronous jsp_batch_run must not be mistaken for this run's
+        if (!JSP_CUDA(cudaStreamSynchronize(b->st_compute))) return -1;
+        memset(b->h_done, 0, b->frames.size() * 4);
+    }
     const bool ok = run_plan_with(b, P, b->st_compute, nullptr, nullptr, [&](int k) {
         const std::vector<int64_t> &fin = P.finished[(size_t)k];
         if (fin.empty()) return true;
