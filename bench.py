@@ -193,7 +193,8 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (arrival time, text)
+        self.t_mark = None
 
     def start(self):
         try:
@@ -207,12 +208,18 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def mark(self):
+        """The timed region starts now: only samples that arrive from here on count."""
+        self.t_mark = time.perf_counter()
+
+    def count(self):
+        return sum(1 for t, _ in self.lines if self.t_mark is None or t >= self.t_mark)
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -220,7 +227,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for t, ln in self.lines:
+            if self.t_mark is not None and t < self.t_mark:
+                continue
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
@@ -361,11 +370,17 @@ def measure(wl, args, rank, local_rank, world, dist, torch, with_e2e=True, with_
     # ---- device-resident timing ----
     flush = st["in_bytes"] + st["out_bytes"] < (512 << 20)          # small working sets: flush the 126 MB L2 between steps
     sampler = ClockSampler(local_rank)
+    sampler.start()                      # nvidia-smi needs up to a second to produce its first line (longer with 8 ranks)
     barrier()
     bd.time_runs(warmup=warmup, iters=1, flush_l2=flush)
     barrier()
-    sampler.start()
+    sampler.mark()
     ms_total, kms, kcnt = bd.time_runs(warmup=0, iters=args.steps, flush_l2=flush)
+    # the timed region of a fast workload is shorter than nvidia-smi's 100 ms period: keep the same load running
+    # (untimed) until two samples have been taken under it
+    t_wait = time.perf_counter()
+    while sampler.proc and sampler.count() < 2 and time.perf_counter() - t_wait < 4.0:
+        bd.time_runs(warmup=0, iters=args.steps, flush_l2=flush)
     barrier()
     clocks = sampler.stop()
     n_symbols = bd.symbols()
