@@ -379,7 +379,7 @@ def measure(wl, args, rank, local_rank, world, dist, torch, with_e2e=True, with_
     # the timed region of a fast workload is shorter than nvidia-smi's 100 ms period: keep the same load running
     # (untimed) until two samples have been taken under it
     t_wait = time.perf_counter()
-    while sampler.proc and sampler.count() < 2 and time.perf_counter() - t_wait < 4.0:
+    while sampler.proc and sampler.count() < 2 and time.perf_counter() - t_wait < 8.0:
         bd.time_runs(warmup=0, iters=args.steps, flush_l2=flush)
     barrier()
     clocks = sampler.stop()
