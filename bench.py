@@ -63,7 +63,7 @@ class C2(Workload):
             self.desc = "MSVideo1 RGB555 1920x1080 key frames, %d/%d/%d%% 1/2/8-colour blocks (sweep), independent streams" % self.MIX
 
     def frames(self, rank, n=None, threads=16):
-        from jsplayer_b200 import synth
+        import synth
         synth.load()
         n = self.n if n is None else n
 
@@ -91,7 +91,7 @@ class SPWorkload(Workload):
         self.name, self.metric, self.desc = name, metric, desc
 
     def specs(self, rank, n=None):
-        from jsplayer_b200 import StreamSpec, CodecType, synth
+        from jsplayer_b200 import StreamSpec, CodecType
         synth.load()
         n = self.n if n is None else n
         k = min(self.distinct, n)
@@ -127,8 +127,8 @@ class C5(Workload):
 
     def specs(self, rank, n=None):
         import tempfile
-        from jsplayer_b200 import synth, avi
-        from jsplayer_b200.synth.avi import write_avi
+        from jsplayer_b200 import avi
+        from synth.avi import write_avi
         synth.load()
         n = self.n if n is None else n
         tmp = tempfile.mkdtemp(prefix="jsp_c5_")

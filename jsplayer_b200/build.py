@@ -1,7 +1,8 @@
-"""In-tree build of the native libraries (sm_100a only).
+"""In-tree build of the product library (sm_100a only).
 
-  libjsplayer_cuda.so   the product: CUDA kernels + C ABI (include/jsplayer_cuda.h)
-  libjsplayer_synth.so  synthetic bitstream encoders (test/bench input generator, plain C)
+  libjsplayer_cuda.so   CUDA kernels + C ABI (include/jsplayer_cuda.h)
+
+(The synthetic bitstream encoders live in the top-level synth/ package and build themselves, as does the CPU checker.)
 
 nvcc cross-compiles without a GPU, so this runs on the CPU-only build container too.
 """
@@ -13,9 +14,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SYNTH = os.path.join(HERE, "synth")
 CUDA_LIB = os.path.join(HERE, "libjsplayer_cuda.so")
-SYNTH_LIB = os.path.join(HERE, "libjsplayer_synth.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -90,28 +89,8 @@ def build_cuda(force=False, verbose=False):
     return CUDA_LIB
 
 
-def build_synth(force=False):
-    srcs = _sources(SYNTH, (".c",))
-    deps = srcs + _sources(SYNTH, (".h",))
-    if not force and not _stale(SYNTH_LIB, deps):
-        return SYNTH_LIB
-    with _Lock(SYNTH_LIB):
-        if not force and not _stale(SYNTH_LIB, deps):
-            return SYNTH_LIB
-        cc = os.environ.get("CC", "gcc")
-        tmp = SYNTH_LIB + ".tmp%d" % os.getpid()
-        cmd = [cc, "-O2", "-std=gnu11", "-fPIC", "-shared", "-Wall", "-o", tmp] + srcs + ["-lm"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("gcc failed building libjsplayer_synth.so")
-        os.replace(tmp, SYNTH_LIB)
-        _stamp(SYNTH_LIB, deps)
-    return SYNTH_LIB
-
-
 def build_all(force=False, verbose=False):
-    return build_cuda(force, verbose), build_synth(force)
+    return (build_cuda(force, verbose),)
 
 
 if __name__ == "__main__":

@@ -1,7 +1,7 @@
 /*
  * ans_oracle.c -- CPU restatement of EntroCoderANS (reference src/EntroCoders.hx:182-313) with the byte-wise rANS
  * decoder (src/ANS.hx:5-49).  The adaptive models of ANS.hx (:54-872) are restated in
- * jsplayer_b200/synth/ans_models.{h,c} -- next to the synthetic rANS encoder, which has to run the very same models
+ * synth/ans_models.{h,c} -- next to the synthetic rANS encoder, which has to run the very same models
  *  -- and are compiled into liboracle.so from there (oracle/Makefile).  The dependency points
  * from the oracle to the encoder's models, never from the product to the oracle.
  * TEST INFRASTRUCTURE ONLY.
@@ -11,7 +11,7 @@
  * asking for a symbol after the reader has run past the end, or a renormalisation that cannot terminate, is
  * reported through failed() -- no valid stream does either.
  */
-#include "../jsplayer_b200/synth/ans_models.h"
+#include "../synth/ans_models.h"
 #include "sp_entro.h"
 #include <stdlib.h>
 

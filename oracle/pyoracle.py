@@ -38,7 +38,7 @@ def _digest(srcs):
 def build(force=False):
     """Builds liboracle.so when its sources changed (content hash, not mtimes: the built file travels with a snapshot of
     the repo); one builder at a time (torchrun ranks)."""
-    models = os.path.join(os.path.dirname(HERE), "jsplayer_b200", "synth")
+    models = os.path.join(os.path.dirname(HERE), "synth")
     srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
     srcs += [os.path.join(models, f) for f in ("ans_models.c", "ans_models.h")]
     stamp = LIB_PATH + ".srchash"

@@ -9,8 +9,13 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(HERE), "libjsplayer_synth.so")
+LIB_PATH = os.path.join(HERE, "libjsplayer_synth.so")
 _lib = None
+
+
+def build(force=False):
+    from . import _build as _b
+    return _b.build(force)
 
 
 class Msv1Recipe(C.Structure):
@@ -21,9 +26,7 @@ class Msv1Recipe(C.Structure):
 def load():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            from .. import build
-            build.build_synth()
+        build()
         lib = C.CDLL(LIB_PATH)
         lib.jsp_synth_msv1_frame.restype = C.c_size_t
         lib.jsp_synth_msv1_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(Msv1Recipe), C.c_void_p, C.c_size_t]

@@ -19,6 +19,8 @@ def _native_libs():
     from jsplayer_b200 import build
     from oracle import pyoracle
     build.build_all()
+    import synth
+    synth.build()
     pyoracle.build()
 
 

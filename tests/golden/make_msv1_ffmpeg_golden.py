@@ -18,7 +18,7 @@ import cv2
 import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
-from jsplayer_b200 import synth                      # noqa: E402
+import synth                      # noqa: E402
 from jsplayer_b200.synth.avi import write_avi        # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))

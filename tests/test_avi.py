@@ -6,8 +6,9 @@ import struct
 import numpy as np
 import pytest
 
-from jsplayer_b200 import synth, avi, CodecType
-from jsplayer_b200.synth.avi import avi_bytes, _chunk, _list
+from jsplayer_b200 import avi, CodecType
+import synth
+from synth.avi import avi_bytes, _chunk, _list
 
 
 def parse(b):

@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from conftest import ROOT
-from jsplayer_b200 import _lib, synth
+from jsplayer_b200 import _lib
+import synth
 import jsplayer_b200 as J
 from oracle import pyoracle as O
 

@@ -3,7 +3,8 @@ their real picture sizes, with fewer streams where the config is about stream co
 import numpy as np
 import pytest
 
-from jsplayer_b200 import synth, BatchDecoder, StreamSpec, CodecType, _lib
+from jsplayer_b200 import BatchDecoder, StreamSpec, CodecType, _lib
+import synth
 from oracle import pyoracle as O
 
 pytestmark = pytest.mark.gpu

@@ -4,8 +4,9 @@ each file as one stream."""
 import numpy as np
 import pytest
 
-from jsplayer_b200 import synth, avi, BatchDecoder, _lib
-from jsplayer_b200.synth.avi import write_avi
+from jsplayer_b200 import avi, BatchDecoder, _lib
+import synth
+from synth.avi import write_avi
 from oracle import pyoracle as O
 
 pytestmark = pytest.mark.gpu

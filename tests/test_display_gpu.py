@@ -4,7 +4,8 @@ src/Manager.hx:363-381, with the render-time flip of src/Main.hx:946) and the ke
 import numpy as np
 import pytest
 
-from jsplayer_b200 import synth, BatchDecoder, StreamSpec, CodecType, _lib
+from jsplayer_b200 import BatchDecoder, StreamSpec, CodecType, _lib
+import synth
 from oracle import pyoracle as O
 
 pytestmark = pytest.mark.gpu

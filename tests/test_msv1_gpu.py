@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN_MSV1, load_golden
-from jsplayer_b200 import synth, BatchDecoder, StreamSpec, MSVideo1_16bit, MSVideo1_8bit, CodecType, DecoderState
+from jsplayer_b200 import BatchDecoder, StreamSpec, MSVideo1_16bit, MSVideo1_8bit, CodecType, DecoderState
+import synth
 from jsplayer_b200 import _lib
 from oracle import pyoracle as O
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN_MSV1, load_golden
-from jsplayer_b200 import synth
+import synth
 from oracle import pyoracle as O
 
 

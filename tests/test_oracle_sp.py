@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from jsplayer_b200 import synth
+import synth
 from oracle import pyoracle as O
 
 

@@ -3,7 +3,8 @@ pictures, `changed`, `significant_changes` and error status."""
 import numpy as np
 import pytest
 
-from jsplayer_b200 import synth, BatchDecoder, StreamSpec, ScreenPressor, CodecType, DecoderState, _lib
+from jsplayer_b200 import BatchDecoder, StreamSpec, ScreenPressor, CodecType, DecoderState, _lib
+import synth
 from oracle import pyoracle as O
 
 pytestmark = pytest.mark.gpu

@@ -4,7 +4,8 @@ to the back-to-back path (pageable destinations) and to the CPU oracle."""
 import numpy as np
 import pytest
 
-from jsplayer_b200 import synth, BatchDecoder, StreamSpec, CodecType, _lib
+from jsplayer_b200 import BatchDecoder, StreamSpec, CodecType, _lib
+import synth
 from oracle import pyoracle as O
 
 pytestmark = pytest.mark.gpu

@@ -5,7 +5,8 @@ worker at one frame per 1 ms timer tick (Manager.hx:139-141); this shows what a 
 import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from jsplayer_b200 import synth, MSVideo1_16bit, ScreenPressor, DecoderState
+from jsplayer_b200 import MSVideo1_16bit, ScreenPressor, DecoderState
+import synth
 from jsplayer_b200.batch import PinnedBuffer
 from oracle import pyoracle as O
 

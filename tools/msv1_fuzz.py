@@ -3,7 +3,8 @@ streams (RGB555 and 8-bit, odd sizes, multi-tile frames); every frame must come 
 oracle has it (the block area of the picture, changed / error flags).  Usage (GPU box): python tools/msv1_fuzz.py [campaign]."""
 import numpy as np, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from jsplayer_b200 import synth, BatchDecoder, StreamSpec, CodecType, _lib
+from jsplayer_b200 import BatchDecoder, StreamSpec, CodecType, _lib
+import synth
 from oracle import pyoracle as O
 SEED = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 nbad = 0

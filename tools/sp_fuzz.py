@@ -6,7 +6,8 @@ Round 1 found with it: unreported late failures and JavaScript-double arithmetic
 a stale tile column and the out-of-picture predictor chain in the kernels."""
 import numpy as np, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from jsplayer_b200 import synth, BatchDecoder, StreamSpec, CodecType, _lib
+from jsplayer_b200 import BatchDecoder, StreamSpec, CodecType, _lib
+import synth
 from oracle import pyoracle as O
 SP = CodecType.codec_screenpressor
 nbad = 0

@@ -3,7 +3,8 @@ tools/sp_section_profile.py).  Workload: bench.py's C4 content (1920x1080, 1 I +
 frame), 16 streams."""
 import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from jsplayer_b200 import synth, BatchDecoder, StreamSpec, CodecType, _lib
+from jsplayer_b200 import BatchDecoder, StreamSpec, CodecType, _lib
+import synth
 lib = _lib.load()
 if not hasattr(lib, "jsp_debug_spp_profile"):
     raise SystemExit("build the library with section timers first:\n"

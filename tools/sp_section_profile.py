@@ -6,7 +6,8 @@ coders.  Results of round 1: profiles/r01_sp_section_profile.txt, discussion in 
 """
 import ctypes as C, numpy as np, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from jsplayer_b200 import synth, BatchDecoder, StreamSpec, CodecType, _lib
+from jsplayer_b200 import BatchDecoder, StreamSpec, CodecType, _lib
+import synth
 lib = _lib.load()
 if not hasattr(lib, "jsp_debug_sp_profile"):
     raise SystemExit("build the library with section timers first:\n"
