@@ -43,17 +43,18 @@ int main(int argc, char **argv)
     jsp_destroy(probe);
 
     /* one descriptor per keyframe-delimited segment: the unit of sharding over GPUs (no exchange step exists) */
-    jsp_stream_desc *sd = (jsp_stream_desc *)calloc((size_t)n + 1, sizeof *sd);
-    int n_seg = 0;
-    for (int i = 0; i < n; i++) {
-        if (i == 0 || key[i]) {
-            jsp_stream_desc *d = &sd[n_seg++];
-            d->codec = info.codec; d->width = info.width; d->height = info.height; d->bpp = info.bpp;
-            d->palette = pal_bytes > 0 ? palette : NULL; d->palette_bytes = pal_bytes > 1024 ? 1024 : pal_bytes;
-            d->bytes = file; d->frame_off = off + i; d->frame_len = len + i; d->frame_key = key + i;
-            d->n_frames = 0;
-        }
-        sd[n_seg - 1].n_frames++;
+    int32_t *seg_first = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n + 1)), *seg_ver = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n + 1));
+    int n_seg = jsp_segment_stream(info.codec, file, off, len, key, n, seg_first, seg_ver);
+    if (n_seg < 0) { fprintf(stderr, "segmenting failed\n"); return 1; }
+    jsp_stream_desc *sd = (jsp_stream_desc *)calloc((size_t)n_seg + 1, sizeof *sd);
+    for (int k = 0; k < n_seg; k++) {
+        const int i = seg_first[k];
+        jsp_stream_desc *d = &sd[k];
+        d->codec = info.codec; d->width = info.width; d->height = info.height; d->bpp = info.bpp;
+        d->palette = pal_bytes > 0 ? palette : NULL; d->palette_bytes = pal_bytes > 1024 ? 1024 : pal_bytes;
+        d->bytes = file; d->frame_off = off + i; d->frame_len = len + i; d->frame_key = key + i;
+        d->n_frames = (k + 1 < n_seg ? seg_first[k + 1] : n) - i;
+        d->sp_version = seg_ver[k];          /* ScreenPressor keeps its entropy coder across key frames */
     }
     size_t npix = (size_t)info.width * info.height;
     int32_t *pictures = (int32_t *)jsp_host_alloc(npix * 4 * (size_t)n);

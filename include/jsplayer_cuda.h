@@ -71,6 +71,11 @@ typedef struct {
     const uint64_t *frame_off;   /* n_frames offsets into bytes */
     const uint32_t *frame_len;   /* n_frames lengths */
     const uint8_t  *frame_key;   /* n_frames: 1 = key frame (DecompressI), 0 = DecompressP (Manager.hx:505-512) */
+    int32_t sp_version;          /* ScreenPressor segments cut out of a longer stream: the stream's coder version (2, 3, 4)
+                                    as jsp_segment_stream() reports it, 0 = none yet.  The reference creates its entropy
+                                    coder at the first coded key frame and keeps it (ScreenPressor.hx:160-162); a segment
+                                    that starts with a flat key frame needs to know it.  0 for whole streams. */
+    int32_t reserved;            /* 0 */
 } jsp_stream_desc;
 
 typedef struct jsp_batch jsp_batch;
@@ -159,6 +164,12 @@ JSP_API int         jsp_avi_get_palette(const jsp_avi *a, uint8_t *out, int cap)
  * entry covers the frame (the caller then asks jsp_is_key_frame, DataLoaderAVIIndexed.hx:182). Returns n_frames. */
 JSP_API int         jsp_avi_frame_table(const jsp_avi *a, uint64_t *off, uint32_t *len, uint8_t *key, uint8_t *key_known);
 JSP_API const char *jsp_avi_last_error(void);
+
+/* Frame table -> keyframe-delimited segments (GOPs), the unit of multi-GPU sharding and of seeking (Manager.hx:244-249).
+ * seg_first[k] = first frame of segment k (capacity n_frames), seg_sp_version[k] (may be NULL) = the value to put into
+ * jsp_stream_desc.sp_version for that segment.  Returns the number of segments. */
+JSP_API int jsp_segment_stream(int32_t codec, const uint8_t *bytes, const uint64_t *frame_off, const uint32_t *frame_len,
+                               const uint8_t *frame_key, int32_t n_frames, int32_t *seg_first, int32_t *seg_sp_version);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ class StreamDescC(C.Structure):
     _fields_ = [("codec", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("bpp", C.c_int32),
                 ("palette", C.c_void_p), ("palette_bytes", C.c_int32), ("n_frames", C.c_int32),
                 ("bytes", C.c_void_p), ("frame_off", C.c_void_p), ("frame_len", C.c_void_p),
-                ("frame_key", C.c_void_p)]
+                ("frame_key", C.c_void_p), ("sp_version", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/jsplayer_cuda.h declares: name -> (restype, argtypes)
@@ -68,6 +68,7 @@ PROTOTYPES = {
     "jsp_avi_get_palette": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "jsp_avi_frame_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jsp_avi_last_error": (C.c_char_p, []),
+    "jsp_segment_stream": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "jsp_batch_decode": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -42,19 +42,35 @@ class AviStream:
         o, n = int(self.frame_off[i]), int(self.frame_len[i])
         return self.data[o:o + n]
 
-    def spec(self, lo=0, hi=None):
+    def spec(self, lo=0, hi=None, sp_version=0):
         """StreamSpec for frames [lo, hi) -- no copy: the descriptor points into the file buffer."""
         hi = self.n_frames if hi is None else hi
         return StreamSpec(self.codec, self.width, self.height, self.bpp, bytes_buf=self.data,
                           frame_off=self.frame_off[lo:hi].copy(), frame_len=self.frame_len[lo:hi].copy(),
-                          keys=self.keys[lo:hi].copy(), palette=self.palette)
+                          keys=self.keys[lo:hi].copy(), palette=self.palette, sp_version=sp_version)
+
+    def segments(self):
+        """[(lo, hi, sp_version)] keyframe-delimited segments (jsp_segment_stream of the C ABI); frames before the first
+        key frame form a segment of their own.  sp_version carries the one piece of state ScreenPressor keeps across key
+        frames (its entropy coder, ScreenPressor.hx:160-162) into segments cut out of the stream."""
+        n = self.n_frames
+        if n == 0:
+            return []
+        first = np.zeros(n, dtype=np.int32)
+        ver = np.zeros(n, dtype=np.int32)
+        off = np.ascontiguousarray(self.frame_off, dtype=np.uint64)
+        ln = np.ascontiguousarray(self.frame_len, dtype=np.uint32)
+        keys = np.ascontiguousarray(self.keys, dtype=np.uint8)
+        k = _lib.load().jsp_segment_stream(int(self.codec), self.data.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                                           keys.ctypes.data, n, first.ctypes.data, ver.ctypes.data)
+        if k < 0:
+            raise ValueError("jsp_segment_stream failed")
+        lo = [int(v) for v in first[:k]]
+        return [(a, b, int(v)) for a, b, v in zip(lo, lo[1:] + [n], ver[:k])]
 
     def gops(self):
-        """[(lo, hi)] keyframe-delimited segments; frames before the first key frame form a segment of their own."""
-        starts = [i for i in range(self.n_frames) if self.keys[i]]
-        if not starts or starts[0] != 0:
-            starts = [0] + starts
-        return [(s, e) for s, e in zip(starts, starts[1:] + [self.n_frames]) if e > s]
+        """[(lo, hi)] of segments()."""
+        return [(lo, hi) for lo, hi, _ in self.segments()]
 
 
 def parse_avi(data, path=None, pin=None) -> AviStream:
@@ -105,8 +121,8 @@ def gop_specs(streams: Sequence[AviStream]):
     """One StreamSpec per keyframe-delimited segment of every file, plus (file, lo, hi) for each."""
     specs, where = [], []
     for fi, st in enumerate(streams):
-        for lo, hi in st.gops():
-            specs.append(st.spec(lo, hi)); where.append((fi, lo, hi))
+        for lo, hi, ver in st.segments():
+            specs.append(st.spec(lo, hi, ver)); where.append((fi, lo, hi))
     return specs, where
 
 

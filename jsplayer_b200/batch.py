@@ -25,6 +25,7 @@ class StreamSpec:
     frame_len: Optional[np.ndarray] = None
     keys: Optional[Sequence[int]] = None          # 1 = key frame; default: frame 0 only
     palette: Optional[bytes] = None
+    sp_version: int = 0                           # jsp_stream_desc.sp_version: a segment cut out of a longer ScreenPressor stream
 
     @property
     def n_frames(self):
@@ -134,6 +135,7 @@ class BatchDecoder:
             d.n_frames = len(ln)
             d.bytes = buf.ctypes.data if buf.size else None
             d.frame_off, d.frame_len, d.frame_key = off.ctypes.data, ln.ctypes.data, keys.ctypes.data
+            d.sp_version = int(sp.sp_version)
         self._keep = keep + [descs]
         self.n_frames = int(self._check(self._lib.jsp_batch_configure(self._h, descs, len(self.specs)), "jsp_batch_configure"))
         return self.n_frames

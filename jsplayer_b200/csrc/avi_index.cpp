@@ -55,19 +55,20 @@ void add_frame(jsp_avi *a, uint64_t data_off, uint32_t len)
     a->frames.push_back(Frame{data_off, len, 0, 0});
 }
 
-// marks frame at file offset `data_off` (chunk payload) with the index's key flag
+// marks frame at file offset `data_off` (chunk payload) with the index's key flag.  Frames are collected by one forward
+// walk of the file, so their offsets ascend: a binary search per entry (an index with N bogus entries over M frames
+// costs N log M, not N * M -- untrusted input).
 void apply_index_entry(jsp_avi *a, size_t &cursor, uint64_t data_off, uint32_t size, bool key)
 {
     if (cursor == SIZE_MAX) { a->pending.push_back({data_off, size, key}); return; }
-    // index entries come in file order, as do frames: resume the search at the cursor
-    for (size_t k = 0; k < a->frames.size(); k++) {
-        const size_t i = (cursor + k) % a->frames.size();
-        if (a->frames[i].off == data_off) {
-            a->frames[i].key = key ? 1 : 0; a->frames[i].key_known = 1;
-            if (size < a->frames[i].len) a->frames[i].len = size;
-            cursor = i + 1;
-            return;
-        }
+    size_t lo = 0, hi = a->frames.size();
+    while (lo < hi) {
+        const size_t mid = lo + (hi - lo) / 2;
+        if (a->frames[mid].off < data_off) lo = mid + 1; else hi = mid;
+    }
+    if (lo < a->frames.size() && a->frames[lo].off == data_off) {
+        a->frames[lo].key = key ? 1 : 0; a->frames[lo].key_known = 1;
+        if (size < a->frames[lo].len) a->frames[lo].len = size;
     }
 }
 
@@ -227,5 +228,31 @@ int jsp_avi_frame_table(const jsp_avi *a, uint64_t *off, uint32_t *len, uint8_t 
 }
 
 const char *jsp_avi_last_error(void) { return g_avi_err; }
+
+// Cuts one stream's frame table into independently decodable segments: a segment starts at frame 0 and at every key
+// frame (the unit the reference restarts from when seeking, Manager.hx:244-249).  ScreenPressor keeps ONE piece of
+// state across key frames: the entropy coder is created by the first coded key frame that names a known version and is
+// never replaced (`if (ec == null) initEntro(version)`, ScreenPressor.hx:160-162), and a flat key frame needs it to
+// exist (:112-114).  seg_sp_version[k] carries that state into segment k (-> jsp_stream_desc.sp_version), so that a
+// segment which begins with a flat key frame, or whose key frame carries another version nibble, decodes exactly as
+// it does in stream order.
+int jsp_segment_stream(int32_t codec, const uint8_t *bytes, const uint64_t *frame_off, const uint32_t *frame_len,
+                       const uint8_t *frame_key, int32_t n_frames, int32_t *seg_first, int32_t *seg_sp_version)
+{
+    if (n_frames < 0 || (n_frames > 0 && (!frame_key || !seg_first))) return -1;
+    int n_seg = 0, version = 0;
+    for (int32_t i = 0; i < n_frames; i++) {
+        if (i == 0 || frame_key[i]) {
+            seg_first[n_seg] = i;
+            if (seg_sp_version) seg_sp_version[n_seg] = version;
+            n_seg++;
+        }
+        if (codec == JSP_CODEC_SCREENPRESSOR && version == 0 && frame_key[i] && bytes && frame_off && frame_len && frame_len[i] > 0) {
+            const int head = bytes[frame_off[i]], v = (head >> 4) + 1;
+            if ((head & 0xF) == 2 && v >= 2 && v <= 4) version = v;       // initEntro succeeded: sticky from here on
+        }
+    }
+    return n_seg;
+}
 
 }  // extern "C"

@@ -119,9 +119,9 @@ static void classify_sp(const StreamRec &S, SpHost &H, FrameRec &R, const uint8_
             uint32_t c;
             auto rd = [&](uint32_t i) -> uint32_t { return i < len ? src[i] : 0u; };
             if (S.bpp == 16) {
-                const uint32_t c16 = rd(0) + rd(1) * 256;
+                const uint32_t c16 = len >= 2 ? rd(0) + rd(1) * 256 : 0u;     // src[1] undefined -> NaN -> every `&` gives 0 (:136-141)
                 c = (((c16 >> 10) & 0x1F) << 19) | (((c16 >> 5) & 0x1F) << 11) | ((c16 & 0x1F) << 3);
-            } else c = (rd(3) << 16) | (rd(2) << 8) | rd(1);
+            } else c = len >= 2 ? (rd(3) << 16) | (rd(2) << 8) | rd(1) : 0u;  // `+ b` with b undefined is NaN -> 0; r, g undefined -> 0 under `<<`
             R.kind = FK_SP_FLAT; R.fill_value = c; R.forced = ST_CHANGED;
             R.sp_flags = H.last_flat ? 0u : SPJ_RENEW;        // RenewI skips ec.renewI() after a flat frame (:113)
             H.last_flat = true; H.decodedI = true;
@@ -590,6 +590,8 @@ static int64_t batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_st
         S.codec = D.codec; S.w = D.width; S.h = D.height; S.bpp = D.bpp; S.n_frames = D.n_frames;
         S.first_frame = nf; S.h_bytes = D.bytes; S.pal_off = SIZE_MAX;
         if (D.codec == JSP_CODEC_MSVC8) { S.pal_off = pal_cur; pal_cur += 256; }
+        // a segment cut out of a longer ScreenPressor stream inherits the stream's entropy coder (see jsp_segment_stream)
+        if (D.codec == JSP_CODEC_SCREENPRESSOR && !keep && D.sp_version >= 2 && D.sp_version <= 4) b->sp_hosts[s].version = D.sp_version;
         if (D.codec != JSP_CODEC_SCREENPRESSOR && ((D.width & 3) || (D.height & 3))) remainder = true;
         uint64_t lo = UINT64_MAX, hi = 0;
         for (int f = 0; f < D.n_frames; f++) {

@@ -63,13 +63,16 @@ __device__ __forceinline__ uint32_t sp_segment(int32_t *dst, const int32_t *prev
     case 3: v = px_load(prev, idx, end); break;
     case 5: v = px_load(dst, idx - X - 1, end); break;
     case 4: {
-        uint32_t d = lane < m ? vsub4(px_load(dst, idx - X, end), px_load(dst, idx - X - 1, end)) : 0u;
+        // JavaScript: a neighbour at a negative index is `undefined`, the byte sum is NaN and NaN & 0xFF is 0 -- the WHOLE
+        // pixel is 0 when its above-left neighbour (the lowest index of the three) is outside (ScreenPressor.hx:443-449).
+        // Such pixels (index <= X) are a prefix of the segment; the chain restarts from 0 after them.
+        uint32_t d = (lane < m && idx > X) ? vsub4(px_load(dst, idx - X, end), px_load(dst, idx - X - 1, end)) : 0u;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
             const uint32_t o = __shfl_up_sync(FULLMASK, d, s);
             if (lane >= s) d = vadd4(d, o);
         }
-        v = vadd4(left, d) & 0x00FFFFFFu;
+        v = vadd4(i > X ? left : 0u, d) & 0x00FFFFFFu;
         break;
     }
     default: break;
@@ -265,7 +268,7 @@ static __device__ __noinline__ uint32_t sp_piece_pixelwise(int32_t *dst, const i
         case 1: v = px_load(dst, p - 1, end); break;
         case 2: v = px_load(dst, p - X, end); break;
         case 3: v = px_load(prev, p, end); break;
-        case 4: v = vadd4(px_load(dst, p - 1, end), vsub4(px_load(dst, p - X, end), px_load(dst, p - X - 1, end))) & 0x00FFFFFFu; break;
+        case 4: v = p > X ? vadd4(px_load(dst, p - 1, end), vsub4(px_load(dst, p - X, end), px_load(dst, p - X - 1, end))) & 0x00FFFFFFu : 0u; break;
         case 5: v = px_load(dst, p - X - 1, end); break;
         default: break;
         }
@@ -424,7 +427,7 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
                         uint32_t v = clr;
                         if (ptype == 1) v = px_load(dst, i - 1, end); else if (ptype == 2) v = px_load(dst, i - X, end);
                         else if (ptype == 3) v = px_load(prev, i, end); else if (ptype == 5) v = px_load(dst, i - X - 1, end);
-                        else if (ptype == 4) v = vadd4(px_load(dst, i - 1, end), vsub4(px_load(dst, i - X, end), px_load(dst, i - X - 1, end))) & 0xFFFFFFu;
+                        else if (ptype == 4) v = i > X ? vadd4(px_load(dst, i - 1, end), vsub4(px_load(dst, i - X, end), px_load(dst, i - X - 1, end))) & 0xFFFFFFu : 0u;
                         if (lane == 0 && i >= 0 && i < end) dst[i] = (int32_t)v;
                         __syncwarp();
                         clr = v; n--; xq = x1; y++;
@@ -441,13 +444,14 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
                         case 3: v = ptile[SP_PT_PREV + (y - y1) * 16 + (xq - x1) + lane]; break;
                         case 5: v = row[lane - SP_PT_STRIDE - 1]; break;
                         case 4: {
-                            uint32_t d = lane < m ? vsub4(row[lane - SP_PT_STRIDE], row[lane - SP_PT_STRIDE - 1]) : 0u;
+                            // pixels whose above-left neighbour has a negative index are 0 (see sp_segment)
+                            uint32_t d = (lane < m && i + lane > X) ? vsub4(row[lane - SP_PT_STRIDE], row[lane - SP_PT_STRIDE - 1]) : 0u;
 #pragma unroll
                             for (int sft = 1; sft < 16; sft <<= 1) {           // m <= 16 here
                                 const uint32_t o = __shfl_up_sync(FULLMASK, d, sft);
                                 if (lane >= sft) d = vadd4(d, o);
                             }
-                            v = vadd4(row[-1], d) & 0x00FFFFFFu;
+                            v = vadd4(i > X ? row[-1] : 0u, d) & 0x00FFFFFFu;
                             break;
                         }
                         default: break;

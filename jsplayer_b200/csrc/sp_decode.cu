@@ -3,6 +3,7 @@
 // concurrently whatever their coder is (two launches would each wait for their own slowest warp).
 // Replaces the per-frame entry of reference src/ScreenPressor.hx (DecompressI :117-295, DecompressP :302-484).
 #include "sp_rc.cuh"
+#include <atomic>
 #include "sp_ans.cuh"
 
 namespace jsp {
@@ -114,8 +115,15 @@ void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, 
     while (words <= max_width + 65u) words <<= 1;                    // >= sp_ring_size(max_width)
     if (words > 16384u) words = 1024;                                  // > 64 KB: such I frames fall back to global reads
     static_assert(SP_PTILE_WORDS <= 1024, "P-frame tile fits the minimum dynamic shared memory");
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(sp_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr_set = true; }
+    // the opt-in is per device (context), not per process: jsp_batch_decode(n_gpus > 1) launches from one thread per device
+    static std::atomic<unsigned long long> attr_devices{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_devices.load(std::memory_order_acquire) & bit)) {
+        if (cudaFuncSetAttribute(sp_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess)
+            attr_devices.fetch_or(bit, std::memory_order_release);
+    }
     const bool mixed = n_rc != 0 && n_rc != n_jobs && d_queue;
     sp_decode_kernel<<<n_jobs, 32, (size_t)words * 4, st>>>(d_jobs, words, n_rc, mixed ? d_queue : nullptr);
 }

@@ -82,6 +82,7 @@ static void ea_begin(entro *e, const uint8_t *src, int len, int pos0)   /* :229-
     a->nDec = 0;
 }
 extern __thread unsigned long long g_ora_symbols;
+extern int32_t *g_ora_sym_trace; void ora_sym_trace_put(int kind, int c, int freq, int cum, int tot);
 static inline void ea_count(entro_ans *a)
 {
     g_ora_symbols++;
@@ -99,9 +100,11 @@ static int ea_clr(entro *e, int cxi)                       /* :235-255 */
         /* defined behaviour: an escape interval past symbol 255 (impossible on a valid stream; the reference would
          * index cntab[] out of range on the next symbol and throw) is a failure and the symbol wraps to a byte */
         if (c > 255) { a->rans.failed = 1; c &= 255; }
+        if (g_ora_sym_trace) ora_sym_trace_put(0, c, rcv.freq, rcv.cumFreq, 4096);
     } else {
         c = rans_byte(&a->rans);                           /* Rans.raw, ANS.hx:46-48 */
         cctx_update(dcx, c, a->f0);
+        if (g_ora_sym_trace) ora_sym_trace_put(0, c, 0, 0, 0);
     }
     ea_count(a);
     return c;
@@ -112,25 +115,27 @@ static int ea_bool(entro *e)                               /* :259-269 */
     const int f = rans_get(&a->rans);
     const int flag = f >= (ANS_PROB_SCALE >> 1);
     rans_advance(&a->rans, flag ? ANS_PROB_SCALE >> 1 : 0, ANS_PROB_SCALE >> 1);
+    if (g_ora_sym_trace) ora_sym_trace_put(9, flag, ANS_PROB_SCALE >> 1, flag ? ANS_PROB_SCALE >> 1 : 0, 4096);
     ea_count(a);
     return flag;
 }
-static int ea_f(entro_ans *a, fixed_ctx *t)                /* decodeF, :271-280 */
+static int ea_f(entro_ans *a, fixed_ctx *t, int kind)      /* decodeF, :271-280 */
 {
     dec_receiver rcv;
     fx_decode(t, rans_get(&a->rans), &rcv);
     rans_advance(&a->rans, rcv.cumFreq, rcv.freq);
+    if (g_ora_sym_trace) ora_sym_trace_put(kind, rcv.c, rcv.freq, rcv.cumFreq, 4096);
     ea_count(a);
     return rcv.c;
 }
-static int ea_n(entro *e, int pt) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->ntab[pt]); }
-static int ea_p(entro *e, int pt) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->ptypetab[pt]); }
-static int ea_x(entro *e) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->xxtab); }
-static int ea_bt(entro *e) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->bttab); }
-static int ea_bn(entro *e) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->ntab2); }
-static int ea_sxy(entro *e, int n) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->sxytab[n]); }
-static int ea_mx(entro *e) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->mvtab[0]); }
-static int ea_my(entro *e) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->mvtab[1]); }
+static int ea_n(entro *e, int pt) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->ntab[pt], 1); }
+static int ea_p(entro *e, int pt) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->ptypetab[pt], 2); }
+static int ea_x(entro *e) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->xxtab, 3); }
+static int ea_bt(entro *e) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->bttab, 4); }
+static int ea_bn(entro *e) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->ntab2, 5); }
+static int ea_sxy(entro *e, int n) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->sxytab[n], 6); }
+static int ea_mx(entro *e) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->mvtab[0], 7); }
+static int ea_my(entro *e) { entro_ans *a = (entro_ans *)e; return ea_f(a, &a->mvtab[1], 8); }
 static int ea_canbool(entro *e) { (void)e; return 1; }
 static int ea_diff16(entro *e) { (void)e; return 0; }      /* EntroCoders.hx:214 */
 static int ea_failed(entro *e) { return ((entro_ans *)e)->rans.failed; }

@@ -189,3 +189,22 @@ def key_frame_differs(codec, width, height, bpp, frames, keys, palette=None, ins
                                   pal.size if pal is not None else 0, insignificant_lines, n, blob.ctypes.data,
                                   off.ctypes.data, ln.ctypes.data, k.ctypes.data, out.ctypes.data, differs.ctypes.data)
     return differs
+
+
+def decode_stream_traced(codec, width, height, bpp, frames, keys=None, cap_symbols=4_000_000, **kw):
+    """decode_stream plus the oracle's per-symbol trace: an (n_symbols, 5) int32 array of
+    (call kind, symbol, freq, cumFreq, total) over the whole stream (see ora_sym_trace in rangecoder_oracle.c).
+    Single-threaded test hook."""
+    lib = load()
+    lib.ora_sym_trace.argtypes = [C.c_void_p, C.c_long]
+    lib.ora_sym_trace_count.restype = C.c_long
+    buf = np.zeros((cap_symbols, 5), dtype=np.int32)
+    lib.ora_sym_trace(buf.ctypes.data, cap_symbols)
+    try:
+        res = decode_stream(codec, width, height, bpp, frames, keys=keys, **kw)
+        n = int(lib.ora_sym_trace_count())
+    finally:
+        lib.ora_sym_trace(None, 0)
+    if n > cap_symbols:
+        raise ValueError("trace buffer too small: %d symbols" % n)
+    return res + (buf[:n].copy(),)

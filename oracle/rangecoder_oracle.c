@@ -26,6 +26,7 @@ typedef struct {
     const uint8_t *data;
     int len, pos;
     int poisoned, failed;
+    uint32_t last_cum, last_freq, last_tot;               /* the interval of the last decoded symbol (trace hook) */
 } rangecoder;
 
 static inline void rc_byte(rangecoder *rc)
@@ -49,6 +50,22 @@ static void rc_begin(rangecoder *rc, const uint8_t *src, int len, int pos0)
 /* test hook: entropy-coded symbols decoded so far by the calling thread (both coders).  Thread-local: a shared
  * counter would make the multi-threaded CPU baseline fight over one cache line. */
 __thread unsigned long long g_ora_symbols = 0;
+/* test hook (single-threaded callers only): when set, every entropy-coded symbol both coders hand to the frame loop is
+ * appended as 5 ints: call kind (0 clr, 1 N, 2 P, 3 X, 4 BT, 5 BN, 6 SXY, 7 MX, 8 MY, 9 bool), symbol, freq, cumFreq,
+ * total (range coder: the table total; rANS: 4096, or freq = cumFreq = total = 0 for a raw byte).  Compared against the
+ * independent Python reading (oracle/sp_naive.py) by tests/test_sp_second_reading.py. */
+int32_t *g_ora_sym_trace = 0; long g_ora_sym_trace_cap = 0, g_ora_sym_trace_n = 0;
+void ora_sym_trace(int32_t *buf, long cap_symbols) { g_ora_sym_trace = buf; g_ora_sym_trace_cap = cap_symbols; g_ora_sym_trace_n = 0; }
+long ora_sym_trace_count(void) { return g_ora_sym_trace_n; }
+void ora_sym_trace_put(int kind, int c, int freq, int cum, int tot)
+{
+    if (!g_ora_sym_trace) return;
+    if (g_ora_sym_trace_n < g_ora_sym_trace_cap) {
+        int32_t *p = g_ora_sym_trace + 5 * g_ora_sym_trace_n;
+        p[0] = kind; p[1] = c; p[2] = freq; p[3] = cum; p[4] = tot;
+    }
+    g_ora_sym_trace_n++;
+}
 unsigned long long ora_symbol_count(int reset) { unsigned long long v = g_ora_symbols; if (reset) g_ora_symbols = 0; return v; }
 
 /* Defined behaviour: a failed frame decodes nothing more -- every later call returns 0 and leaves the models alone.
@@ -71,6 +88,7 @@ static inline uint32_t rc_get_freq(rangecoder *rc, uint32_t tot)
 /* RangeCoder.hx:36-43 */
 static inline void rc_decode(rangecoder *rc, uint32_t cum, uint32_t freq)
 {
+    rc->last_cum = cum; rc->last_freq = freq;
     rc->code -= (uint64_t)cum * rc->range;
     rc->range = rc->range * freq;
     while (rc->range < TOP) { rc_byte(rc); rc->range <<= 8; }
@@ -81,6 +99,7 @@ static int rc_decode_val(rangecoder *rc, uint32_t *cnt, int maxc, uint32_t step)
 {
     if (rc_frozen(rc)) return 0;
     uint32_t totfr = cnt[maxc];
+    rc->last_tot = totfr;
     uint32_t value = rc_get_freq(rc, totfr);
     int c = 0; uint32_t cumfr = 0, cnt_c = 0;
     while (c < maxc) {
@@ -105,6 +124,7 @@ static int rc_decode_val_uni(rangecoder *rc, uint32_t *cnt, uint32_t step)
 {
     if (rc_frozen(rc)) return 0;
     uint32_t totfr = cnt[16];
+    rc->last_tot = totfr;
     uint32_t value = rc_get_freq(rc, totfr);
     int x = 0; uint32_t cumfr = 0, cnt_x = 0;
     while (x < 16) {
@@ -186,15 +206,16 @@ static void erc_renewI(entro *e)
 }
 
 static void erc_begin(entro *e, const uint8_t *src, int len, int pos0) { rc_begin(&((entro_rc *)e)->rc, src, len, pos0); }
-static int erc_clr(entro *e, int cxi) { entro_rc *r = (entro_rc *)e; return rc_decode_val_uni(&r->rc, r->cntab + (size_t)cxi * CNTABSZ, SC_STEP); }
-static int erc_n(entro *e, int pt) { entro_rc *r = (entro_rc *)e; return rc_decode_val(&r->rc, r->ntab[pt], 256, SC_NSTEP); }
-static int erc_p(entro *e, int pt) { entro_rc *r = (entro_rc *)e; return rc_decode_val(&r->rc, r->ptypetab[pt], 6, SC_UNSTEP); }
-static int erc_x(entro *e) { entro_rc *r = (entro_rc *)e; return rc_decode_val(&r->rc, r->xxtab, 256, SC_XXSTEP); }
-static int erc_bt(entro *e) { entro_rc *r = (entro_rc *)e; return rc_decode_val(&r->rc, r->bttab, 5, SC_BTSTEP); }
-static int erc_bn(entro *e) { entro_rc *r = (entro_rc *)e; return rc_decode_val(&r->rc, r->ntab2, 256, SC_BTNSTEP); }
-static int erc_sxy(entro *e, int n) { entro_rc *r = (entro_rc *)e; return rc_decode_val(&r->rc, r->sxytab[n], 16, SC_SXYSTEP); }
-static int erc_mx(entro *e) { entro_rc *r = (entro_rc *)e; return rc_decode_val(&r->rc, r->mvtab[0], SP_MSR_X * 2, SC_MSTEP); }
-static int erc_my(entro *e) { entro_rc *r = (entro_rc *)e; return rc_decode_val(&r->rc, r->mvtab[1], SP_MSR_Y * 2, SC_MSTEP); }
+#define ERC_T(kind, expr) do { int c_ = (expr); if (g_ora_sym_trace && !r->rc.failed) ora_sym_trace_put(kind, c_, (int)r->rc.last_freq, (int)r->rc.last_cum, (int)r->rc.last_tot); return c_; } while (0)
+static int erc_clr(entro *e, int cxi) { entro_rc *r = (entro_rc *)e; ERC_T(0, rc_decode_val_uni(&r->rc, r->cntab + (size_t)cxi * CNTABSZ, SC_STEP)); }
+static int erc_n(entro *e, int pt) { entro_rc *r = (entro_rc *)e; ERC_T(1, rc_decode_val(&r->rc, r->ntab[pt], 256, SC_NSTEP)); }
+static int erc_p(entro *e, int pt) { entro_rc *r = (entro_rc *)e; ERC_T(2, rc_decode_val(&r->rc, r->ptypetab[pt], 6, SC_UNSTEP)); }
+static int erc_x(entro *e) { entro_rc *r = (entro_rc *)e; ERC_T(3, rc_decode_val(&r->rc, r->xxtab, 256, SC_XXSTEP)); }
+static int erc_bt(entro *e) { entro_rc *r = (entro_rc *)e; ERC_T(4, rc_decode_val(&r->rc, r->bttab, 5, SC_BTSTEP)); }
+static int erc_bn(entro *e) { entro_rc *r = (entro_rc *)e; ERC_T(5, rc_decode_val(&r->rc, r->ntab2, 256, SC_BTNSTEP)); }
+static int erc_sxy(entro *e, int n) { entro_rc *r = (entro_rc *)e; ERC_T(6, rc_decode_val(&r->rc, r->sxytab[n], 16, SC_SXYSTEP)); }
+static int erc_mx(entro *e) { entro_rc *r = (entro_rc *)e; ERC_T(7, rc_decode_val(&r->rc, r->mvtab[0], SP_MSR_X * 2, SC_MSTEP)); }
+static int erc_my(entro *e) { entro_rc *r = (entro_rc *)e; ERC_T(8, rc_decode_val(&r->rc, r->mvtab[1], SP_MSR_Y * 2, SC_MSTEP)); }
 static int erc_canbool(entro *e) { (void)e; return 0; }
 static int erc_bool(entro *e) { (void)e; return 0; }
 static int erc_diff16(entro *e) { (void)e; return 1; }       /* EntroCoders.hx:72 */

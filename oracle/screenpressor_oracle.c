@@ -10,7 +10,8 @@
  *  - the reference's frame buffers are 4x too large (Manager.hx:114-118) and a final run may spill past
  *    X*Y; here pictures are exactly X*Y and writes past the end are dropped;
  *  - out-of-frame reads (negative indices, motion vectors leaving the picture) yield 0
- *    (JavaScript `undefined` stored into an Int32Array);
+ *    (JavaScript `undefined` stored into an Int32Array); predictor 4 adds BYTES of three neighbours, and there one
+ *    `undefined` operand makes the whole sum NaN -> the pixel is 0 (not "the missing neighbour counts as 0");
  *  - a P frame starts from a copy of the previous picture (the reference copies unchanged blocks one by
  *    one, ScreenPressor.hx:468-474; every pixel of a valid frame is written either way);
  *  - a flat I frame before any coded I frame (ec == null, ScreenPressor.hx:112-114) and a stream whose
@@ -149,11 +150,11 @@ int sp_decompress_i(sp_dec *s, const uint8_t *src, int len, int32_t *dst)
         renew_i(s);
         int32_t c;
         if (s->bpp == 16) {
-            int clr16 = RD(0) + RD(1) * 256;
+            int clr16 = len >= 2 ? RD(0) + RD(1) * 256 : 0;               /* src[1] undefined -> NaN -> 0 under every `&` */
             int b = (clr16 & 0x1F) << 3, g = ((clr16 >> 5) & 0x1F) << 3, r = ((clr16 >> 10) & 0x1F) << 3;
             c = (r << 16) + (g << 8) + b;
         } else {
-            c = (RD(3) << 16) + (RD(2) << 8) + RD(1);
+            c = len >= 2 ? (RD(3) << 16) + (RD(2) << 8) + RD(1) : 0;      /* `+ b` with b undefined is NaN -> stored as 0 */
         }
         for (long i = 0; i < end; i++) dst[i] = c;
         s->prevFrame = dst; s->last_one_was_flat = c; s->decodedI = 1;
@@ -300,7 +301,10 @@ int sp_decompress_p(sp_dec *s, const uint8_t *src, int len, int32_t *dst, const 
                         case 1: clr = px_get(dst, i - 1, end); break;
                         case 2: clr = px_get(dst, i + off + 1, end); break;
                         case 3: clr = prev ? px_get(prev, i, end) : 0; break;
-                        case 4: clr = grad(px_get(dst, i - 1, end), px_get(dst, i + off + 1, end), px_get(dst, i + off, end)); break;
+                        /* JavaScript: dstbytes[k] with k < 0 is `undefined`, the sum is NaN and NaN & 0xFF is 0 -- ONE
+                         * neighbour outside the buffer zeroes the whole pixel (ScreenPressor.hx:443-449); the above-left
+                         * neighbour has the lowest index of the three.  Found by the second reading (oracle/sp_naive.py). */
+                        case 4: clr = (i + off < 0) ? 0 : grad(px_get(dst, i - 1, end), px_get(dst, i + off + 1, end), px_get(dst, i + off, end)); break;
                         case 5: clr = px_get(dst, i + off, end); break;
                         default: break;
                         }

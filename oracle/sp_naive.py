@@ -22,6 +22,9 @@ It is slow (pure Python, ~1 us per byte-code) and only ever sees small frames.
 
 UNDEF = None          # JavaScript `undefined`
 
+import collections
+EVENTS = collections.Counter()      # instrumentation only (which rare model paths a corpus exercised); not in the reference
+
 
 class JsSemanticsError(Exception):
     """Raised where the reference would compute with NaN / Infinity inside the coder state (corrupt streams only)."""
@@ -89,6 +92,7 @@ class Rans:
         self.reinitImpl(srcdata, pos0)
 
     def reinit(self):
+        EVENTS["rans_reinit"] += 1
         self.reinitImpl(self.data, self.pos)
 
     def _rd(self, i):
@@ -164,6 +168,7 @@ class FixedSizeRansCtx:
         self.cnts[c] = self.cnts[c] + step
         self.cntsum += step
         if self.cntsum + step > Rans.PROB_SCALE:
+            EVENTS["fixed_rebuild_%d" % self.NSym] += 1
             self.cntsum = 0
             cf = 0
             for j in range(self.NSym):
@@ -306,6 +311,7 @@ class SmallContext:
         return True
 
     def rescale(self):
+        EVENTS["small_rescale_S%d" % self.S] += 1
         s = 256 - self.d
         for i in range(self.d):
             self.freqs[i] = self.freqs[i] - (self.freqs[i] >> 1)
@@ -592,6 +598,7 @@ class Cx6:
         self.cnts[S] = sum_
 
     def rescaleDec(self):
+        EVENTS["cx6_rescaleDec"] += 1
         _cnts = Cx6._cnts
         _freqs = Cx6._freqs
         sh = self.fshift - 1 if self.fshift > 0 else 0
@@ -666,6 +673,7 @@ class Cx6:
         return pos
 
     def growDec(self):
+        EVENTS["cx6_grow"] += 1
         S = self.symbols.length * 2
         sym = U8(S)
         cs = U16(S + 1)
@@ -896,6 +904,7 @@ class RangeCoder:
         cnt[c] = cnt_c + step
         totfr += step
         if totfr > RangeCoder.BOT:
+            EVENTS["rc_rescale_%d" % maxc] += 1
             totfr = 0
             for i in range(maxc):
                 nc = (cnt[i] >> 1) + 1
@@ -931,6 +940,7 @@ class RangeCoder:
         cnt[off + x] = cnt_x + step
         totfr += step
         if totfr > RangeCoder.BOT:
+            EVENTS["rc_rescale_uni"] += 1
             totfr = 0
             for i in range(off + 17, off + 256 + 17):
                 nc = (cnt[i] >> 1) + 1
@@ -1153,6 +1163,8 @@ class EntroCoderANS:
             dcx.update(c)
             if self.trace is not None:
                 self.trace.append((0, c, 0, 0, 0))
+        if k0 != dcx.u[0]:
+            EVENTS["kind_%d_to_%d" % (k0, dcx.u[0])] += 1
         self.kinds_seen.add((k0, dcx.u[0]))
         self._count()
         return c
@@ -1589,7 +1601,7 @@ def decode_stream(width, height, bpp, frames, insignificant_lines=0, trace=False
                 continue
             pics.append(dst.a[:n_px])
             changed.append(True)
-            signif.append(True)
+            signif.append(False)        # DecompressI has no significant_changes; the batch convention reports 0
         else:
             prev = sp.PreviousFrame()
             dst = FrameBuf(n_px)

@@ -201,3 +201,27 @@ def test_two_ranks_shard_gops_without_exchange():
         assert got[rank] == mine and n_specs == n
         assert sorted(got[0] + got[1]) == list(range(n))                 # every GOP decoded exactly once
         assert tmax == max(len(got[0]), len(got[1]))
+
+
+def test_segmenter_carries_the_screenpressor_coder_version():
+    """jsp_segment_stream: segments start at key frames; ScreenPressor's entropy coder is created by the first coded key
+    frame that names a known version and kept (ScreenPressor.hx:160-162), so later segments inherit it."""
+    import ctypes as C
+    from jsplayer_b200 import _lib
+    lib = _lib.load()
+    frames = [b"\x99", b"\x11abc", b"\x01zz", b"\x52", b"\x22abcdef", b"\x01", b"\x11abc", b"\x01", b"\x32xyz", b""]
+    keys = [0, 1, 0, 1, 1, 0, 1, 0, 1, 1]
+    blob = np.frombuffer(b"".join(frames) + b"\0", dtype=np.uint8).copy()
+    ln = np.array([len(f) for f in frames], dtype=np.uint32)
+    off = np.concatenate([[0], np.cumsum(ln)[:-1]]).astype(np.uint64)
+    k = np.array(keys, dtype=np.uint8)
+    first = np.zeros(len(frames), dtype=np.int32); ver = np.zeros(len(frames), dtype=np.int32)
+    n = lib.jsp_segment_stream(int(CodecType.codec_screenpressor), blob.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                               k.ctypes.data, len(frames), first.ctypes.data, ver.ctypes.data)
+    assert n == 7
+    assert list(first[:n]) == [0, 1, 3, 4, 6, 8, 9]
+    # flat 0x11 and the unknown-version 0x52 create no coder; 0x22 (version 3) does, and 0x32 later does not replace it
+    assert list(ver[:n]) == [0, 0, 0, 0, 3, 3, 3]
+    n = lib.jsp_segment_stream(int(CodecType.codec_msvc16), blob.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                               k.ctypes.data, len(frames), first.ctypes.data, ver.ctypes.data)
+    assert n == 7 and not ver[:n].any()

@@ -126,3 +126,40 @@ def test_plain_c_host_decodes_an_avi(tmp_path):
                 s = (s * 31 + v) & 0xFFFFFFFF
             assert int(parts[-1], 16) == s, "%s frame %d" % (name, f)
             assert int(parts[parts.index("status") + 1]) == 0
+
+
+def test_gop_split_with_flat_key_frames_matches_in_order_decoding(tmp_path):
+    """A ScreenPressor file whose GOPs begin with FLAT key frames: in stream order the reference decodes them with the
+    entropy coder an earlier coded key frame created (ScreenPressor.hx:132-155, :160-162).  Cut into segments, the
+    segment has to be told (jsp_segment_stream -> jsp_stream_desc.sp_version), or the flat frame is an error and every
+    P frame after it degrades to copy-previous."""
+    w, h = 96, 64
+    for version in (2, 3, 4):
+        enc = synth.SPEncoder(w, h, 24, version)
+        p0 = synth.screen(w, h, 1)
+        frames, keys = [enc.iframe(p0)], [1]
+        cur = p0
+        for g in range(3):
+            nxt, mv = synth.screen_next(cur, 10 + g, 80)
+            frames.append(enc.pframe(nxt, cur, mv)); keys.append(0)
+            flat = np.full((h, w), 0x102030 * (g + 1), dtype=np.int32)
+            frames.append(enc.flat(0x102030 * (g + 1))); keys.append(1)            # a GOP that starts with a flat key frame
+            cur, mv = synth.screen_next(flat, 20 + g, 120)
+            frames.append(enc.pframe(cur, flat, mv)); keys.append(0)
+            nxt, mv = synth.screen_next(cur, 30 + g, 120)
+            frames.append(enc.pframe(nxt, cur, mv)); keys.append(0)
+            cur = nxt
+        path = str(tmp_path / ("flat%d.avi" % version))
+        write_avi(path, w, h, 24, b"SCPR", frames, keys)
+        st = avi.load_avi(path, pinned=True)
+        segs = st.segments()
+        assert len(segs) == 4 and [v for _, _, v in segs] == [0, version, version, version]
+        specs, where = avi.gop_specs([st])
+        bd = BatchDecoder()
+        bd.configure(specs)
+        outs, flags = bd.decode_host()
+        bd.close()
+        exp, ch, sg, stt = O.decode_stream(O.CODEC_SCREENPRESSOR, w, h, 24, frames, keys=keys)
+        assert (stt == 0).all() and not (flags & _lib.JSP_FRAME_ERROR).any()
+        for i in range(len(frames)):
+            assert (outs[i] == exp[i]).all(), "version %d frame %d" % (version, i)

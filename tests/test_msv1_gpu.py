@@ -96,6 +96,24 @@ def test_trailing_garbage_and_pad_byte(is8):
     check_stream(is8, w, h, frames, keys=[1, 1, 1])
 
 
+@pytest.mark.parametrize("is8", [False, True])
+def test_bytes_after_a_terminator_hold_a_second_terminator(is8):
+    """Skip count 0 (`00 84`) / the 8-bit `00 00` end the frame: the rest is copied from the previous picture.  Lanes
+    past the terminator still parse the trailing bytes; a SECOND terminator pattern among them must not move the
+    "rest of frame" copy (sm.big_blk0 used to be a plain store racing with the real one)."""
+    w, h = 256, 128
+    rng = np.random.default_rng(7)
+    key = synth.msv1_frame(is8, w, h, 3)
+    term = b"\x00\x00" if is8 else b"\x00\x84"
+    frames, keys = [key], [1]
+    for trial in range(12):
+        head = synth.msv1_frame(is8, w, h, 50 + trial, skip_permille=300)[: int(rng.integers(2, 600)) & ~1]
+        tail = rng.integers(0, 256, size=int(rng.integers(4, 900)) & ~1, dtype=np.uint8).tobytes()
+        junk = b"".join(tail[i:i + 32] + term for i in range(0, len(tail), 32))      # many more terminator patterns
+        frames.append(head + term + junk); keys.append(0)
+    check_stream(is8, w, h, frames, keys=keys)
+
+
 def test_random_bytes_do_not_crash_and_match():
     """Arbitrary bytes are a valid opcode stream for this codec; the walk must agree with the oracle."""
     rng = np.random.default_rng(99)
