@@ -262,8 +262,14 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
         // longest frames first: when a launch has more warps than the device holds, the late starters are the short ones
         std::vector<int64_t> order(by_level[lv]);
         std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return b->frames[x].len > b->frames[y].len; });
-        // range-coder frames first (the kernel deals the two coders to different SMs when both are present)
+        // range-coder frames first (the kernel deals the two coders to different SMs when both are present), and among them
+        // the coded I frames first (second-generation kernels: one launch per coder and frame type)
         std::stable_partition(order.begin(), order.end(), [&](int64_t x) { return b->sp_hosts[b->frames[x].stream].version <= 2; });
+        {
+            auto rc_end = std::stable_partition(order.begin(), order.end(), [&](int64_t x) { return b->sp_hosts[b->frames[x].stream].version <= 2; });
+            std::stable_partition(order.begin(), rc_end, [&](int64_t x) { return b->frames[x].kind == FK_SP_I; });
+        }
+        int n_rc_i = 0;
         for (int64_t f : order) {
             const FrameRec &R = b->frames[f];
             if (R.kind != FK_SP_I && R.kind != FK_SP_P && !(R.kind == FK_SP_FLAT && (R.sp_flags & SPJ_RENEW))) continue;
@@ -282,6 +288,7 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             J.X = (uint32_t)S.w; J.Y = (uint32_t)S.h; J.flags = R.sp_flags | (H.version > 2 ? SPJ_ANS : 0u);
             J.insign_blocks = (uint32_t)(((S.w + 15) / 16) * ((std::max(0, b->insign_lines) + 15) / 16));
             (H.version > 2 ? n_ans : n_rc)++;
+            if (H.version <= 2 && R.kind == FK_SP_I) n_rc_i++;
             max_w = std::max(max_w, J.X);
             T.spjobs.push_back(J);
             if (R.kind != FK_SP_FLAT) fin.push_back(f);
@@ -289,7 +296,7 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
         if (T.spjobs.size() > first) {
             const int kclass = n_ans == 0 ? JSP_K_SP_ENTROPY_RC : (n_rc == 0 ? JSP_K_SP_ENTROPY_ANS : JSP_K_SP_ENTROPY_MIXED);
             Launch L{kclass, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), max_w, (uint32_t)ticket_cursor};
-            L.n_rc = (uint32_t)n_rc;
+            L.n_rc = (uint32_t)n_rc; L.n_rc_i = (uint32_t)n_rc_i;
             ticket_cursor += 2;
             plan.launches.push_back(L);
             plan.finished.push_back(std::move(fin));
@@ -401,7 +408,9 @@ template <class F> static bool run_plan_with(jsp_batch *b, const Plan &P, cudaSt
                                b->d_tile_map, b->d_tile_cnt, b->d_tickets + L.ticket, b->sm_count, st);
             break;
         case JSP_K_SP_ENTROPY_RC: case JSP_K_SP_ENTROPY_ANS: case JSP_K_SP_ENTROPY_MIXED:
-            launch_sp_decode(b->d_spjobs + L.first, L.count, L.max_vec4, L.n_rc, b->d_tickets + L.ticket, st);
+            if (sp_generation() < 2 ||
+                !launch_sp2_level(b->d_spjobs + L.first, L.n_rc_i, L.n_rc - L.n_rc_i, L.count - L.n_rc, L.max_vec4, b->d_tickets + L.ticket, st))
+                launch_sp_decode(b->d_spjobs + L.first, L.count, L.max_vec4, L.n_rc, b->d_tickets + L.ticket, st);
             break;
         default: break;
         }
@@ -686,7 +695,7 @@ static int64_t batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_st
             SpHost &H = b->sp_hosts[s];
             const bool ans = H.version > 2;
             H.n_slots = b->persist_streams ? 1 : std::max(1, std::min(H.n_segments, max_slots));
-            H.state_stride = ans ? sp_ans_state_bytes() : sp_rc_state_bytes();
+            H.state_stride = ans ? sp_ans_state_bytes() : (sp_generation() >= 2 ? sp2_rc_state_bytes() : sp_rc_state_bytes());
             H.rows_stride = ((ans ? sp_ans_ctx_bytes() : sp_rc_rows_bytes()) + 255) & ~(size_t)255;
             H.bts_stride = ((size_t)((b->streams[s].w + 15) / 16) * ((b->streams[s].h + 15) / 16) + 255) & ~(size_t)255;
             H.state_off = st_cur; st_cur += H.state_stride * H.n_slots;
@@ -717,6 +726,7 @@ static int64_t batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_st
                         for (int k = 0; k < H.n_slots; k++) {
                             uint8_t *stp = b->d_sp_state + H.state_off + k * H.state_stride, *rwp = b->d_sp_rows + H.rows_off + k * H.rows_stride;
                             if (H.version > 2) sp_ans_state_init(stp, rwp, 1u, b->st_compute);
+                            else if (sp_generation() >= 2) sp2_rc_state_init(stp, rwp, 1u, b->st_compute);
                             else sp_rc_state_init(stp, rwp, 1u, b->st_compute);
                         }
                     }

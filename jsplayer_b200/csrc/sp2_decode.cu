@@ -1,0 +1,332 @@
+// sp2_decode.cu -- second-generation ScreenPressor kernels (range coder; see sp2_rc.cuh for the symbol decoder).
+//
+//  sp2_rc_i_kernel   coded I frames (ScreenPressor.hx:117-295), one CTA of TWO warps per frame:
+//      warp 0 ("E") runs the entropy decode -- the serial chain -- and nothing else: per run it decodes the predictor
+//               type, the colour (3 symbols, only for type 0) and the run length, and pushes (type, length, colour) into a
+//               shared-memory queue;
+//      warp 1 ("R") pops runs and reconstructs pixels: fills, copies from the row above and the gradient predictor, 32
+//               pixels per step, written to the picture in HBM and to a shared-memory ring of the last X + 1 pixels.
+//      Round 1 did both in one warp, and the run write (~430 cycles: shared-memory round trips, a 5-step shuffle prefix
+//      sum for the gradient predictor, two warp barriers) sat in the middle of the symbol chain.  The decoder needs
+//      reconstructed pixels only for the colour CONTEXT of the next type-0 run (ScreenPressor.hx:274-275), so that one
+//      value is fetched lazily: E waits for R to drain and reads the last pixel from the ring -- by then R has had a whole
+//      decodeP of head start.  The gradient predictor needs no prefix sum at all: left + above - aboveleft telescopes
+//      along a run to  p[i] = p[start-1] + above[i] - above[start-1]  per byte (R below).
+//  sp2_rc_p_kernel   P frames (:302-484) and model resets of flat frames: one warp, round 1's frame loop
+//      (sp_common.cuh) on the new symbol decoder.
+//
+// Separate kernels per (coder, frame type) keep each hot loop small: round 1's single kernel held both coders and both
+// frame loops in 68 000 instructions (1.1 MB of SASS) against a 32 KB L1.5 instruction cache.
+#include "sp2_rc.cuh"
+#include <atomic>
+
+namespace jsp {
+namespace g2 {
+
+// ---- E -> R run queue (shared memory, single producer / single consumer) -------------------------------------------
+// One entry = two words, BOTH carrying generation bits of the slot (run index / RQ_N + 1), so a torn read can never pass
+// for a complete entry:  w0 = colour | type << 24 | (gen & 31) << 27,  w1 = length | (gen & 0xFFFF) << 16.
+constexpr int RQ_N = 64;
+constexpr uint32_t RQ_END = 7;                                   // type 7: end of frame
+struct RunQueue {
+    alignas(16) uint2 e[RQ_N];
+    uint32_t done;                                               // runs R has completed (written by R, release; read by E, acquire)
+    uint32_t pad[3];
+};
+
+__device__ __forceinline__ void st_volatile_v2(uint2 *p, uint32_t a, uint32_t b)
+{
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 ld_volatile_v2(const uint2 *p)
+{
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+
+struct Producer {
+    RunQueue *q;
+    uint32_t issued, seen_done;
+    __device__ __forceinline__ void push(uint32_t type, uint32_t n, uint32_t clr)
+    {
+        while (issued - seen_done >= (uint32_t)RQ_N) seen_done = ld_relaxed(&q->done);     // back-pressure (rare)
+        const uint32_t gen = issued / RQ_N + 1u;
+        st_volatile_v2(&q->e[issued % RQ_N], (clr & 0xFFFFFFu) | (type << 24) | ((gen & 31u) << 27), n | ((gen & 0xFFFFu) << 16));
+        issued++;
+    }
+    __device__ __forceinline__ void drain() { while (ld_acquire(&q->done) != issued) {} seen_done = issued; }
+};
+
+// ---- warp 1: pixel reconstruction (ScreenPressor.hx:242-273) -------------------------------------------------------
+__device__ __forceinline__ void sp2_recon_iframe(RunQueue *q, const SpJob &J, uint32_t *ring, uint32_t rmask)
+{
+    const int lane = (int)lane_id();
+    const long X = J.X, end = (long)J.X * J.Y;
+    int32_t *dst = J.dst;
+    const int chunk = X < 32 ? (int)X : 32;          // a chunk never reads pixels it writes itself (the row above is X away)
+    long di = 0;
+    uint32_t lastval = 0, consumed = 0;
+    for (;;) {
+        const uint32_t gen = consumed / RQ_N + 1u;
+        uint2 e;
+        do { e = ld_volatile_v2(&q->e[consumed % RQ_N]); } while (((e.x >> 27) != (gen & 31u)) || ((e.y >> 16) != (gen & 0xFFFFu)));
+        const uint32_t type = (e.x >> 24) & 7u, clr = e.x & 0xFFFFFFu;
+        const int n = (int)(e.y & 0xFFFFu);
+        if (type == RQ_END) break;
+        for (int o = 0; o < n; o += chunk) {
+            const int m = n - o < chunk ? n - o : chunk;
+            const long s = di + o, idx = s + lane;
+            uint32_t v = clr, last = clr;
+            switch (type) {
+            case 1: v = last = lastval; break;
+            case 2: v = ring[(uint32_t)(idx - X) & rmask]; last = ring[(uint32_t)(s + m - 1 - X) & rmask]; break;
+            case 5: v = ring[(uint32_t)(idx - X - 1) & rmask]; last = ring[(uint32_t)(s + m - 2 - X) & rmask]; break;
+            case 4: {
+                // p[i] = p[i-1] + above[i] - aboveleft[i] per byte and aboveleft[i] = above[i-1]: the sum telescopes to
+                // p[i] = p[s-1] + above[i] - above[s-1] -- no scan along the run
+                const uint32_t a0 = ring[(uint32_t)(s - 1 - X) & rmask];
+                v = vadd4(lastval, vsub4(ring[(uint32_t)(idx - X) & rmask], a0)) & 0x00FFFFFFu;
+                last = vadd4(lastval, vsub4(ring[(uint32_t)(s + m - 1 - X) & rmask], a0)) & 0x00FFFFFFu;
+                break;
+            }
+            default: break;
+            }
+            __syncwarp();                                  // every lane has read the ring before slots are overwritten
+            if (lane < m && idx < end) { dst[idx] = (int32_t)v; ring[(uint32_t)idx & rmask] = v; }
+            lastval = last;
+            __syncwarp();
+        }
+        di += n;
+        consumed++;
+        if (lane == 0) st_release(&q->done, consumed);
+    }
+}
+
+// ---- warp 0: entropy decode of a coded I frame ---------------------------------------------------------------------
+template <class Coder>
+__device__ __forceinline__ void sp2_entropy_iframe(Coder &ec, Producer &pq, const SpJob &J, const uint32_t *ring, uint32_t rmask)
+{
+    const long X = J.X, end = (long)J.X * J.Y;
+    const int cxshift = (J.flags & SPJ_CXSHIFT0) ? 0 : 2;
+    int maskcx1 = 0xFC00, shiftcx1 = 4, shiftcx = 18;
+    if (J.flags & SPJ_DIFF16) { maskcx1 = 0xFF00; shiftcx1 = 2; shiftcx = 16; }
+    ec.renewI();
+    ec.decodeBegin(J.src, J.len, 1);
+    int cx = 0, cx1 = 0;
+    long di = 0, k = 0;
+    uint32_t clr = 0;
+    auto decode_rgb = [&]() -> uint32_t {                 // ScreenPressor.hx:173-183
+        uint32_t px = 0;
+#pragma unroll 1
+        for (int ch = 0; ch < 3; ch++) {
+            const int v = ec.decodeClr(sp_ctx_index(ec, ch, cx, cx1));
+            cx1 = (cx << 6) & 0xFC0; cx = v >> cxshift;
+            px += (uint32_t)v << (8 * ch);
+        }
+        return px;
+    };
+    long budget = sp_run_budget(X, J.Y);
+    while (k < X + 1) {                                    // first X+1 pixels: (colour, run) pairs, :170-197
+        if (--budget < 0) ec.fail_frame();
+        clr = decode_rgb();
+        const int n = ec.decodeN(0);
+        if (ec.failed()) return;
+        k += n;
+        if (n > 0) pq.push(0u, (uint32_t)n, clr);
+        di += n;
+    }
+    int ptype = 0;
+    bool clr_lazy = false;                                 // clr = the last pixel written so far; fetched from R when needed
+    bool ctx_from_clr = false;                             // the contexts are recomputed from clr after every run of this loop (:274-275)
+    while (di < end) {                                     // :218-286
+        if (--budget < 0) ec.fail_frame();
+        ptype = ec.decodeP(ptype);
+        if (ptype == 0) {
+            if (clr_lazy) { pq.drain(); clr = ring[(uint32_t)(di - 1) & rmask]; clr_lazy = false; }
+            if (ctx_from_clr) { cx1 = ((int)clr & maskcx1) >> shiftcx1; cx = (int)clr >> shiftcx; }
+            clr = decode_rgb();
+        }
+        int n = ec.decodeN(ptype);
+        if (ec.failed()) return;
+        if (ptype == 3 || ptype > 5) n = 0;                // no such predictor in an I frame: nothing is written
+        if (ptype == 1) clr_lazy = true;                   // `clr = dst[lasti]` even for an empty run (:252)
+        else if (ptype != 0 && n > 0) clr_lazy = true;     // clr = the run's last pixel
+        if (n > 0) pq.push((uint32_t)ptype, (uint32_t)n, clr);
+        di += n;
+        ctx_from_clr = true;
+    }
+}
+
+__global__ void __launch_bounds__(64)
+sp2_rc_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
+{
+    __shared__ RcShared shm;
+    __shared__ RunQueue rq;
+    extern __shared__ uint32_t ring[];                     // the last X + 1 pixels (power of two > X + 65 words)
+    const SpJob J = jobs[blockIdx.x];
+    const uint32_t rmask = sp_ring_size(J.X) - 1u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < RQ_N) rq.e[threadIdx.x] = make_uint2(0u, 0u);
+    if (threadIdx.x == 0) rq.done = 0;
+    __syncthreads();
+    RcCoder ec;
+    bool failed = false;
+    if (warp == 0) {
+        ec.open(J, shm);
+        Producer pq{&rq, 0u, 0u};
+        sp2_entropy_iframe(ec, pq, J, ring, rmask);
+        pq.push(RQ_END, 0u, 0u);
+        failed = ec.failed();
+    } else {
+        sp2_recon_iframe(&rq, J, ring, rmask);
+    }
+    __syncthreads();                                       // R has written every pixel E queued
+    if (warp == 0) {
+        ec.close(J, shm);
+        uint32_t bits = ST_CHANGED;
+        if (failed) { bits = ST_ERROR; sp_undo_frame(J, true); }
+        if (lane == 0) { atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
+    }
+    if (J.done) {                                          // the host may copy the picture out while the launch still runs
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t *>(J.done) = 1u;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+sp2_rc_p_kernel(const SpJob *__restrict__ jobs, uint32_t tile_words)
+{
+    __shared__ RcShared shm;
+    extern __shared__ uint32_t ptile_mem[];
+    const SpJob J = jobs[blockIdx.x];
+    uint32_t *ptile = tile_words >= SP_PTILE_WORDS ? ptile_mem : nullptr;
+    RcCoder ec;
+    ec.open(J, shm);
+    uint32_t bits = 0;
+    if (J.flags & SPJ_RENEW) ec.renewI();
+    else sp_decode_pframe(ec, J, bits, ptile);
+    ec.close(J, shm);
+    if (ec.failed()) {
+        bits = ST_ERROR;
+        if (!(J.flags & SPJ_RENEW)) sp_undo_frame(J, false);
+    }
+    __syncwarp();
+    if (lane_id() == 0) { if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
+    sp_signal_done(J);
+}
+
+}  // namespace g2
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+int sp_generation()
+{
+    static const int gen = [] { const char *e = getenv("JSP_SP_GEN"); return e && e[0] == '1' ? 1 : 2; }();
+    return gen;
+}
+
+size_t sp2_rc_state_bytes() { return (sizeof(g2::RcState) + 255) & ~(size_t)255; }
+void sp2_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t st)
+{
+    g2::RcState h;
+    memset(&h, 0, sizeof h);
+    h.gen = gen0; h.rows = reinterpret_cast<uint32_t *>(d_rows);
+    cudaStreamSynchronize(st);      // ordered after the memsets queued on st
+    cudaMemcpy(reinterpret_cast<char *>(d_state) + offsetof(g2::RcState, gen), &h.gen, sizeof(g2::RcState) - offsetof(g2::RcState, gen),
+               cudaMemcpyHostToDevice);
+}
+
+namespace {
+struct DevAux {                                            // per device: side streams so that the kernels of one level overlap
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    bool attr = false, ok = false;
+};
+DevAux g_aux[64];
+std::atomic<unsigned long long> g_aux_ready{0};
+
+DevAux *aux_for_current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    DevAux &A = g_aux[dev];
+    const unsigned long long bit = 1ull << dev;
+    if (!(g_aux_ready.load(std::memory_order_acquire) & bit)) {
+        // one host thread drives a device (jsp_batch_decode: one thread per GPU), so no lock is needed per entry
+        bool ok = true;
+        for (int i = 0; i < 2; i++) {
+            ok = ok && cudaStreamCreateWithFlags(&A.s[i], cudaStreamNonBlocking) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&A.join[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        ok = ok && cudaEventCreateWithFlags(&A.fork, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(g2::sp2_rc_i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(g2::sp2_rc_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
+        A.ok = ok;
+        g_aux_ready.fetch_or(bit, std::memory_order_release);
+    }
+    return A.ok ? &A : nullptr;
+}
+}  // namespace
+
+// Jobs of one dependency level, ordered by the planner: [range-coder I frames | range-coder P frames and model resets |
+// rANS frames].  The three groups run as three concurrent launches (the level lasts as long as its slowest frame).
+void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, uint32_t n_rc, uint32_t *d_queue, cudaStream_t st);
+bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_rc_p, uint32_t n_ans, uint32_t max_width, uint32_t *d_queue, cudaStream_t st)
+{
+    DevAux *A = aux_for_current_device();
+    uint32_t words = 1024;                                             // at least the P-frame block tile (SP_PTILE_WORDS)
+    while (words <= max_width + 65u) words <<= 1;                      // >= sp_ring_size(max_width)
+    if (!A || words > 16384u) return false;                            // caller falls back to the first-generation kernel
+    const int groups = (n_rc_i ? 1 : 0) + (n_rc_p ? 1 : 0) + (n_ans ? 1 : 0);
+    const bool fork = groups > 1;
+    if (fork) cudaEventRecord(A->fork, st);
+    int side = 0;
+    auto stream_for = [&](bool first) -> cudaStream_t {
+        if (first || !fork) return st;
+        cudaStream_t s = A->s[side];
+        cudaStreamWaitEvent(s, A->fork, 0);
+        return s;
+    };
+    auto joined = [&](cudaStream_t s) {
+        if (s == st) return;
+        cudaEventRecord(A->join[side], s);
+        cudaStreamWaitEvent(st, A->join[side], 0);
+        side++;
+    };
+    bool first = true;
+    if (n_rc_i) {
+        cudaStream_t s = stream_for(first); first = false;
+        g2::sp2_rc_i_kernel<<<n_rc_i, 64, (size_t)words * 4, s>>>(d_jobs, words);
+        joined(s);
+    }
+    if (n_rc_p) {
+        cudaStream_t s = stream_for(first); first = false;
+        g2::sp2_rc_p_kernel<<<n_rc_p, 32, (size_t)1024 * 4, s>>>(d_jobs + n_rc_i, 1024);
+        joined(s);
+    }
+    if (n_ans) {
+        cudaStream_t s = stream_for(first); first = false;
+        launch_sp_decode(d_jobs + n_rc_i + n_rc_p, n_ans, max_width, 0, nullptr, s);
+        joined(s);
+    }
+    return true;
+}
+
+}  // namespace jsp
