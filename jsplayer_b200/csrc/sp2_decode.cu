@@ -23,6 +23,22 @@
 namespace jsp {
 namespace g2 {
 
+// Optional section timing (JSP_NVCC_EXTRA=-DJSP_SP2_PROF): cycles per warp role, summed over the launch into g_sp2_prof[]
+//  0 decodeP  1 decode_rgb  2 decodeN  3 push (incl. back-pressure)  4 drain wait  5 E whole loop  6 runs  7 colour runs
+//  8 R wait for an entry  9 R run write  10 R whole loop  11 drains
+#ifdef JSP_SP2_PROF
+__device__ unsigned long long g_sp2_prof[16];
+#define P2_DECL long long _p2[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long _p2t = clock64();
+#define P2_T(k) { const long long _n = clock64(); _p2[k] += _n - _p2t; _p2t = _n; }
+#define P2_C(k) _p2[k]++;
+#define P2_FLUSH if (lane_id() == 0) { for (int _k = 0; _k < 12; _k++) if (_p2[_k]) atomicAdd(&g_sp2_prof[_k], (unsigned long long)_p2[_k]); }
+#else
+#define P2_DECL
+#define P2_T(k)
+#define P2_C(k)
+#define P2_FLUSH
+#endif
+
 // ---- E -> R run queue (shared memory, single producer / single consumer) -------------------------------------------
 // One entry = two words, BOTH carrying generation bits of the slot (run index / RQ_N + 1), so a torn read can never pass
 // for a complete entry:  w0 = colour | type << 24 | (gen & 31) << 27,  w1 = length | (gen & 0xFFFF) << 16.
@@ -30,7 +46,7 @@ constexpr int RQ_N = 64;
 constexpr uint32_t RQ_END = 7;                                   // type 7: end of frame
 struct RunQueue {
     alignas(16) uint2 e[RQ_N];
-    uint32_t done;                                               // runs R has completed (written by R, release; read by E, acquire)
+    uint32_t done;                                               // runs R has completed (written by R, read by E)
     uint32_t pad[3];
 };
 
@@ -44,15 +60,15 @@ __device__ __forceinline__ uint2 ld_volatile_v2(const uint2 *p)
     asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
+// `done` is published with a plain volatile store and read with a plain volatile load.  A release / acquire pair would be
+// the textbook choice, but st.release makes the reconstruction warp wait for the acknowledgement of its GLOBAL stores
+// (the picture) before every queue step -- hundreds of cycles -- when all that has to be ordered is SHARED memory: ring
+// stores before the counter store.  Shared memory is one in-order pipeline per SM, accesses of one warp are performed in
+// program order (a __syncwarp() separates the lanes' ring stores from lane 0's counter store), and the reader's ring load
+// is issued after its counter load has returned.
+__device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v)
 {
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
-    return v;
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p)
 {
@@ -71,7 +87,18 @@ struct Producer {
         st_volatile_v2(&q->e[issued % RQ_N], (clr & 0xFFFFFFu) | (type << 24) | ((gen & 31u) << 27), n | ((gen & 0xFFFFu) << 16));
         issued++;
     }
-    __device__ __forceinline__ void drain() { while (ld_acquire(&q->done) != issued) {} seen_done = issued; }
+    // the same without a branch: the entry is written to the next slot either way (harmless: its generation bits make it valid
+    // only once `issued` has moved past it) and `issued` advances only for n > 0
+    __device__ __forceinline__ void push_if(bool yes, uint32_t type, uint32_t n, uint32_t clr)
+    {
+        const uint32_t gen = issued / RQ_N + 1u;
+        const uint32_t g0 = yes ? gen : gen - 1u;                                // a skipped entry keeps the slot's OLD generation
+        st_volatile_v2(&q->e[issued % RQ_N], (clr & 0xFFFFFFu) | (type << 24) | ((g0 & 31u) << 27), n | ((g0 & 0xFFFFu) << 16));
+        issued += yes ? 1u : 0u;
+    }
+    __device__ __forceinline__ bool full() const { return issued - seen_done >= (uint32_t)RQ_N; }
+    __device__ __forceinline__ void wait_room() { while (full()) seen_done = ld_relaxed(&q->done); }
+    __device__ __forceinline__ void drain() { while (ld_relaxed(&q->done) != issued) {} seen_done = issued; }
 };
 
 // ---- warp 1: pixel reconstruction (ScreenPressor.hx:242-273) -------------------------------------------------------
@@ -83,40 +110,47 @@ __device__ __forceinline__ void sp2_recon_iframe(RunQueue *q, const SpJob &J, ui
     const int chunk = X < 32 ? (int)X : 32;          // a chunk never reads pixels it writes itself (the row above is X away)
     long di = 0;
     uint32_t lastval = 0, consumed = 0;
+    P2_DECL
+#ifdef JSP_SP2_PROF
+    const long long _r0 = clock64();
+#endif
     for (;;) {
         const uint32_t gen = consumed / RQ_N + 1u;
         uint2 e;
         do { e = ld_volatile_v2(&q->e[consumed % RQ_N]); } while (((e.x >> 27) != (gen & 31u)) || ((e.y >> 16) != (gen & 0xFFFFu)));
+        P2_T(8)
         const uint32_t type = (e.x >> 24) & 7u, clr = e.x & 0xFFFFFFu;
         const int n = (int)(e.y & 0xFFFFu);
         if (type == RQ_END) break;
         for (int o = 0; o < n; o += chunk) {
             const int m = n - o < chunk ? n - o : chunk;
             const long s = di + o, idx = s + lane;
+            // every predictor's inputs are loaded (5 independent shared-memory reads), the type only selects: no branches.
+            //   above[i] = ring[i - X], aboveleft[i] = ring[i - X - 1];  `e` = the chunk's last pixel
+            const uint32_t ab = ring[(uint32_t)(idx - X) & rmask], al = ring[(uint32_t)(idx - X - 1) & rmask];
+            const uint32_t ab_e = ring[(uint32_t)(s + m - 1 - X) & rmask], al_e = ring[(uint32_t)(s + m - 2 - X) & rmask];
+            const uint32_t al_s = ring[(uint32_t)(s - 1 - X) & rmask];
+            // predictor 4: p[i] = p[i-1] + above[i] - aboveleft[i] per byte and aboveleft[i] = above[i-1], so the sum telescopes to
+            // p[i] = p[s-1] + above[i] - above[s-1] -- no scan along the run
+            const uint32_t g = vadd4(lastval, vsub4(ab, al_s)) & 0x00FFFFFFu, g_e = vadd4(lastval, vsub4(ab_e, al_s)) & 0x00FFFFFFu;
             uint32_t v = clr, last = clr;
-            switch (type) {
-            case 1: v = last = lastval; break;
-            case 2: v = ring[(uint32_t)(idx - X) & rmask]; last = ring[(uint32_t)(s + m - 1 - X) & rmask]; break;
-            case 5: v = ring[(uint32_t)(idx - X - 1) & rmask]; last = ring[(uint32_t)(s + m - 2 - X) & rmask]; break;
-            case 4: {
-                // p[i] = p[i-1] + above[i] - aboveleft[i] per byte and aboveleft[i] = above[i-1]: the sum telescopes to
-                // p[i] = p[s-1] + above[i] - above[s-1] -- no scan along the run
-                const uint32_t a0 = ring[(uint32_t)(s - 1 - X) & rmask];
-                v = vadd4(lastval, vsub4(ring[(uint32_t)(idx - X) & rmask], a0)) & 0x00FFFFFFu;
-                last = vadd4(lastval, vsub4(ring[(uint32_t)(s + m - 1 - X) & rmask], a0)) & 0x00FFFFFFu;
-                break;
-            }
-            default: break;
-            }
-            __syncwarp();                                  // every lane has read the ring before slots are overwritten
+            v = type == 1 ? lastval : v;  last = type == 1 ? lastval : last;
+            v = type == 2 ? ab : v;       last = type == 2 ? ab_e : last;
+            v = type == 5 ? al : v;       last = type == 5 ? al_e : last;
+            v = type == 4 ? g : v;        last = type == 4 ? g_e : last;
             if (lane < m && idx < end) { dst[idx] = (int32_t)v; ring[(uint32_t)idx & rmask] = v; }
             lastval = last;
-            __syncwarp();
+            __syncwarp();                                  // the next chunk / run may read what other lanes just wrote
         }
         di += n;
         consumed++;
-        if (lane == 0) st_release(&q->done, consumed);
+        if (lane == 0) st_relaxed(&q->done, consumed);
+        P2_T(9)
     }
+#ifdef JSP_SP2_PROF
+    _p2[10] = clock64() - _r0;
+#endif
+    P2_FLUSH
 }
 
 // ---- warp 0: entropy decode of a coded I frame ---------------------------------------------------------------------
@@ -134,8 +168,8 @@ __device__ __forceinline__ void sp2_entropy_iframe(Coder &ec, Producer &pq, cons
     uint32_t clr = 0;
     auto decode_rgb = [&]() -> uint32_t {                 // ScreenPressor.hx:173-183
         uint32_t px = 0;
-#pragma unroll 1
-        for (int ch = 0; ch < 3; ch++) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {                 // unrolled: a loop's back edge costs a symbol ~40 cycles
             const int v = ec.decodeClr(sp_ctx_index(ec, ch, cx, cx1));
             cx1 = (cx << 6) & 0xFC0; cx = v >> cxshift;
             px += (uint32_t)v << (8 * ch);
@@ -155,23 +189,42 @@ __device__ __forceinline__ void sp2_entropy_iframe(Coder &ec, Producer &pq, cons
     int ptype = 0;
     bool clr_lazy = false;                                 // clr = the last pixel written so far; fetched from R when needed
     bool ctx_from_clr = false;                             // the contexts are recomputed from clr after every run of this loop (:274-275)
-    while (di < end) {                                     // :218-286
-        if (--budget < 0) ec.fail_frame();
+    P2_DECL
+#ifdef JSP_SP2_PROF
+    const long long _e0 = clock64();
+#endif
+    // :218-286.  Two branches per run: "colour follows" and the loop's back edge -- the rest is selects.  The run budget
+    // (a frame of zero-length runs must not spin for ever) is checked at the END of a run instead of before the next one:
+    // a failed coder decodes nothing more, so the result is the same.
+    if (di < end) for (;;) {
+        P2_T(11)
         ptype = ec.decodeP(ptype);
+        P2_T(0)
         if (ptype == 0) {
-            if (clr_lazy) { pq.drain(); clr = ring[(uint32_t)(di - 1) & rmask]; clr_lazy = false; }
+            if (clr_lazy) { pq.drain(); clr = ring[(uint32_t)(di - 1) & rmask]; clr_lazy = false; P2_T(4) }
             if (ctx_from_clr) { cx1 = ((int)clr & maskcx1) >> shiftcx1; cx = (int)clr >> shiftcx; }
             clr = decode_rgb();
+            P2_T(1) P2_C(7)
         }
         int n = ec.decodeN(ptype);
-        if (ec.failed()) return;
-        if (ptype == 3 || ptype > 5) n = 0;                // no such predictor in an I frame: nothing is written
-        if (ptype == 1) clr_lazy = true;                   // `clr = dst[lasti]` even for an empty run (:252)
-        else if (ptype != 0 && n > 0) clr_lazy = true;     // clr = the run's last pixel
-        if (n > 0) pq.push((uint32_t)ptype, (uint32_t)n, clr);
+        P2_T(2)
+        n = (ptype == 3 || ptype > 5) ? 0 : n;             // no such predictor in an I frame: nothing is written
+        // `clr = dst[lasti]` even for an empty run of predictor 1 (:252); otherwise clr = the run's last pixel
+        clr_lazy = clr_lazy | (ptype == 1) | (ptype != 0 && n > 0);
+        const bool put = n > 0 && !ec.failed();
+        if (pq.full()) pq.wait_room();
+        pq.push_if(put, (uint32_t)ptype, (uint32_t)n, clr);
         di += n;
         ctx_from_clr = true;
+        --budget;
+        P2_T(3) P2_C(6)
+        if (di >= end || ec.failed() || budget <= 0) break;  // round 1 checked `--budget < 0` before a run: same count
     }
+    if (budget <= 0 && di < end) ec.fail_frame();
+#ifdef JSP_SP2_PROF
+    _p2[5] = clock64() - _e0;
+#endif
+    P2_FLUSH
 }
 
 __global__ void __launch_bounds__(64)
@@ -182,7 +235,9 @@ sp2_rc_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
     extern __shared__ uint32_t ring[];                     // the last X + 1 pixels (power of two > X + 65 words)
     const SpJob J = jobs[blockIdx.x];
     const uint32_t rmask = sp_ring_size(J.X) - 1u;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the role as a warp-uniform value the compiler can SEE is uniform (a ballot result): a branch on threadIdx.x >> 5 makes it
+    // guard every warp collective below with a divergence check (BRA.DIV, ~12 cycles each on the symbol chain)
+    const int warp = __ballot_sync(0xffffffffu, threadIdx.x >= 32) ? 1 : 0, lane = threadIdx.x & 31;
     if (threadIdx.x < RQ_N) rq.e[threadIdx.x] = make_uint2(0u, 0u);
     if (threadIdx.x == 0) rq.done = 0;
     __syncthreads();
@@ -234,6 +289,16 @@ sp2_rc_p_kernel(const SpJob *__restrict__ jobs, uint32_t tile_words)
 }
 
 }  // namespace g2
+
+#ifdef JSP_SP2_PROF
+extern "C" __attribute__((visibility("default"))) int jsp_debug_sp2_profile(unsigned long long *out, int reset)
+{
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyFromSymbol(out, g2::g_sp2_prof, sizeof z) != cudaSuccess) return -1;
+    if (reset) cudaMemcpyToSymbol(g2::g_sp2_prof, z, sizeof z);
+    return 0;
+}
+#endif
 
 // ---- host side -----------------------------------------------------------------------------------------------------
 int sp_generation()

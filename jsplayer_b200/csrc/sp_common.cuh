@@ -147,9 +147,9 @@ __device__ __forceinline__ void sp_undo_frame(const SpJob &J, bool iframe)
 template <class Coder>
 __device__ __forceinline__ int sp_ctx_index(Coder &ec, int channel, int cx, int cx1)
 {
-    int i = cx + cx1;
-    if (i < 0 || i >= 4096) { ec.fail_frame(); i &= 4095; }
-    return channel * 4096 + i;
+    const int i = cx + cx1;
+    if ((unsigned)i >= 4096u) ec.fail_frame();     // (two selects, no branch: the index is on every colour symbol's chain)
+    return channel * 4096 + (i & 4095);
 }
 
 // Zero-length runs are legal syntax and cost almost no bits once their model has adapted, so a hostile stream could keep
