@@ -117,7 +117,12 @@ __device__ __forceinline__ void sp2_recon_iframe(RunQueue *q, const SpJob &J, ui
     for (;;) {
         const uint32_t gen = consumed / RQ_N + 1u;
         uint2 e;
-        do { e = ld_volatile_v2(&q->e[consumed % RQ_N]); } while (((e.x >> 27) != (gen & 31u)) || ((e.y >> 16) != (gen & 0xFFFFu)));
+        // poll with a short sleep: a tight spin competes with the entropy warps of this SM sub-partition for issue slots
+        for (;;) {
+            e = ld_volatile_v2(&q->e[consumed % RQ_N]);
+            if (((e.x >> 27) == (gen & 31u)) && ((e.y >> 16) == (gen & 0xFFFFu))) break;
+            __nanosleep(32);
+        }
         P2_T(8)
         const uint32_t type = (e.x >> 24) & 7u, clr = e.x & 0xFFFFFFu;
         const int n = (int)(e.y & 0xFFFFu);
@@ -161,7 +166,7 @@ __device__ __forceinline__ void sp2_entropy_iframe(Coder &ec, Producer &pq, cons
     const int cxshift = (J.flags & SPJ_CXSHIFT0) ? 0 : 2;
     int maskcx1 = 0xFC00, shiftcx1 = 4, shiftcx = 18;
     if (J.flags & SPJ_DIFF16) { maskcx1 = 0xFF00; shiftcx1 = 2; shiftcx = 16; }
-    ec.renewI();
+    ec.renewI(&reinterpret_cast<RcState *>(J.state)->small);      // the tables only P frames use are reset where they live: in HBM
     ec.decodeBegin(J.src, J.len, 1);
     int cx = 0, cx1 = 0;
     long di = 0, k = 0;
@@ -230,21 +235,33 @@ __device__ __forceinline__ void sp2_entropy_iframe(Coder &ec, Producer &pq, cons
 __global__ void __launch_bounds__(64)
 sp2_rc_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
 {
-    __shared__ RcShared shm;
+    __shared__ alignas(16) uint8_t shm_bytes[RC_SHARED_I_BYTES];   // RcShared without the tables only P frames use
     __shared__ RunQueue rq;
     extern __shared__ uint32_t ring[];                     // the last X + 1 pixels (power of two > X + 65 words)
+    RcShared *shm = reinterpret_cast<RcShared *>(shm_bytes);
     const SpJob J = jobs[blockIdx.x];
     const uint32_t rmask = sp_ring_size(J.X) - 1u;
-    // the role as a warp-uniform value the compiler can SEE is uniform (a ballot result): a branch on threadIdx.x >> 5 makes it
-    // guard every warp collective below with a divergence check (BRA.DIV, ~12 cycles each on the symbol chain)
-    const int warp = __ballot_sync(0xffffffffu, threadIdx.x >= 32) ? 1 : 0, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    // Which of the CTA's two warps decodes?  A warp runs on SM sub-partition (hardware warp id) % 4, a CTA's warps usually
+    // get ids 2k and 2k + 1, and the entropy warps are the ones that are issue-bound: if it were always the first warp, all of
+    // an SM's entropy warps would sit on sub-partitions 0 and 2 (measured: 427 cycles per symbol alone, 680 with 7 CTAs per
+    // SM).  So pair k takes its first warp if (k >> 1) is even and its second otherwise: sub-partitions 0, 2, 1, 3, 0, ...
+    __shared__ uint32_t s_wid[2];
+    uint32_t my_wid;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(my_wid));
+    if (lane == 0) s_wid[threadIdx.x >> 5] = my_wid;
     if (threadIdx.x < RQ_N) rq.e[threadIdx.x] = make_uint2(0u, 0u);
     if (threadIdx.x == 0) rq.done = 0;
     __syncthreads();
+    const uint32_t wa = s_wid[0], wb = s_wid[1];
+    const bool take_second = ((min(wa, wb) >> 2) & 1u) != 0, am_second = (wa != wb) ? my_wid == max(wa, wb) : threadIdx.x >= 32;
+    // the role as a warp-uniform value the compiler can SEE is uniform (a ballot result): a branch on anything derived from
+    // threadIdx makes it guard every warp collective below with a divergence check (BRA.DIV, ~12 cycles each on the chain)
+    const int warp = __ballot_sync(0xffffffffu, am_second == take_second) ? 0 : 1;       // 0 = entropy, 1 = reconstruction
     RcCoder ec;
     bool failed = false;
     if (warp == 0) {
-        ec.open(J, shm);
+        ec.open(J, shm, RC_SMALL_I_BYTES);
         Producer pq{&rq, 0u, 0u};
         sp2_entropy_iframe(ec, pq, J, ring, rmask);
         pq.push(RQ_END, 0u, 0u);
@@ -254,7 +271,7 @@ sp2_rc_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
     }
     __syncthreads();                                       // R has written every pixel E queued
     if (warp == 0) {
-        ec.close(J, shm);
+        ec.close(J, RC_SMALL_I_BYTES);
         uint32_t bits = ST_CHANGED;
         if (failed) { bits = ST_ERROR; sp_undo_frame(J, true); }
         if (lane == 0) { atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
@@ -274,11 +291,11 @@ sp2_rc_p_kernel(const SpJob *__restrict__ jobs, uint32_t tile_words)
     const SpJob J = jobs[blockIdx.x];
     uint32_t *ptile = tile_words >= SP_PTILE_WORDS ? ptile_mem : nullptr;
     RcCoder ec;
-    ec.open(J, shm);
+    ec.open(J, &shm, (uint32_t)sizeof(RcSmall));
     uint32_t bits = 0;
-    if (J.flags & SPJ_RENEW) ec.renewI();
+    if (J.flags & SPJ_RENEW) ec.renewI(&shm.small);
     else sp_decode_pframe(ec, J, bits, ptile);
-    ec.close(J, shm);
+    ec.close(J, (uint32_t)sizeof(RcSmall));
     if (ec.failed()) {
         bits = ST_ERROR;
         if (!(J.flags & SPJ_RENEW)) sp_undo_frame(J, false);

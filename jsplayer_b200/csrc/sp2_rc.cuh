@@ -89,17 +89,22 @@ constexpr int RC_ROWS = 3 * 4096;
 constexpr uint32_t RC_CLR_STEP = 400;                          // SC_STEP, EntroCoders.hx:43
 
 struct RcSmall {
-    RcBig<8> ntab[6], xxtab, ntab2;
+    RcBig<8> ntab[6];
+    RcTiny ptypetab[6];
+    // tables only P frames use: an I-frame kernel keeps them out of shared memory (it resets them directly in HBM)
+    RcBig<8> xxtab, ntab2;
     RcBig<16> mvtab[2];
-    RcTiny sxytab[4], ptypetab[6], bttab;
+    RcTiny sxytab[4], bttab;
 };
+constexpr uint32_t RC_SMALL_I_BYTES = (uint32_t)offsetof(RcSmall, xxtab);   // the part every frame type needs
 
-constexpr int RC_CACHE_ROWS = 12;                              // LRU cache of colour rows in shared memory
-struct RcShared {
-    RcSmall small;
+constexpr int RC_CACHE_ROWS = 10;                              // LRU cache of colour rows in shared memory
+struct RcShared {                                              // bitstream window and row cache first: their offsets do not depend
+    alignas(16) uint8_t win[256];                              // on how much of `small` a kernel keeps (two 128-byte halves, circular)
     RcBig<8> cache[RC_CACHE_ROWS];
-    alignas(16) uint8_t win[256];                              // bitstream window: two 128-byte halves, circular
+    RcSmall small;
 };
+constexpr uint32_t RC_SHARED_I_BYTES = (uint32_t)offsetof(RcShared, small) + RC_SMALL_I_BYTES;
 
 struct RcState {                                               // per stream, in HBM
     RcSmall small;
@@ -234,13 +239,14 @@ static __device__ __noinline__ int rc_row_miss(RcBig<8> *cache, uint32_t *rows, 
 
 struct RcCoder {
     static constexpr bool kCanDecodeBool = false;              // EntroCoders.hx:178
+    RcShared *shm;                                             // generic pointer (cold paths)
     RcSmall *sm;
     RcBig<8> *cache;
-    uint8_t *win;
-    uint32_t sm_a;                                             // shared-window address of the RcShared (= of its first member, `small`);
-                                                               // everything else is sm_a + a compile-time offset
+    uint32_t sm_a;                                             // shared-window address of the RcShared; everything else is sm_a + a
+                                                               // compile-time offset
     uint32_t lane4;                                            // 4 * lane
-    static constexpr uint32_t kCacheOff = (uint32_t)offsetof(RcShared, cache), kWinOff = (uint32_t)offsetof(RcShared, win);
+    static constexpr uint32_t kCacheOff = (uint32_t)offsetof(RcShared, cache), kWinOff = (uint32_t)offsetof(RcShared, win),
+                              kSmallOff = (uint32_t)offsetof(RcShared, small);
     int my_tag;                                                // lane < RC_CACHE_ROWS: context index held by slot `lane`, -1 = empty (and in lanes >= RC_CACHE_ROWS)
     uint32_t my_age, tick;
     uint32_t *rows;
@@ -317,14 +323,16 @@ struct RcCoder {
         __syncwarp();
         rc_refill_tiny(t.P, (uint32_t)N, step);
     }
-    __device__ __forceinline__ void renewI()                                     // EntroCoders.hx:81-130
+    // EntroCoders.hx:81-130.  p_only = where the tables only P frames use live: shared memory (P-frame kernel) or the stream's
+    // state in HBM (I-frame kernel, which does not stage them)
+    __device__ __forceinline__ void renewI(RcSmall *p_only)
     {
         gen = gen + 1;
         for (int t = 0; t < 6; t++) { init_big(sm->ntab[t], 400u); init_tiny<6>(sm->ptypetab[t], 1000u); }
-        init_big(sm->xxtab, 1u); init_big(sm->ntab2, 20u);
-        init_big(sm->mvtab[0], 100u); init_big(sm->mvtab[1], 100u);
-        for (int t = 0; t < 4; t++) init_tiny<16>(sm->sxytab[t], 100u);
-        init_tiny<5>(sm->bttab, 10u);
+        init_big(p_only->xxtab, 1u); init_big(p_only->ntab2, 20u);
+        init_big(p_only->mvtab[0], 100u); init_big(p_only->mvtab[1], 100u);
+        for (int t = 0; t < 4; t++) init_tiny<16>(p_only->sxytab[t], 100u);
+        init_tiny<5>(p_only->bttab, 10u);
         __syncwarp();
     }
 
@@ -372,7 +380,7 @@ struct RcCoder {
         const int lane = (int)lane_id();
         if (pos > lim) catch_up();
         nsym++;
-        uint32_t *P = reinterpret_cast<uint32_t *>(sm) + ((ta - sm_a) >> 2);
+        uint32_t *P = reinterpret_cast<uint32_t *>(shm) + ((ta - sm_a) >> 2);
         const uint32_t p = P[lane], cnt = P[29], tot = P[30], inv = P[31];
         const uint32_t r = udiv1(range, tot, inv);
         const uint32_t pr = p * r;
@@ -440,7 +448,7 @@ struct RcCoder {
         const int lane = (int)lane_id();
         if (pos > lim) catch_up();
         nsym++;
-        uint32_t *tab = reinterpret_cast<uint32_t *>(sm) + ((ta - sm_a) >> 2);
+        uint32_t *tab = reinterpret_cast<uint32_t *>(shm) + ((ta - sm_a) >> 2);
         const uint32_t base = tab[32 * K + lane], tot = tab[32 * K + 32], tag = tab[32 * K + 33], inv = tab[32 * K + 34], cnt = tab[32 * K + 35];
         const uint32_t r = udiv1(range, tot, inv);
         const uint32_t br = base * r;
@@ -494,46 +502,46 @@ struct RcCoder {
         __syncwarp();
     }
 
-    __device__ __forceinline__ uint32_t small_a(const void *t) const { return sm_a + (uint32_t)(reinterpret_cast<const char *>(t) - reinterpret_cast<const char *>(sm)); }
     __device__ __forceinline__ int decodeClr(int cxi)                            // DecodeValUni, RangeCoder.hx:82-130, on a cached colour row
     {
         const uint32_t slot = row_lookup(cxi);
         const bool miss = slot >= (uint32_t)RC_CACHE_ROWS;
         return decode_big<8>(row_addr(miss ? 0u : slot), RC_CLR_STEP, miss ? cxi : -1);
     }
-    __device__ __forceinline__ int decodeN(int ptype) { return decode_big<8>(sm_a + (uint32_t)offsetof(RcSmall, ntab) + (uint32_t)ptype * (uint32_t)sizeof(RcBig<8>), 400u); }   // EntroCoders.hx:142-144
-    __device__ __forceinline__ int decodeP(int ptype) { return decode_tiny<6>(sm_a + (uint32_t)offsetof(RcSmall, ptypetab) + (uint32_t)ptype * (uint32_t)sizeof(RcTiny), 1000u); }
-    __device__ __forceinline__ int decodeX() { return decode_big<8>(sm_a + (uint32_t)offsetof(RcSmall, xxtab), 1u); }
-    __device__ __forceinline__ int decodeBT() { return decode_tiny<5>(sm_a + (uint32_t)offsetof(RcSmall, bttab), 10u); }
-    __device__ __forceinline__ int decodeBN() { return decode_big<8>(sm_a + (uint32_t)offsetof(RcSmall, ntab2), 20u); }
-    __device__ __forceinline__ int decodeSXY(int n) { return decode_tiny<16>(sm_a + (uint32_t)offsetof(RcSmall, sxytab) + (uint32_t)n * (uint32_t)sizeof(RcTiny), 100u); }
-    __device__ __forceinline__ int decodeMX() { return decode_big<16>(sm_a + (uint32_t)offsetof(RcSmall, mvtab), 100u); }
-    __device__ __forceinline__ int decodeMY() { return decode_big<16>(sm_a + (uint32_t)offsetof(RcSmall, mvtab) + (uint32_t)sizeof(RcBig<16>), 100u); }
+    __device__ __forceinline__ int decodeN(int ptype) { return decode_big<8>(sm_a + kSmallOff + (uint32_t)offsetof(RcSmall, ntab) + (uint32_t)ptype * (uint32_t)sizeof(RcBig<8>), 400u); }   // EntroCoders.hx:142-144
+    __device__ __forceinline__ int decodeP(int ptype) { return decode_tiny<6>(sm_a + kSmallOff + (uint32_t)offsetof(RcSmall, ptypetab) + (uint32_t)ptype * (uint32_t)sizeof(RcTiny), 1000u); }
+    __device__ __forceinline__ int decodeX() { return decode_big<8>(sm_a + kSmallOff + (uint32_t)offsetof(RcSmall, xxtab), 1u); }
+    __device__ __forceinline__ int decodeBT() { return decode_tiny<5>(sm_a + kSmallOff + (uint32_t)offsetof(RcSmall, bttab), 10u); }
+    __device__ __forceinline__ int decodeBN() { return decode_big<8>(sm_a + kSmallOff + (uint32_t)offsetof(RcSmall, ntab2), 20u); }
+    __device__ __forceinline__ int decodeSXY(int n) { return decode_tiny<16>(sm_a + kSmallOff + (uint32_t)offsetof(RcSmall, sxytab) + (uint32_t)n * (uint32_t)sizeof(RcTiny), 100u); }
+    __device__ __forceinline__ int decodeMX() { return decode_big<16>(sm_a + kSmallOff + (uint32_t)offsetof(RcSmall, mvtab), 100u); }
+    __device__ __forceinline__ int decodeMY() { return decode_big<16>(sm_a + kSmallOff + (uint32_t)offsetof(RcSmall, mvtab) + (uint32_t)sizeof(RcBig<16>), 100u); }
     __device__ __forceinline__ bool decodeBool() { return false; }
 
-    // ---- per-frame set-up / tear-down: the small tables travel between the stream's state in HBM and shared memory ----
-    __device__ __forceinline__ void open(const SpJob &J, RcShared &shm)
+    // ---- per-frame set-up / tear-down: `bytes` of the small tables (all of them, or the part I frames use) travel between
+    //      the stream's state in HBM and shared memory ----
+    __device__ __forceinline__ void open(const SpJob &J, RcShared *shared, uint32_t bytes)
     {
         RcState *st = reinterpret_cast<RcState *>(J.state);
-        sm = &shm.small; cache = shm.cache; win = shm.win;
-        sm_a = smem_addr(&shm);
+        shm = shared; sm = &shared->small; cache = shared->cache;
+        sm_a = smem_addr(shared);
         asm volatile("mov.u32 %0, %0;" : "+r"(sm_a));        // opaque: or the compiler re-derives the address (S2R + LEA, ~25 cycles) at every use
         lane4 = 4u * lane_id();
         my_tag = -1; my_age = 0; tick = 0;
         rows = st->rows; gen = st->gen;
         fail = false; range = 0; code = 0; data = J.src; len = J.len; pos = 0; lim = 0; w0 = 0; w1 = 0; pre = 0; nsym = 0;
         const uint4 *g = reinterpret_cast<const uint4 *>(&st->small);
-        uint4 *s = reinterpret_cast<uint4 *>(&shm.small);
-        for (int i = (int)lane_id(); i < (int)(sizeof(RcSmall) / 16); i += 32) s[i] = g[i];
+        uint4 *s = reinterpret_cast<uint4 *>(&shared->small);
+        for (int i = (int)lane_id(); i < (int)(bytes / 16); i += 32) s[i] = g[i];
         __syncwarp();
     }
-    __device__ __forceinline__ void close(const SpJob &J, RcShared &shm)
+    __device__ __forceinline__ void close(const SpJob &J, uint32_t bytes)
     {
         RcState *st = reinterpret_cast<RcState *>(J.state);
         flush_rows();
         uint4 *g = reinterpret_cast<uint4 *>(&st->small);
-        const uint4 *s = reinterpret_cast<const uint4 *>(&shm.small);
-        for (int i = (int)lane_id(); i < (int)(sizeof(RcSmall) / 16); i += 32) g[i] = s[i];
+        const uint4 *s = reinterpret_cast<const uint4 *>(sm);
+        for (int i = (int)lane_id(); i < (int)(bytes / 16); i += 32) g[i] = s[i];
         if (lane_id() == 0) st->gen = gen;
     }
 };
