@@ -268,8 +268,9 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
         {
             auto rc_end = std::stable_partition(order.begin(), order.end(), [&](int64_t x) { return b->sp_hosts[b->frames[x].stream].version <= 2; });
             std::stable_partition(order.begin(), rc_end, [&](int64_t x) { return b->frames[x].kind == FK_SP_I; });
+            std::stable_partition(rc_end, order.end(), [&](int64_t x) { return b->frames[x].kind == FK_SP_I; });
         }
-        int n_rc_i = 0;
+        int n_rc_i = 0, n_ans_i = 0;
         for (int64_t f : order) {
             const FrameRec &R = b->frames[f];
             if (R.kind != FK_SP_I && R.kind != FK_SP_P && !(R.kind == FK_SP_FLAT && (R.sp_flags & SPJ_RENEW))) continue;
@@ -288,7 +289,7 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             J.X = (uint32_t)S.w; J.Y = (uint32_t)S.h; J.flags = R.sp_flags | (H.version > 2 ? SPJ_ANS : 0u);
             J.insign_blocks = (uint32_t)(((S.w + 15) / 16) * ((std::max(0, b->insign_lines) + 15) / 16));
             (H.version > 2 ? n_ans : n_rc)++;
-            if (H.version <= 2 && R.kind == FK_SP_I) n_rc_i++;
+            if (R.kind == FK_SP_I) (H.version <= 2 ? n_rc_i : n_ans_i)++;
             max_w = std::max(max_w, J.X);
             T.spjobs.push_back(J);
             if (R.kind != FK_SP_FLAT) fin.push_back(f);
@@ -296,7 +297,7 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
         if (T.spjobs.size() > first) {
             const int kclass = n_ans == 0 ? JSP_K_SP_ENTROPY_RC : (n_rc == 0 ? JSP_K_SP_ENTROPY_ANS : JSP_K_SP_ENTROPY_MIXED);
             Launch L{kclass, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), max_w, (uint32_t)ticket_cursor};
-            L.n_rc = (uint32_t)n_rc; L.n_rc_i = (uint32_t)n_rc_i;
+            L.n_rc = (uint32_t)n_rc; L.n_rc_i = (uint32_t)n_rc_i; L.n_ans_i = (uint32_t)n_ans_i;
             ticket_cursor += 2;
             plan.launches.push_back(L);
             plan.finished.push_back(std::move(fin));
@@ -409,7 +410,7 @@ template <class F> static bool run_plan_with(jsp_batch *b, const Plan &P, cudaSt
             break;
         case JSP_K_SP_ENTROPY_RC: case JSP_K_SP_ENTROPY_ANS: case JSP_K_SP_ENTROPY_MIXED:
             if (sp_generation() < 2 ||
-                !launch_sp2_level(b->d_spjobs + L.first, L.n_rc_i, L.n_rc - L.n_rc_i, L.count - L.n_rc, L.max_vec4, b->d_tickets + L.ticket, st))
+                !launch_sp2_level(b->d_spjobs + L.first, L.n_rc_i, L.n_rc - L.n_rc_i, L.n_ans_i, L.count - L.n_rc - L.n_ans_i, L.max_vec4, st))
                 launch_sp_decode(b->d_spjobs + L.first, L.count, L.max_vec4, L.n_rc, b->d_tickets + L.ticket, st);
             break;
         default: break;

@@ -48,7 +48,7 @@ void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, 
 int sp_generation();
 size_t sp2_rc_state_bytes();
 void sp2_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t st);
-bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_rc_p, uint32_t n_ans, uint32_t max_width, uint32_t *d_queue, cudaStream_t st);
+bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_rc_p, uint32_t n_ans_i, uint32_t n_ans_p, uint32_t max_width, cudaStream_t st);
 
 struct StreamRec {
     int codec, w, h, bpp;
@@ -86,7 +86,7 @@ struct Launch {
     uint32_t max_vec4;              // copy jobs: largest job
     uint32_t ticket;                // ticket counter slot (MSVideo1 tiles; two job queues of a mixed ScreenPressor launch)
     uint32_t n_rc = 0;              // ScreenPressor: the first n_rc jobs are range-coder frames
-    uint32_t n_rc_i = 0;            // ... of which the first n_rc_i are coded I frames (second-generation kernels: sp2_decode.cu)
+    uint32_t n_rc_i = 0, n_ans_i = 0;   // ... and each coder's jobs start with its coded I frames (second-generation kernels: sp2_decode.cu)
 };
 
 struct CopyRange { const uint8_t *h; size_t d_off; size_t bytes; };

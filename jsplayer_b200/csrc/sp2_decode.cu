@@ -18,6 +18,7 @@
 // Separate kernels per (coder, frame type) keep each hot loop small: round 1's single kernel held both coders and both
 // frame loops in 68 000 instructions (1.1 MB of SASS) against a 32 KB L1.5 instruction cache.
 #include "sp2_rc.cuh"
+#include "sp_ans.cuh"
 #include <atomic>
 
 namespace jsp {
@@ -101,6 +102,28 @@ struct Producer {
     __device__ __forceinline__ void drain() { while (ld_relaxed(&q->done) != issued) {} seen_done = issued; }
 };
 
+// Which of the CTA's two warps decodes?  A warp runs on SM sub-partition (hardware warp id) % 4, a CTA's warps usually get
+// ids 2k and 2k + 1, and the entropy warps are the ones that are issue-bound: if it were always the first warp, all of an
+// SM's entropy warps would sit on sub-partitions 0 and 2 (measured: 427 cycles per symbol alone, 680 with 7 CTAs per SM,
+// 608 with this).  So pair k takes its first warp if (k >> 1) is even and its second otherwise: sub-partitions 0, 2, 1, 3, ...
+// Also clears the run queue.  Returns 0 for the entropy warp, 1 for the reconstruction warp -- as a ballot result, i.e. a
+// value the compiler can SEE is warp-uniform: a branch on anything derived from threadIdx makes it guard every warp
+// collective below with a divergence check (BRA.DIV, ~12 cycles each on the symbol chain).
+__device__ __forceinline__ int sp2_pick_roles(RunQueue *rq)
+{
+    __shared__ uint32_t s_wid[2];
+    const int lane = threadIdx.x & 31;
+    uint32_t my_wid;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(my_wid));
+    if (lane == 0) s_wid[threadIdx.x >> 5] = my_wid;
+    if (threadIdx.x < RQ_N) rq->e[threadIdx.x] = make_uint2(0u, 0u);
+    if (threadIdx.x == 0) rq->done = 0;
+    __syncthreads();
+    const uint32_t wa = s_wid[0], wb = s_wid[1];
+    const bool take_second = ((min(wa, wb) >> 2) & 1u) != 0, am_second = (wa != wb) ? my_wid == max(wa, wb) : threadIdx.x >= 32;
+    return __ballot_sync(0xffffffffu, am_second == take_second) ? 0 : 1;
+}
+
 // ---- warp 1: pixel reconstruction (ScreenPressor.hx:242-273) -------------------------------------------------------
 __device__ __forceinline__ void sp2_recon_iframe(RunQueue *q, const SpJob &J, uint32_t *ring, uint32_t rmask)
 {
@@ -166,7 +189,7 @@ __device__ __forceinline__ void sp2_entropy_iframe(Coder &ec, Producer &pq, cons
     const int cxshift = (J.flags & SPJ_CXSHIFT0) ? 0 : 2;
     int maskcx1 = 0xFC00, shiftcx1 = 4, shiftcx = 18;
     if (J.flags & SPJ_DIFF16) { maskcx1 = 0xFF00; shiftcx1 = 2; shiftcx = 16; }
-    ec.renewI(&reinterpret_cast<RcState *>(J.state)->small);      // the tables only P frames use are reset where they live: in HBM
+    ec.begin_iframe(J);                                    // model reset (EntroCoders.hx:81-130 / :216-227)
     ec.decodeBegin(J.src, J.len, 1);
     int cx = 0, cx1 = 0;
     long di = 0, k = 0;
@@ -242,22 +265,7 @@ sp2_rc_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
     const SpJob J = jobs[blockIdx.x];
     const uint32_t rmask = sp_ring_size(J.X) - 1u;
     const int lane = threadIdx.x & 31;
-    // Which of the CTA's two warps decodes?  A warp runs on SM sub-partition (hardware warp id) % 4, a CTA's warps usually
-    // get ids 2k and 2k + 1, and the entropy warps are the ones that are issue-bound: if it were always the first warp, all of
-    // an SM's entropy warps would sit on sub-partitions 0 and 2 (measured: 427 cycles per symbol alone, 680 with 7 CTAs per
-    // SM).  So pair k takes its first warp if (k >> 1) is even and its second otherwise: sub-partitions 0, 2, 1, 3, 0, ...
-    __shared__ uint32_t s_wid[2];
-    uint32_t my_wid;
-    asm volatile("mov.u32 %0, %%warpid;" : "=r"(my_wid));
-    if (lane == 0) s_wid[threadIdx.x >> 5] = my_wid;
-    if (threadIdx.x < RQ_N) rq.e[threadIdx.x] = make_uint2(0u, 0u);
-    if (threadIdx.x == 0) rq.done = 0;
-    __syncthreads();
-    const uint32_t wa = s_wid[0], wb = s_wid[1];
-    const bool take_second = ((min(wa, wb) >> 2) & 1u) != 0, am_second = (wa != wb) ? my_wid == max(wa, wb) : threadIdx.x >= 32;
-    // the role as a warp-uniform value the compiler can SEE is uniform (a ballot result): a branch on anything derived from
-    // threadIdx makes it guard every warp collective below with a divergence check (BRA.DIV, ~12 cycles each on the chain)
-    const int warp = __ballot_sync(0xffffffffu, am_second == take_second) ? 0 : 1;       // 0 = entropy, 1 = reconstruction
+    const int warp = sp2_pick_roles(&rq);                  // 0 = entropy, 1 = reconstruction
     RcCoder ec;
     bool failed = false;
     if (warp == 0) {
@@ -305,6 +313,65 @@ sp2_rc_p_kernel(const SpJob *__restrict__ jobs, uint32_t tile_words)
     sp_signal_done(J);
 }
 
+
+// ---- rANS streams (v3 / v4): the same two kernels on round 1's coder (sp_ans.cuh) ----
+__global__ void __launch_bounds__(64)
+sp2_ans_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
+{
+    __shared__ AnsShared shm;
+    __shared__ RunQueue rq;
+    extern __shared__ uint32_t ring[];
+    const SpJob J = jobs[blockIdx.x];
+    const uint32_t rmask = sp_ring_size(J.X) - 1u;
+    const int lane = threadIdx.x & 31;
+    const int warp = sp2_pick_roles(&rq);
+    AnsCoder ec;
+    bool failed = false;
+    if (warp == 0) {
+        ec.open(J, shm);
+        Producer pq{&rq, 0u, 0u};
+        sp2_entropy_iframe(ec, pq, J, ring, rmask);
+        pq.push(RQ_END, 0u, 0u);
+        failed = ec.failed();
+    } else {
+        sp2_recon_iframe(&rq, J, ring, rmask);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        ec.close(J);
+        uint32_t bits = ST_CHANGED;
+        if (failed) { bits = ST_ERROR; sp_undo_frame(J, true); }
+        if (lane == 0) { atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
+    }
+    if (J.done) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t *>(J.done) = 1u;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+sp2_ans_p_kernel(const SpJob *__restrict__ jobs, uint32_t tile_words)
+{
+    __shared__ AnsShared shm;
+    extern __shared__ uint32_t ptile_mem[];
+    const SpJob J = jobs[blockIdx.x];
+    uint32_t *ptile = tile_words >= SP_PTILE_WORDS ? ptile_mem : nullptr;
+    AnsCoder ec;
+    ec.open(J, shm);
+    uint32_t bits = 0;
+    if (J.flags & SPJ_RENEW) ec.renewI();
+    else sp_decode_pframe(ec, J, bits, ptile);
+    ec.close(J);
+    if (ec.failed()) {
+        bits = ST_ERROR;
+        if (!(J.flags & SPJ_RENEW)) sp_undo_frame(J, false);
+    }
+    __syncwarp();
+    if (lane_id() == 0) { if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
+    sp_signal_done(J);
+}
+
 }  // namespace g2
 
 #ifdef JSP_SP2_PROF
@@ -337,8 +404,8 @@ void sp2_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t 
 
 namespace {
 struct DevAux {                                            // per device: side streams so that the kernels of one level overlap
-    cudaStream_t s[2] = {nullptr, nullptr};
-    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
     bool attr = false, ok = false;
 };
 DevAux g_aux[64];
@@ -353,13 +420,15 @@ DevAux *aux_for_current_device()
     if (!(g_aux_ready.load(std::memory_order_acquire) & bit)) {
         // one host thread drives a device (jsp_batch_decode: one thread per GPU), so no lock is needed per entry
         bool ok = true;
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 3; i++) {
             ok = ok && cudaStreamCreateWithFlags(&A.s[i], cudaStreamNonBlocking) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&A.join[i], cudaEventDisableTiming) == cudaSuccess;
         }
         ok = ok && cudaEventCreateWithFlags(&A.fork, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(g2::sp2_rc_i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(g2::sp2_rc_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(g2::sp2_ans_i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(g2::sp2_ans_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
         A.ok = ok;
         g_aux_ready.fetch_or(bit, std::memory_order_release);
     }
@@ -368,45 +437,35 @@ DevAux *aux_for_current_device()
 }  // namespace
 
 // Jobs of one dependency level, ordered by the planner: [range-coder I frames | range-coder P frames and model resets |
-// rANS frames].  The three groups run as three concurrent launches (the level lasts as long as its slowest frame).
-void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, uint32_t n_rc, uint32_t *d_queue, cudaStream_t st);
-bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_rc_p, uint32_t n_ans, uint32_t max_width, uint32_t *d_queue, cudaStream_t st)
+// rANS I frames | rANS P frames and model resets].  The groups run as concurrent launches (the level lasts as long as its
+// slowest frame).
+bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_rc_p, uint32_t n_ans_i, uint32_t n_ans_p, uint32_t max_width, cudaStream_t st)
 {
     DevAux *A = aux_for_current_device();
     uint32_t words = 1024;                                             // at least the P-frame block tile (SP_PTILE_WORDS)
     while (words <= max_width + 65u) words <<= 1;                      // >= sp_ring_size(max_width)
-    if (!A || words > 16384u) return false;                            // caller falls back to the first-generation kernel
-    const int groups = (n_rc_i ? 1 : 0) + (n_rc_p ? 1 : 0) + (n_ans ? 1 : 0);
+    if (!A || words > 8192u) return false;                             // caller falls back to the first-generation kernel
+    const uint32_t n[4] = {n_rc_i, n_rc_p, n_ans_i, n_ans_p};
+    int groups = 0;
+    for (int g = 0; g < 4; g++) groups += n[g] ? 1 : 0;
     const bool fork = groups > 1;
     if (fork) cudaEventRecord(A->fork, st);
-    int side = 0;
-    auto stream_for = [&](bool first) -> cudaStream_t {
-        if (first || !fork) return st;
-        cudaStream_t s = A->s[side];
-        cudaStreamWaitEvent(s, A->fork, 0);
-        return s;
-    };
-    auto joined = [&](cudaStream_t s) {
-        if (s == st) return;
-        cudaEventRecord(A->join[side], s);
-        cudaStreamWaitEvent(st, A->join[side], 0);
-        side++;
-    };
-    bool first = true;
-    if (n_rc_i) {
-        cudaStream_t s = stream_for(first); first = false;
-        g2::sp2_rc_i_kernel<<<n_rc_i, 64, (size_t)words * 4, s>>>(d_jobs, words);
-        joined(s);
-    }
-    if (n_rc_p) {
-        cudaStream_t s = stream_for(first); first = false;
-        g2::sp2_rc_p_kernel<<<n_rc_p, 32, (size_t)1024 * 4, s>>>(d_jobs + n_rc_i, 1024);
-        joined(s);
-    }
-    if (n_ans) {
-        cudaStream_t s = stream_for(first); first = false;
-        launch_sp_decode(d_jobs + n_rc_i + n_rc_p, n_ans, max_width, 0, nullptr, s);
-        joined(s);
+    int side = 0; bool first = true;
+    uint32_t off = 0;
+    for (int g = 0; g < 4; g++) {
+        if (!n[g]) continue;
+        cudaStream_t s = st;
+        if (!first) { s = A->s[side]; cudaStreamWaitEvent(s, A->fork, 0); }
+        const SpJob *jobs = d_jobs + off;
+        switch (g) {
+        case 0: g2::sp2_rc_i_kernel<<<n[g], 64, (size_t)words * 4, s>>>(jobs, words); break;
+        case 1: g2::sp2_rc_p_kernel<<<n[g], 32, (size_t)1024 * 4, s>>>(jobs, 1024); break;
+        case 2: g2::sp2_ans_i_kernel<<<n[g], 64, (size_t)words * 4, s>>>(jobs, words); break;
+        default: g2::sp2_ans_p_kernel<<<n[g], 32, (size_t)1024 * 4, s>>>(jobs, 1024); break;
+        }
+        if (!first) { cudaEventRecord(A->join[side], s); cudaStreamWaitEvent(st, A->join[side], 0); side++; }
+        first = false;
+        off += n[g];
     }
     return true;
 }

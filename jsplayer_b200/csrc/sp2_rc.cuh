@@ -336,6 +336,9 @@ struct RcCoder {
         __syncwarp();
     }
 
+    // I-frame kernel: the tables only P frames use are reset where they live, in the stream's state in HBM
+    __device__ __forceinline__ void begin_iframe(const SpJob &J) { renewI(&reinterpret_cast<RcState *>(J.state)->small); }
+
     // number of renormalisation bytes: `while (range < TOP) range <<= 8` runs once per leading zero byte (3 compares beat clz)
     static __device__ __forceinline__ uint32_t renorm_bytes(uint32_t width)
     {

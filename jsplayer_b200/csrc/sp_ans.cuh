@@ -198,21 +198,21 @@ __device__ __forceinline__ int scale_shift(int tot, int &scaled)      // `while 
     scaled = tot;
     return shift;
 }
-__device__ void insort(uint8_t *a, int n)                             // Sorter.insort, ANS.hx:862-872
+static __device__ void insort(uint8_t *a, int n)                             // Sorter.insort, ANS.hx:862-872
 {
     for (int i = 1; i < n; i++) {
         int j = i;
         while (j > 0 && a[j - 1] > a[j]) { const uint8_t t = a[j]; a[j] = a[j - 1]; a[j - 1] = t; j--; }
     }
 }
-__device__ void fill_dec(uint8_t *dec, int i, int cf, int fr)
+static __device__ void fill_dec(uint8_t *dec, int i, int cf, int fr)
 {
     const int k0 = (cf + 127) >> 7, k1 = ((cf + fr - 1) >> 7) + 1;
     for (int k = k0; k < k1; k++) if (k >= 0 && k < 32) dec[k] = (uint8_t)i;
 }
 
 // SmallContext.create, :226-238 -- the Cx1 list is in B[0..d)
-__device__ void sc_create(CxHdr &H, uint8_t *B, int S, int c)
+static __device__ void sc_create(CxHdr &H, uint8_t *B, int S, int c)
 {
     const int d = H.d;
     uint16_t *fq = u16p(B, B_SC_FR);
@@ -224,14 +224,14 @@ __device__ void sc_create(CxHdr &H, uint8_t *B, int S, int c)
         if (B[i] == c) { fq[i] = 100; H.maxpos = (uint8_t)i; } else fq[i] = 50;
     }
 }
-__device__ void sc_rescale(CxHdr &H, uint8_t *B, int &totFr)          // :254-261
+static __device__ void sc_rescale(CxHdr &H, uint8_t *B, int &totFr)          // :254-261
 {
     uint16_t *fq = u16p(B, B_SC_FR);
     int s = 256 - H.d;
     for (int i = 0; i < H.d; i++) { fq[i] = (uint16_t)(fq[i] - (fq[i] >> 1)); s += fq[i]; }
     totFr = s;
 }
-__device__ bool sc_add(CxHdr &H, uint8_t *B, int pos, int c, int &totFr)   // addSymb, :240-252
+static __device__ bool sc_add(CxHdr &H, uint8_t *B, int pos, int c, int &totFr)   // addSymb, :240-252
 {
     if (H.d == H.S) return false;
     uint16_t *fq = u16p(B, B_SC_FR);
@@ -243,7 +243,7 @@ __device__ bool sc_add(CxHdr &H, uint8_t *B, int pos, int c, int &totFr)   // ad
     return true;
 }
 // SmallContext.decodeSC, :263-309
-__device__ bool sc_decode(CxHdr &H, uint8_t *B, int someFreq, CxRes &r, int totFr0, int &totFr)
+static __device__ bool sc_decode(CxHdr &H, uint8_t *B, int someFreq, CxRes &r, int totFr0, int &totFr)
 {
     uint16_t *fq = u16p(B, B_SC_FR);
     totFr = totFr0;
@@ -284,7 +284,7 @@ __device__ bool sc_decode(CxHdr &H, uint8_t *B, int someFreq, CxRes &r, int totF
     r.cum = someFreq << shift; r.freq = 1 << shift;
     return sc_add(H, B, pos, r.c, totFr);
 }
-__device__ void c5_calcsum(CxHdr &H, uint8_t *B)                      // :374-378
+static __device__ void c5_calcsum(CxHdr &H, uint8_t *B)                      // :374-378
 {
     const uint16_t *fq = u16p(B, B_SC_FR);
     int t = 256 - H.d;
@@ -292,7 +292,7 @@ __device__ void c5_calcsum(CxHdr &H, uint8_t *B)                      // :374-37
     H.cntsum = (uint32_t)t;
 }
 // Cx5.createFrom4, :350-372 (in place)
-__device__ void c5_from4(CxHdr &H, uint8_t *B, int c)
+static __device__ void c5_from4(CxHdr &H, uint8_t *B, int c)
 {
     uint16_t *fq = u16p(B, B_SC_FR);
     uint8_t os[4]; uint16_t of[4];
@@ -312,14 +312,14 @@ __device__ void c5_from4(CxHdr &H, uint8_t *B, int c)
 }
 
 // ---- Cx6 ----
-__device__ void c6_init(CxHdr &H, uint8_t *B, int S)
+static __device__ void c6_init(CxHdr &H, uint8_t *B, int S)
 {
     H.S = (uint8_t)S;
     uint32_t *w = reinterpret_cast<uint32_t *>(B);
     for (int i = 0; i < B6_BYTES / 4; i++) w[i] = 0;
     H.cntsum = 0;
 }
-__device__ void c6_calcsum(CxHdr &H, uint8_t *B)                      // :571-578
+static __device__ void c6_calcsum(CxHdr &H, uint8_t *B)                      // :571-578
 {
     const uint16_t *cn = u16p(B, B6_CNT);
     const int shft = H.fshift > 0 ? H.fshift - 1 : 0;
@@ -327,7 +327,7 @@ __device__ void c6_calcsum(CxHdr &H, uint8_t *B)                      // :571-57
     for (int i = 0; i < H.S; i++) sum += cn[i];
     H.cntsum = (uint32_t)sum & 0xFFFFu;
 }
-__device__ void c6_rescale(CxHdr &H, uint8_t *B, uint8_t *big)        // rescaleDec, :580-604
+static __device__ void c6_rescale(CxHdr &H, uint8_t *B, uint8_t *big)        // rescaleDec, :580-604
 {
     uint16_t *fr = u16p(B, B6_FR), *cm = u16p(B, B6_CUM), *cn = u16p(B, B6_CNT);
     uint16_t *_cnts = reinterpret_cast<uint16_t *>(big), *_cum = _cnts + 256;
@@ -348,7 +348,7 @@ __device__ void c6_rescale(CxHdr &H, uint8_t *B, uint8_t *big)        // rescale
     }
     H.cntsum = (uint32_t)cntsum & 0xFFFFu;
 }
-__device__ void c6_incr(CxHdr &H, uint8_t *B, uint8_t *big, int pos)  // incrCntDec, :680-696
+static __device__ void c6_incr(CxHdr &H, uint8_t *B, uint8_t *big, int pos)  // incrCntDec, :680-696
 {
     uint16_t *fr = u16p(B, B6_FR), *cm = u16p(B, B6_CUM), *cn = u16p(B, B6_CNT);
     const int step = 25 << H.fshift;
@@ -363,7 +363,7 @@ __device__ void c6_incr(CxHdr &H, uint8_t *B, uint8_t *big, int pos)  // incrCnt
     if ((int)H.cntsum + step > ANS_SCALE) c6_rescale(H, B, big);
 }
 // Cx6.createFrom5, :431-505 (in place: B holds the Cx5; c did not fit)
-__device__ void c6_from5(CxHdr &H, uint8_t *B, uint8_t *big, int c)
+static __device__ void c6_from5(CxHdr &H, uint8_t *B, uint8_t *big, int c)
 {
     uint8_t *os = big + 1024; uint16_t *of = reinterpret_cast<uint16_t *>(big + 1040);
     const int oldd = H.d;
@@ -418,7 +418,7 @@ __device__ void c6_from5(CxHdr &H, uint8_t *B, uint8_t *big, int c)
     H.kind = CXK_6;
 }
 // Cx6.createFrom2, :507-555 (B holds the Cx2 list; c was met the second time)
-__device__ void c6_from2(CxHdr &H, uint8_t *B, uint8_t *big, int c, int f0)
+static __device__ void c6_from2(CxHdr &H, uint8_t *B, uint8_t *big, int c, int f0)
 {
     const int oldd = H.d;
     uint8_t *ss = big + 1024;
@@ -453,7 +453,7 @@ __device__ void c6_from2(CxHdr &H, uint8_t *B, uint8_t *big, int c, int f0)
     }
     H.kind = CXK_6;
 }
-__device__ int c6_add(CxHdr &H, uint8_t *B, int c, int freq, int cum)     // addDec, :652-661
+static __device__ int c6_add(CxHdr &H, uint8_t *B, int c, int freq, int cum)     // addDec, :652-661
 {
     if (H.d >= 40 || H.d >= H.S) return -1;
     const int pos = H.d;
@@ -463,7 +463,7 @@ __device__ int c6_add(CxHdr &H, uint8_t *B, int c, int freq, int cum)     // add
     return pos;
 }
 // Cx6.decode, :606-650; false = the context must be upgraded to Cx7 (r.c is the symbol)
-__device__ bool c6_decode(CxHdr &H, uint8_t *B, uint8_t *big, int someFreq, CxRes &r)
+static __device__ bool c6_decode(CxHdr &H, uint8_t *B, uint8_t *big, int someFreq, CxRes &r)
 {
     const uint16_t *fr = u16p(B, B6_FR), *cm = u16p(B, B6_CUM);
     int lfreq = 0, lcum = 0, lowerSym = 0;
@@ -496,7 +496,7 @@ __device__ bool c6_decode(CxHdr &H, uint8_t *B, uint8_t *big, int someFreq, CxRe
 }
 
 // ---- Cx7 under construction in `big` (cumFreq @0, freq @512, cnts @1024), decTable in the header ----
-__device__ void c7_from3(CxHdr &H, uint8_t *B, uint8_t *big, int c)   // :711-739
+static __device__ void c7_from3(CxHdr &H, uint8_t *B, uint8_t *big, int c)   // :711-739
 {
     uint16_t *cm = reinterpret_cast<uint16_t *>(big), *fr = cm + 256, *cn = cm + 512;
     for (int i = 0; i < 256; i++) { fr[i] = 1; cn[i] = 1; }
@@ -518,7 +518,7 @@ __device__ void c7_from3(CxHdr &H, uint8_t *B, uint8_t *big, int c)   // :711-73
     H.cntsum = (uint32_t)cntsum;
     H.kind = CXK_7;
 }
-__device__ void c7_from6(CxHdr &H, uint8_t *B, uint8_t *big)          // :741-771
+static __device__ void c7_from6(CxHdr &H, uint8_t *B, uint8_t *big)          // :741-771
 {
     uint16_t *cm = reinterpret_cast<uint16_t *>(big), *fr = cm + 256, *cn = cm + 512;
     const uint16_t *fr6 = u16p(B, B6_FR), *cm6 = u16p(B, B6_CUM), *cn6 = u16p(B, B6_CNT);
@@ -543,7 +543,7 @@ __device__ void c7_from6(CxHdr &H, uint8_t *B, uint8_t *big)          // :741-77
 }
 
 enum { FOUND, ADDED, NOROOM };
-__device__ int find_or_add(CxHdr &H, uint8_t *B, int c, int cap)      // SymbList.findOrAdd, :163-171
+static __device__ int find_or_add(CxHdr &H, uint8_t *B, int c, int cap)      // SymbList.findOrAdd, :163-171
 {
     const int d = H.d;
     for (int i = 0; i < d; i++) if (B[i] == c) return FOUND;
@@ -963,6 +963,34 @@ struct AnsCoder {
         }
         count();
         return c;
+    }
+
+    // ---- per-frame set-up / tear-down for the second-generation kernels (sp2_decode.cu) ----
+    __device__ __forceinline__ void begin_iframe(const SpJob &) { renewI(); }
+    __device__ __forceinline__ void open(const SpJob &J, AnsShared &shared)
+    {
+        AnsState *st = reinterpret_cast<AnsState *>(J.state);
+        sm = &shared; hdrs = st->hdrs; bodies = st->bodies; gen = st->gen;
+        f0 = (J.flags & SPJ_ANS_V3) ? 64 : 32;                       // Cx6.f0, EntroCoders.hx:210 / ScreenPressor.hx:69-72
+        fail = false; overrun = false; x = 0; data = J.src; len = J.len; pos = 0; wbase = 0x80000000u; nDec = 0; nsym = 0;
+        my_tag = -1; my_age = 0; tick = 0;
+#ifdef JSP_PROFILE_SECTIONS
+        for (int k = 0; k < 16; k++) aprof[k] = 0;
+#endif
+        const uint4 *g = reinterpret_cast<const uint4 *>(&st->small);
+        uint4 *s = reinterpret_cast<uint4 *>(&shared.small);
+        for (int i = (int)lane_id(); i < (int)(sizeof(AnsSmall) / 16); i += 32) s[i] = g[i];
+        __syncwarp();
+    }
+    __device__ __forceinline__ void close(const SpJob &J)
+    {
+        AnsState *st = reinterpret_cast<AnsState *>(J.state);
+        flush_slots();
+        __syncwarp();
+        uint4 *g = reinterpret_cast<uint4 *>(&st->small);
+        const uint4 *s = reinterpret_cast<const uint4 *>(&sm->small);
+        for (int i = (int)lane_id(); i < (int)(sizeof(AnsSmall) / 16); i += 32) g[i] = s[i];
+        if (lane_id() == 0) st->gen = gen;
     }
 
     __device__ bool decodeBool()                                      // EntroCoders.hx:259-269
