@@ -92,6 +92,7 @@ class SPWorkload(Workload):
 
     def specs(self, rank, n=None):
         from jsplayer_b200 import StreamSpec, CodecType
+        import synth
         synth.load()
         n = self.n if n is None else n
         k = min(self.distinct, n)
@@ -128,6 +129,7 @@ class C5(Workload):
     def specs(self, rank, n=None):
         import tempfile
         from jsplayer_b200 import avi
+        import synth
         from synth.avi import write_avi
         synth.load()
         n = self.n if n is None else n

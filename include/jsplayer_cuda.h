@@ -40,6 +40,10 @@ JSP_API const char *jsp_version(void);
 /* pinned host memory for frame / bitstream buffers (what DataLoaderAVIIndexed's frame table holds) */
 JSP_API void *jsp_host_alloc(size_t bytes);
 JSP_API void  jsp_host_free(void *p);
+/* host topology helpers behind JSP_BATCH_NUMA_BIND: the NUMA node of a device (-1 = unknown or single node) and the bind itself
+ * for threads the caller owns (returns the node, -1 = nothing changed) */
+JSP_API int   jsp_numa_node_of_device(int device);
+JSP_API int   jsp_numa_bind_thread(int device);
 
 /* ---- per-stream drop-in: one stateful codec per stream, frames in order, host buffers ----
  * new MSVideo1_16bit(w,h) MSVideo1.hx:20-31 | new MSVideo1_8bit(w,h,palette) :267-274 |
@@ -82,6 +86,10 @@ typedef struct jsp_batch jsp_batch;
 
 enum {
     JSP_BATCH_SIGNIFICANCE = 1,  /* also compute PFrameResult.significant_changes exactly (extra previous-frame reads) */
+    JSP_BATCH_NUMA_BIND    = 2,  /* jsp_batch_create moves the CALLING thread to the CPUs of the device's NUMA node and prefers
+                                    that node for its later allocations (jsp_host_alloc from this thread): the staging memory of
+                                    the end-to-end path then sits next to the GPU's PCIe root.  No effect on a
+                                    single-node host or with JSP_NUMA_BIND=0 in the environment. */
 };
 
 /* Per-frame result flags written by jsp_batch_results(). */

@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(HERE, "libjsplayer_cuda.so")
 JSP_N_KERNELS = 8
 KERNEL_NAMES = ["msv1_decode", "frame_copy", "sp_entropy_rc", "sp_entropy_ans", "sp_recon", "signif", "sp_entropy_mixed", "k7"]
 JSP_BATCH_SIGNIFICANCE = 1
+JSP_BATCH_NUMA_BIND = 2
 JSP_FRAME_CHANGED, JSP_FRAME_SIGNIFICANT, JSP_FRAME_ERROR, JSP_FRAME_DIFFERS = 1, 2, 4, 8
 JSP_DISPLAY_FLIP = 1
 
@@ -36,6 +37,8 @@ PROTOTYPES = {
     "jsp_version": (C.c_char_p, []),
     "jsp_host_alloc": (C.c_void_p, [C.c_size_t]),
     "jsp_host_free": (None, [C.c_void_p]),
+    "jsp_numa_node_of_device": (C.c_int, [C.c_int]),
+    "jsp_numa_bind_thread": (C.c_int, [C.c_int]),
     "jsp_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "jsp_destroy": (None, [C.c_void_p]),
     "jsp_preinit": (None, [C.c_void_p, C.c_int]),

@@ -58,10 +58,13 @@ class PinnedBuffer:
 
 
 class BatchDecoder:
-    def __init__(self, device=-1, insignificant_lines=0, significance=False):
+    def __init__(self, device=-1, insignificant_lines=0, significance=False, numa_bind=False):
+        """numa_bind: move the calling thread (and the pinned buffers it allocates afterwards) to the device's NUMA node --
+        for one-process-per-GPU hosts (JSP_BATCH_NUMA_BIND)."""
         self._lib = _lib.require_gpu()
         self._h = self._lib.jsp_batch_create(int(device), int(insignificant_lines),
-                                             _lib.JSP_BATCH_SIGNIFICANCE if significance else 0)
+                                             (_lib.JSP_BATCH_SIGNIFICANCE if significance else 0) |
+                                             (_lib.JSP_BATCH_NUMA_BIND if numa_bind else 0))
         if not self._h:
             raise RuntimeError("jsp_batch_create failed: " + _lib.last_error())
         self._keep = []
@@ -163,8 +166,28 @@ class BatchDecoder:
                 ptrs[i] = a.ctypes.data
         return ptrs
 
-    def alloc_outputs(self, pinned=False):
+    def alloc_outputs(self, pinned=False, ring_bytes=0, keep_streams=()):
+        """Host pictures for download / decode_host.  ring_bytes > 0 (pinned only): a bounded ring instead of one buffer per
+        frame -- what a player does (Manager.hx:424-443 recycles 9 buffers): frame i lands in ring slot i mod R, so every byte
+        still crosses PCIe but the host keeps only the last R pictures; the frames of `keep_streams` get buffers of their own
+        (so they can be checked afterwards)."""
         shapes = self.frame_shapes()
+        if pinned and ring_bytes:
+            first = np.cumsum([0] + [sp.n_frames for sp in self.specs])
+            own = set()
+            for s in keep_streams:
+                own.update(range(int(first[s]), int(first[s + 1])))
+            biggest = max(h * w for h, w in shapes)
+            slots = max(2, int(ring_bytes) // (biggest * 4))
+            pb = PinnedBuffer((slots + len(own)) * biggest * 4, np.int32)
+            self._keep.append(pb)
+            outs, k, r = [], slots, 0
+            for i, (h, w) in enumerate(shapes):
+                if i in own:
+                    outs.append(pb.array[k * biggest:k * biggest + h * w].reshape(h, w)); k += 1
+                else:
+                    outs.append(pb.array[r * biggest:r * biggest + h * w].reshape(h, w)); r = (r + 1) % slots
+            return outs
         if pinned:
             total = sum(h * w for h, w in shapes)
             pb = PinnedBuffer(total * 4, np.int32)

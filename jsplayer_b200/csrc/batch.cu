@@ -527,6 +527,8 @@ jsp_batch *jsp_batch_create(int device, int insignificant_lines, int flags)
     if (device < 0) { if (!JSP_CUDA(cudaGetDevice(&device))) return nullptr; }
     if (device >= n) { set_error("device %d out of range (%d devices)", device, n); return nullptr; }
     if (!JSP_CUDA(cudaSetDevice(device))) return nullptr;
+    // the thread that drives this device, and the pinned buffers it allocates from here on, move to the device's NUMA node
+    if (flags & JSP_BATCH_NUMA_BIND) bind_thread_to_device(device);
     jsp_batch *b = new jsp_batch();
     b->device = device; b->insign_lines = insignificant_lines; b->flags = flags;
     cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -1193,7 +1195,8 @@ int jsp_batch_decode(const jsp_stream_desc *streams, int n_streams, int n_gpus, 
             for (int f = 0; f < streams[s].n_frames; f++) { outs.push_back(out_frames ? out_frames[first[s] + f] : nullptr); gidx.push_back(first[s] + f); }
         }
         if (sd.empty()) return;
-        jsp_batch *b = jsp_batch_create(g, 0, JSP_BATCH_SIGNIFICANCE);
+        // with several GPUs every device has its own host thread (created below), which may be moved to the device's NUMA node
+        jsp_batch *b = jsp_batch_create(g, 0, JSP_BATCH_SIGNIFICANCE | (n_gpus > 1 ? JSP_BATCH_NUMA_BIND : 0));
         std::vector<uint8_t> fl(outs.size());
         if (!b || jsp_batch_configure(b, sd.data(), (int)sd.size()) < 0 || jsp_batch_decode_host(b, outs.data(), fl.data())) {
             rc[g] = -1; errs[g] = jsp_last_error();
@@ -1209,8 +1212,8 @@ int jsp_batch_decode(const jsp_stream_desc *streams, int n_streams, int n_gpus, 
         catch (...) { rc[g] = -1; errs[g] = "unknown failure"; }
     };
     std::vector<std::thread> th;
-    for (int g = 1; g < n_gpus; g++) th.emplace_back(work, g);
-    work(0);
+    if (n_gpus == 1) work(0);                              // on the caller's thread, whose CPU affinity is left alone
+    else for (int g = 0; g < n_gpus; g++) th.emplace_back(work, g);
     for (auto &t : th) t.join();
     for (int g = 0; g < n_gpus; g++) if (rc[g]) { set_error("gpu %d: %s", g, errs[g].c_str()); return -1; }
     return 0;

@@ -45,6 +45,7 @@ size_t sp_ans_ctx_bytes();
 void sp_ans_state_init(void *d_state, void *d_ctx, uint32_t gen0, cudaStream_t st);
 void launch_sp_decode(const SpJob *d_jobs, uint32_t n_jobs, uint32_t max_width, uint32_t n_rc, uint32_t *d_queue, cudaStream_t st);   // sp_decode.cu: both coders, one launch
 // sp2_decode.cu: second-generation kernels (JSP_SP_GEN=1 in the environment selects the first generation for A/B runs)
+int bind_thread_to_device(int device);                     // numa_bind.cpp
 int sp_generation();
 size_t sp2_rc_state_bytes();
 void sp2_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t st);

@@ -36,6 +36,15 @@ constexpr u64 MAP_TERM  = 0xFull << 60;           // nibble 15 maps to 15: "chai
 constexpr u64 MAP_IDENT = 0x876543210ull | MAP_TERM;
 constexpr u64 ONES9     = 0x111111111ull;
 constexpr uint32_t TERM = 15;
+// Watchdog of the two look-back spins.  Forward progress is by construction (tickets hand tiles out in table order, so a
+// tile's predecessors are held by CTAs that are resident or finished and only ever wait for lower tickets), but a spin with no
+// bound would turn any future scheduling mistake into a silent hang of the stream.  A predecessor that has not published after
+// this many polls (seconds; a tile takes microseconds) fails the FRAME (ST_ERROR, nothing more is decoded into it) instead.
+// -DJSP_SPIN_LIMIT=n overrides (tests/test_msv1_gpu.py builds nothing special: the limit is always on).
+#ifndef JSP_SPIN_LIMIT
+#define JSP_SPIN_LIMIT (1u << 26)
+#endif
+constexpr uint32_t MSV1_SPIN_LIMIT = JSP_SPIN_LIMIT;
 
 __device__ __forceinline__ uint32_t nib(u64 m, uint32_t e) { return (uint32_t)(m >> (4 * e)) & 15u; }
 
@@ -375,12 +384,15 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
         if (tile + 1 < F.n_tiles) st_state(slot, aconst ? (FLAG_INCL | c) : (FLAG_AGG | (A & 0xFFFFFFFFFull)));
         // look back for this tile's entry offset
         uint32_t e0 = 0;
+        bool stalled = false;
         if (tile > 0) {
             u64 acc = MAP_IDENT;
             int j = (int)tile - 1;
             for (;;) {
                 u64 st;
-                do { st = ld_state(tile_map + F.state_base + j); } while ((st & FLAG_MASK) == 0);
+                uint32_t spins = 0;
+                do { st = ld_state(tile_map + F.state_base + j); } while ((st & FLAG_MASK) == 0 && ++spins < MSV1_SPIN_LIMIT);
+                if ((st & FLAG_MASK) == 0) { stalled = true; e0 = TERM; break; }      // watchdog: see MSV1_SPIN_LIMIT
                 if ((st & FLAG_MASK) == FLAG_INCL) { e0 = nib(acc, (uint32_t)st & 15u); break; }
                 acc = compose<NENT>((st & 0xFFFFFFFFFull) | MAP_TERM, acc);
                 uint32_t cc;
@@ -393,6 +405,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
         uint32_t e = e0;
         for (int w = 0; w < 4; w++) { sm.wentry[w] = e; e = nib(sm.wmap[w], e); }
         if (e0 == TERM) sm.terminated = 1;
+        if (stalled) atomicOr(F.status, ST_ERROR);
     }
     __syncthreads();
     if (lane == 0) { known = true; entry = sm.wentry[warp]; }
@@ -449,7 +462,9 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
             int j = (int)tile - 1;
             for (;;) {
                 u64 st;
-                do { st = ld_state(tile_cnt + F.state_base + j); } while ((st & FLAG_MASK) == 0);
+                uint32_t spins = 0;
+                do { st = ld_state(tile_cnt + F.state_base + j); } while ((st & FLAG_MASK) == 0 && ++spins < MSV1_SPIN_LIMIT);
+                if ((st & FLAG_MASK) == 0) { atomicOr(F.status, ST_ERROR); first = nblocks; break; }   // watchdog: decode nothing
                 first = sat_add(first, (uint32_t)st, nblocks);
                 if ((st & FLAG_MASK) == FLAG_INCL || j == 0) break;
                 --j;

@@ -163,3 +163,74 @@ def test_gop_split_with_flat_key_frames_matches_in_order_decoding(tmp_path):
         assert (stt == 0).all() and not (flags & _lib.JSP_FRAME_ERROR).any()
         for i in range(len(frames)):
             assert (outs[i] == exp[i]).all(), "version %d frame %d" % (version, i)
+
+
+def _one_shot(specs, n_gpus, shapes):
+    import ctypes as C
+    lib = _lib.require_gpu()
+    n = len(specs)
+    descs = (_lib.StreamDescC * n)()
+    keep, total = [], 0
+    for i, sp in enumerate(specs):
+        off = np.ascontiguousarray(sp.frame_off, dtype=np.uint64); ln = np.ascontiguousarray(sp.frame_len, dtype=np.uint32)
+        keys = np.ascontiguousarray(sp.keys, dtype=np.uint8)
+        pal = np.frombuffer(sp.palette, dtype=np.uint8).copy() if sp.palette else None
+        keep += [off, ln, keys, pal]
+        d = descs[i]
+        d.codec, d.width, d.height, d.bpp = int(sp.codec), sp.width, sp.height, sp.bpp
+        d.palette = pal.ctypes.data if pal is not None else None
+        d.palette_bytes = pal.size if pal is not None else 0
+        d.n_frames = len(ln)
+        d.bytes = sp.bytes_buf.ctypes.data
+        d.frame_off, d.frame_len, d.frame_key = off.ctypes.data, ln.ctypes.data, keys.ctypes.data
+        d.sp_version = int(sp.sp_version)
+        total += len(ln)
+    outs = [np.zeros(shapes[i], dtype=np.int32) for i in range(total)]
+    ptrs = (C.c_void_p * total)(*[o.ctypes.data for o in outs])
+    changed = np.zeros(total, dtype=np.uint8); signif = np.zeros(total, dtype=np.uint8); status = np.zeros(total, dtype=np.int32)
+    rc = lib.jsp_batch_decode(descs, n, n_gpus, ptrs, changed.ctypes.data, signif.ctypes.data, status.ctypes.data)
+    assert rc == 0, _lib.last_error()
+    return outs, changed, signif, status
+
+
+def test_multi_gpu_outputs_equal_the_single_gpu_outputs(tmp_path):
+    """"2/4/8-GPU outputs must equal the 1-GPU output byte-for-byte".  The mini corpus plus a 1080p pair of
+    files (MSVideo1 + ScreenPressor, key frame every 4), cut into GOP segments and decoded by jsp_batch_decode on 1 GPU and
+    on every power-of-two GPU count the box has.  Pictures, changed / significant flags and status must be identical (and
+    the 1-GPU pictures equal the oracle's).  Skipped on a single-GPU box (run it with `gpurun --gpus 2`)."""
+    lib = _lib.require_gpu()
+    ndev = lib.jsp_device_count()
+    if ndev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    files, w, h = make_corpus(tmp_path)
+    W, H = 1920, 1080
+    big = []
+    frames = [synth.msv1_frame(False, W, H, 900 + f, skip_permille=0 if f % 4 == 0 else 700) for f in range(12)]
+    keys = [1 if f % 4 == 0 else 0 for f in range(12)]
+    p = str(tmp_path / "big_m.avi"); write_avi(p, W, H, 16, b"CRAM", frames, keys)
+    big.append((p, O.CODEC_MSVC16, 16, None, frames, keys))
+    frames, keys, _ = synth.sp_stream(W, H, 12, seed=77, version=4, gop=4, change_permille=30)
+    p = str(tmp_path / "big_s.avi"); write_avi(p, W, H, 24, b"SCPR", frames, keys)
+    big.append((p, O.CODEC_SCREENPRESSOR, 24, None, frames, keys))
+    allfiles = files + big
+    streams = [avi.load_avi(p, pinned=True) for p, *_ in allfiles]
+    specs, where = avi.gop_specs(streams)
+    shapes = []
+    for (fi, lo, hi) in where:
+        shapes += [(streams[fi].height, streams[fi].width)] * (hi - lo)
+    ref = _one_shot(specs, 1, shapes)
+    exp = [O.decode_stream(codec, streams[k].width, streams[k].height, bpp, frames, keys=keys, palette=pal)[0]
+           for k, (_, codec, bpp, pal, frames, keys) in enumerate(allfiles)]
+    i = 0
+    for (fi, lo, hi) in where:
+        for f in range(lo, hi):
+            assert (ref[0][i] == exp[fi][f]).all(), "1 GPU: file %d frame %d" % (fi, f)
+            i += 1
+    g = 2
+    while g <= ndev:
+        got = _one_shot(specs, g, shapes)
+        for i in range(len(shapes)):
+            assert got[0][i].tobytes() == ref[0][i].tobytes(), "%d GPUs: picture %d differs from the 1-GPU picture" % (g, i)
+        for k in (1, 2, 3):
+            assert (got[k] == ref[k]).all()
+        g *= 2

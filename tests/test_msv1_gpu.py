@@ -255,3 +255,25 @@ def test_absurd_picture_sizes_are_refused():
         with pytest.raises(RuntimeError, match="out of range"):
             bd.configure([StreamSpec(CodecType.codec_msvc16, w, h, 16, frames=[frame], keys=[1])])
         bd.close()
+
+
+@pytest.mark.parametrize("height,mix", [(3112, (0, 0, 100)), (3200, (0, 0, 100)), (3112, (25, 50, 25))])
+def test_one_frame_whose_lookback_chain_exceeds_residency(height, mix):
+    """ONE frame, ~7000 bitstream tiles in a single look-back chain.  8192 x 3112 with 18-byte blocks is 28.7 MB = 7002 tiles:
+    below the persistent-grid threshold (6 x 8 x 148 = 7104), so the launch is 7002 one-shot CTAs for 1184 resident slots --
+    the chain crosses several waves and forward progress rests on the tile-major tickets alone.  8192 x 3200 (7200 tiles)
+    takes the persistent grid.  The look-back watchdog (MSV1_SPIN_LIMIT) would fail the frame instead of hanging: the
+    frame must decode, error-free and bit-exact, twice in a row (the tile states are reset between runs)."""
+    w = 8192
+    frame = synth.msv1_frame(False, w, height, 0x7000 + height, mix=mix)
+    if mix == (0, 0, 100):
+        tiles = (len(frame) + 4095) // 4096
+        assert (7000 <= tiles < 7104) if height == 3112 else (tiles >= 7104)
+    exp = oracle_stream(False, w, height, [frame])[0]
+    bd = BatchDecoder()
+    bd.configure([StreamSpec(CodecType.codec_msvc16, w, height, 16, frames=[frame])])
+    for _ in range(2):
+        outs, flags = bd.decode_host()
+        assert not (flags & _lib.JSP_FRAME_ERROR).any()
+        assert (outs[0] == exp[0]).all()
+    bd.close()
