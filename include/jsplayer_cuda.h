@@ -113,6 +113,10 @@ JSP_API int        jsp_batch_sync(jsp_batch *b);
  * row order; NULL entries are skipped.  flags[i] = JSP_FRAME_* bits. */
 JSP_API int        jsp_batch_download(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags);
 JSP_API int        jsp_batch_results(jsp_batch *b, uint8_t *flags);             /* flags only */
+/* The search behind Manager.SkipStills (Manager.hx:289-317, DataLoader.FindPossibleChange DataLoader.hx:239-252) over the
+ * decoded batch: first frame >= from_frame of `stream` whose change is significant (key frames: JSP_FRAME_DIFFERS, P frames:
+ * JSP_FRAME_SIGNIFICANT -- needs JSP_BATCH_SIGNIFICANCE), else the stream's last frame; -1 on error. */
+JSP_API int64_t    jsp_batch_next_significant(jsp_batch *b, int stream, int64_t from_frame);
 /* Display epilogue of the caller (Manager.fill_bitmap_data, Manager.hx:363-381): pictures are converted on the device
  * from 0x00RRGGBB to the Int32 view of canvas bytes R,G,B,A (alpha 255; ScreenPressor at 16 bpp: 0xFF000000 | c << 3),
  * optionally flipped vertically (the negative-Y matrix Main applies when drawing, Main.hx:318,946), then downloaded. */

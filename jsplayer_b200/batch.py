@@ -220,6 +220,11 @@ class BatchDecoder:
         self._check(self._lib.jsp_batch_results(self._h, flags.ctypes.data), "jsp_batch_results")
         return flags
 
+    def next_significant(self, stream, from_frame):
+        """Manager.SkipStills' search over the decoded batch: the next frame of `stream` at or after `from_frame` whose change
+        is significant (its last frame when there is none)."""
+        return int(self._check(self._lib.jsp_batch_next_significant(self._h, int(stream), int(from_frame)), "jsp_batch_next_significant"))
+
     def decode_host(self, outs=None):
         """upload + decode + download through host buffers (the end-to-end call)."""
         if outs is None:

@@ -630,7 +630,7 @@ static int64_t batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_st
         const size_t npix_pad = (npix + 63) & ~(size_t)63;
         for (int f = 0; f < D.n_frames; f++) {
             FrameRec R{};
-            R.stream = s; R.len = D.frame_len[f]; R.key = D.frame_key[f] ? 1 : 0;
+            R.stream = s; R.len = D.frame_len[f]; R.key = D.frame_key[f] ? 1 : 0; R.key_in = R.key;
             R.d_src = S.d_base + (size_t)(D.frame_len[f] ? D.frame_off[f] - lo : 0);
             R.out_off = out_cur; out_cur += npix_pad;
             R.prev = f > 0 ? nf + f - 1 : -1;
@@ -878,6 +878,25 @@ int jsp_batch_results(jsp_batch *b, uint8_t *flags)
     }
     if (flags) for (size_t i = 0; i < n; i++) flags[i] = public_flags(b->h_status[i]);
     return 0;
+}
+
+// Manager.SkipStills (Manager.hx:289-317) asks the loader for the next frame whose change is significant
+// (DataLoader.FindPossibleChange, DataLoader.hx:239-252) and decodes forward until it knows.  After a batch decode every
+// frame's answer is known: a key frame carries what Manager.worker would have stored for it (frames_differ_significantly,
+// JSP_FRAME_DIFFERS), a P frame its PFrameResult.significant_changes.  Returns the first frame >= from_frame of `stream` with
+// a significant change, the stream's last frame when there is none (as the reference does), -1 on bad arguments.
+int64_t jsp_batch_next_significant(jsp_batch *b, int stream, int64_t from_frame)
+{
+    if (!b || stream < 0 || stream >= (int)b->streams.size()) { set_error("jsp_batch_next_significant: bad arguments"); return -1; }
+    if (jsp_batch_results(b, nullptr)) return -1;
+    const StreamRec &S = b->streams[stream];
+    if (S.n_frames <= 0) return -1;
+    for (int64_t f = from_frame < 0 ? 0 : from_frame; f < S.n_frames; f++) {
+        const FrameRec &R = b->frames[(size_t)(S.first_frame + f)];
+        const uint8_t fl = public_flags(b->h_status[S.first_frame + f]);
+        if (fl & (R.key_in ? JSP_FRAME_DIFFERS : JSP_FRAME_SIGNIFICANT)) return f;
+    }
+    return S.n_frames - 1;
 }
 
 // D2H of pictures [lo, hi) on stream st; adjacent host destinations are merged into one copy

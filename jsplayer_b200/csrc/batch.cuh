@@ -70,6 +70,7 @@ struct FrameRec {
     int level;
     int kind;
     uint8_t key;
+    uint8_t key_in;                 // the caller's key flag (key may be demoted: a "key" frame that copies from its predecessor)
     uint32_t n_tiles, state_base;
     uint32_t state_base2;           // the frame's tile-state slice in the chunked (pipelined) plans
     uint32_t forced;                // status bits decided on the host (ST_ERROR, ST_CHANGED of flat frames)

@@ -125,7 +125,24 @@ __device__ __forceinline__ int sp2_pick_roles(RunQueue *rq)
 }
 
 // ---- warp 1: pixel reconstruction (ScreenPressor.hx:242-273) -------------------------------------------------------
-__device__ __forceinline__ void sp2_recon_iframe(RunQueue *q, const SpJob &J, uint32_t *ring, uint32_t rmask)
+// The last X + 1 reconstructed pixels: a power-of-two ring in shared memory, or -- pictures too wide for 64 KB, a separate
+// instantiation -- the picture itself in HBM (the "ring" index is the pixel index; the same warp wrote those pixels, __syncwarp
+// orders them).
+// Indices below 0 occur only while the first X + 1 pixels are decoded, where the loaded value is never selected: clamped.
+template <bool HBM>
+struct RingRef {
+    uint32_t *p; uint32_t mask;
+    static constexpr bool in_hbm() { return HBM; }
+    __device__ __forceinline__ uint32_t ld(long j) const
+    {
+        if constexpr (HBM) return p[j < 0 ? 0 : j];
+        else return p[(uint32_t)j & mask];
+    }
+    __device__ __forceinline__ void st(long j, uint32_t v) const { if constexpr (!HBM) p[(uint32_t)j & mask] = v; }
+};
+
+template <bool HBM>
+__device__ __forceinline__ void sp2_recon_iframe(RunQueue *q, const SpJob &J, const RingRef<HBM> ring)
 {
     const int lane = (int)lane_id();
     const long X = J.X, end = (long)J.X * J.Y;
@@ -155,9 +172,9 @@ __device__ __forceinline__ void sp2_recon_iframe(RunQueue *q, const SpJob &J, ui
             const long s = di + o, idx = s + lane;
             // every predictor's inputs are loaded (5 independent shared-memory reads), the type only selects: no branches.
             //   above[i] = ring[i - X], aboveleft[i] = ring[i - X - 1];  `e` = the chunk's last pixel
-            const uint32_t ab = ring[(uint32_t)(idx - X) & rmask], al = ring[(uint32_t)(idx - X - 1) & rmask];
-            const uint32_t ab_e = ring[(uint32_t)(s + m - 1 - X) & rmask], al_e = ring[(uint32_t)(s + m - 2 - X) & rmask];
-            const uint32_t al_s = ring[(uint32_t)(s - 1 - X) & rmask];
+            const uint32_t ab = ring.ld(idx - X), al = ring.ld(idx - X - 1);
+            const uint32_t ab_e = ring.ld(s + m - 1 - X), al_e = ring.ld(s + m - 2 - X);
+            const uint32_t al_s = ring.ld(s - 1 - X);
             // predictor 4: p[i] = p[i-1] + above[i] - aboveleft[i] per byte and aboveleft[i] = above[i-1], so the sum telescopes to
             // p[i] = p[s-1] + above[i] - above[s-1] -- no scan along the run
             const uint32_t g = vadd4(lastval, vsub4(ab, al_s)) & 0x00FFFFFFu, g_e = vadd4(lastval, vsub4(ab_e, al_s)) & 0x00FFFFFFu;
@@ -166,12 +183,13 @@ __device__ __forceinline__ void sp2_recon_iframe(RunQueue *q, const SpJob &J, ui
             v = type == 2 ? ab : v;       last = type == 2 ? ab_e : last;
             v = type == 5 ? al : v;       last = type == 5 ? al_e : last;
             v = type == 4 ? g : v;        last = type == 4 ? g_e : last;
-            if (lane < m && idx < end) { dst[idx] = (int32_t)v; ring[(uint32_t)idx & rmask] = v; }
+            if (lane < m && idx < end) { dst[idx] = (int32_t)v; ring.st(idx, v); }
             lastval = last;
             __syncwarp();                                  // the next chunk / run may read what other lanes just wrote
         }
         di += n;
         consumed++;
+        if constexpr (HBM) __threadfence_block();          // the entropy warp reads the last pixel from HBM after it sees `done`
         if (lane == 0) st_relaxed(&q->done, consumed);
         P2_T(9)
     }
@@ -182,8 +200,8 @@ __device__ __forceinline__ void sp2_recon_iframe(RunQueue *q, const SpJob &J, ui
 }
 
 // ---- warp 0: entropy decode of a coded I frame ---------------------------------------------------------------------
-template <class Coder>
-__device__ __forceinline__ void sp2_entropy_iframe(Coder &ec, Producer &pq, const SpJob &J, const uint32_t *ring, uint32_t rmask)
+template <class Coder, bool HBM>
+__device__ __forceinline__ void sp2_entropy_iframe(Coder &ec, Producer &pq, const SpJob &J, const RingRef<HBM> ring)
 {
     const long X = J.X, end = (long)J.X * J.Y;
     const int cxshift = (J.flags & SPJ_CXSHIFT0) ? 0 : 2;
@@ -196,8 +214,10 @@ __device__ __forceinline__ void sp2_entropy_iframe(Coder &ec, Producer &pq, cons
     uint32_t clr = 0;
     auto decode_rgb = [&]() -> uint32_t {                 // ScreenPressor.hx:173-183
         uint32_t px = 0;
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {                 // unrolled: a loop's back edge costs a symbol ~40 cycles
+        // Coder::kUnrollChannels: three inlined copies of the colour decoder (no back edge on the symbol chain) or one -- the rANS
+        // colour decoder is large, and a hot loop that does not fit the instruction cache costs more than the back edge
+#pragma unroll (Coder::kUnrollChannels ? 3 : 1)
+        for (int ch = 0; ch < 3; ch++) {
             const int v = ec.decodeClr(sp_ctx_index(ec, ch, cx, cx1));
             cx1 = (cx << 6) & 0xFC0; cx = v >> cxshift;
             px += (uint32_t)v << (8 * ch);
@@ -205,37 +225,42 @@ __device__ __forceinline__ void sp2_entropy_iframe(Coder &ec, Producer &pq, cons
         return px;
     };
     long budget = sp_run_budget(X, J.Y);
-    while (k < X + 1) {                                    // first X+1 pixels: (colour, run) pairs, :170-197
-        if (--budget < 0) ec.fail_frame();
-        clr = decode_rgb();
-        const int n = ec.decodeN(0);
-        if (ec.failed()) return;
-        k += n;
-        if (n > 0) pq.push(0u, (uint32_t)n, clr);
-        di += n;
-    }
     int ptype = 0;
+    bool head = true;                                      // the first X + 1 pixels: (colour, run) pairs, no predictor types (:170-197)
     bool clr_lazy = false;                                 // clr = the last pixel written so far; fetched from R when needed
-    bool ctx_from_clr = false;                             // the contexts are recomputed from clr after every run of this loop (:274-275)
+    bool ctx_from_clr = false;                             // the contexts are recomputed from clr after every run of the main part (:274-275)
     P2_DECL
 #ifdef JSP_SP2_PROF
     const long long _e0 = clock64();
 #endif
-    // :218-286.  Two branches per run: "colour follows" and the loop's back edge -- the rest is selects.  The run budget
-    // (a frame of zero-length runs must not spin for ever) is checked at the END of a run instead of before the next one:
-    // a failed coder decodes nothing more, so the result is the same.
-    if (di < end) for (;;) {
+    // ONE loop for both parts of the frame, so that the kernel holds one copy of each decoder.  Main part (:218-286): branches
+    // per run are "head?", "colour follows" and the back edge -- the rest is selects.  The run budget (a frame of zero-length
+    // runs must not spin for ever) is checked at the END of a main-part run instead of before the next one: a failed coder
+    // decodes nothing more, so the result is the same.
+    for (;;) {
         P2_T(11)
-        ptype = ec.decodeP(ptype);
+        if (head) { if (--budget < 0) ec.fail_frame(); }
+        else ptype = ec.decodeP(ptype);
         P2_T(0)
         if (ptype == 0) {
-            if (clr_lazy) { pq.drain(); clr = ring[(uint32_t)(di - 1) & rmask]; clr_lazy = false; P2_T(4) }
+            if (clr_lazy) { pq.drain(); if constexpr (HBM) clr = (uint32_t)__ldcg(J.dst + (di - 1 < end ? di - 1 : end - 1)); else clr = ring.ld(di - 1); clr_lazy = false; P2_T(4) }
             if (ctx_from_clr) { cx1 = ((int)clr & maskcx1) >> shiftcx1; cx = (int)clr >> shiftcx; }
             clr = decode_rgb();
             P2_T(1) P2_C(7)
         }
         int n = ec.decodeN(ptype);
         P2_T(2)
+        if (head) {
+            if (ec.failed()) return;
+            k += n;
+            if (n > 0) pq.push(0u, (uint32_t)n, clr);
+            di += n;
+            if (k >= X + 1) {
+                head = false;
+                if (di >= end) break;
+            }
+            continue;
+        }
         n = (ptype == 3 || ptype > 5) ? 0 : n;             // no such predictor in an I frame: nothing is written
         // `clr = dst[lasti]` even for an empty run of predictor 1 (:252); otherwise clr = the run's last pixel
         clr_lazy = clr_lazy | (ptype == 1) | (ptype != 0 && n > 0);
@@ -255,6 +280,7 @@ __device__ __forceinline__ void sp2_entropy_iframe(Coder &ec, Producer &pq, cons
     P2_FLUSH
 }
 
+template <bool HBM>
 __global__ void __launch_bounds__(64)
 sp2_rc_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
 {
@@ -263,7 +289,7 @@ sp2_rc_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
     extern __shared__ uint32_t ring[];                     // the last X + 1 pixels (power of two > X + 65 words)
     RcShared *shm = reinterpret_cast<RcShared *>(shm_bytes);
     const SpJob J = jobs[blockIdx.x];
-    const uint32_t rmask = sp_ring_size(J.X) - 1u;
+    const RingRef<HBM> rr = HBM ? RingRef<HBM>{reinterpret_cast<uint32_t *>(J.dst), 0xFFFFFFFFu} : RingRef<HBM>{ring, sp_ring_size(J.X) - 1u};
     const int lane = threadIdx.x & 31;
     const int warp = sp2_pick_roles(&rq);                  // 0 = entropy, 1 = reconstruction
     RcCoder ec;
@@ -271,11 +297,11 @@ sp2_rc_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
     if (warp == 0) {
         ec.open(J, shm, RC_SMALL_I_BYTES);
         Producer pq{&rq, 0u, 0u};
-        sp2_entropy_iframe(ec, pq, J, ring, rmask);
+        sp2_entropy_iframe(ec, pq, J, rr);
         pq.push(RQ_END, 0u, 0u);
         failed = ec.failed();
     } else {
-        sp2_recon_iframe(&rq, J, ring, rmask);
+        sp2_recon_iframe(&rq, J, rr);
     }
     __syncthreads();                                       // R has written every pixel E queued
     if (warp == 0) {
@@ -314,27 +340,29 @@ sp2_rc_p_kernel(const SpJob *__restrict__ jobs, uint32_t tile_words)
 }
 
 
-// ---- rANS streams (v3 / v4): the same two kernels on round 1's coder (sp_ans.cuh) ----
+// ---- rANS streams (v3 / v4): the same two kernels on the rANS coder (sp_ans.cuh) ----
+template <bool HBM>
 __global__ void __launch_bounds__(64)
 sp2_ans_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
 {
-    __shared__ AnsShared shm;
+    __shared__ alignas(16) uint8_t small_bytes[ANS_SMALL_I_BYTES];   // AnsSmall without the tables only P frames use
+    __shared__ AnsWork work;
     __shared__ RunQueue rq;
     extern __shared__ uint32_t ring[];
     const SpJob J = jobs[blockIdx.x];
-    const uint32_t rmask = sp_ring_size(J.X) - 1u;
+    const RingRef<HBM> rr = HBM ? RingRef<HBM>{reinterpret_cast<uint32_t *>(J.dst), 0xFFFFFFFFu} : RingRef<HBM>{ring, sp_ring_size(J.X) - 1u};
     const int lane = threadIdx.x & 31;
     const int warp = sp2_pick_roles(&rq);
     AnsCoder ec;
     bool failed = false;
     if (warp == 0) {
-        ec.open(J, shm);
+        ec.open(J, reinterpret_cast<AnsSmall *>(small_bytes), &work, ANS_SMALL_I_BYTES);
         Producer pq{&rq, 0u, 0u};
-        sp2_entropy_iframe(ec, pq, J, ring, rmask);
+        sp2_entropy_iframe(ec, pq, J, rr);
         pq.push(RQ_END, 0u, 0u);
         failed = ec.failed();
     } else {
-        sp2_recon_iframe(&rq, J, ring, rmask);
+        sp2_recon_iframe(&rq, J, rr);
     }
     __syncthreads();
     if (warp == 0) {
@@ -358,7 +386,7 @@ sp2_ans_p_kernel(const SpJob *__restrict__ jobs, uint32_t tile_words)
     const SpJob J = jobs[blockIdx.x];
     uint32_t *ptile = tile_words >= SP_PTILE_WORDS ? ptile_mem : nullptr;
     AnsCoder ec;
-    ec.open(J, shm);
+    ec.open(J, &shm.small, &shm.work, (uint32_t)sizeof(AnsSmall));
     uint32_t bits = 0;
     if (J.flags & SPJ_RENEW) ec.renewI();
     else sp_decode_pframe(ec, J, bits, ptile);
@@ -425,9 +453,9 @@ DevAux *aux_for_current_device()
             ok = ok && cudaEventCreateWithFlags(&A.join[i], cudaEventDisableTiming) == cudaSuccess;
         }
         ok = ok && cudaEventCreateWithFlags(&A.fork, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(g2::sp2_rc_i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(g2::sp2_rc_i_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(g2::sp2_rc_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(g2::sp2_ans_i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(g2::sp2_ans_i_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(g2::sp2_ans_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
         A.ok = ok;
         g_aux_ready.fetch_or(bit, std::memory_order_release);
@@ -444,7 +472,9 @@ bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_rc_p, uin
     DevAux *A = aux_for_current_device();
     uint32_t words = 1024;                                             // at least the P-frame block tile (SP_PTILE_WORDS)
     while (words <= max_width + 65u) words <<= 1;                      // >= sp_ring_size(max_width)
-    if (!A || words > 8192u) return false;                             // caller falls back to the first-generation kernel
+    if (!A) return false;                                              // caller falls back to the first-generation kernel
+    if (words > 16384u) words = 0;                                     // > 64 KB (pictures wider than 16 318): the I-frame kernels
+                                                                       // read the row above from the picture in HBM instead
     const uint32_t n[4] = {n_rc_i, n_rc_p, n_ans_i, n_ans_p};
     int groups = 0;
     for (int g = 0; g < 4; g++) groups += n[g] ? 1 : 0;
@@ -458,9 +488,15 @@ bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_rc_p, uin
         if (!first) { s = A->s[side]; cudaStreamWaitEvent(s, A->fork, 0); }
         const SpJob *jobs = d_jobs + off;
         switch (g) {
-        case 0: g2::sp2_rc_i_kernel<<<n[g], 64, (size_t)words * 4, s>>>(jobs, words); break;
+        case 0:
+            if (words) g2::sp2_rc_i_kernel<false><<<n[g], 64, (size_t)words * 4, s>>>(jobs, words);
+            else g2::sp2_rc_i_kernel<true><<<n[g], 64, 0, s>>>(jobs, 0);
+            break;
         case 1: g2::sp2_rc_p_kernel<<<n[g], 32, (size_t)1024 * 4, s>>>(jobs, 1024); break;
-        case 2: g2::sp2_ans_i_kernel<<<n[g], 64, (size_t)words * 4, s>>>(jobs, words); break;
+        case 2:
+            if (words) g2::sp2_ans_i_kernel<false><<<n[g], 64, (size_t)words * 4, s>>>(jobs, words);
+            else g2::sp2_ans_i_kernel<true><<<n[g], 64, 0, s>>>(jobs, 0);
+            break;
         default: g2::sp2_ans_p_kernel<<<n[g], 32, (size_t)1024 * 4, s>>>(jobs, 1024); break;
         }
         if (!first) { cudaEventRecord(A->join[side], s); cudaStreamWaitEvent(st, A->join[side], 0); side++; }

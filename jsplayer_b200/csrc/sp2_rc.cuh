@@ -238,6 +238,7 @@ static __device__ __noinline__ int rc_row_miss(RcBig<8> *cache, uint32_t *rows, 
 }
 
 struct RcCoder {
+    static constexpr bool kUnrollChannels = true;            // three inlined copies of the colour decoder (sp2_decode.cu)
     static constexpr bool kCanDecodeBool = false;              // EntroCoders.hx:178
     RcShared *shm;                                             // generic pointer (cold paths)
     RcSmall *sm;

@@ -20,6 +20,7 @@
 #include "sp_common.cuh"
 #include <cstddef>
 #include <cstring>
+#include <type_traits>
 
 namespace jsp {
 
@@ -31,25 +32,37 @@ constexpr int ANS_HDR_BYTES = 64, ANS_BODY_BYTES = 1536;
 enum { CXK_NONE = 0, CXK_1, CXK_2, CXK_3, CXK_4, CXK_5, CXK_6, CXK_7 };
 
 // ---- fixed-size adaptive table: separate arrays instead of the reference's (freq, cumFreq) pairs ----
+// cum[] carries 8 sentinel entries (0xFFFF: above every slot value) behind the table, so a forward scan needs no bound check.
+// Tables of 256 / 512 symbols also carry `lut`: the symbol that holds slot 16 * b, for b = 0..255 -- a finer decTable
+// (ANS.hx:105-126 looks up decTable[f >> 7] and scans on; this one starts at most 15 symbols short).  Frequencies change
+// only in the periodic rebuild (ANS.hx:89-102), which also rewrites lut.
 template <int N>
 struct FxTab {
     static constexpr int NP = N < 32 ? 32 : N;
     static constexpr int K = NP / 32;
-    alignas(16) uint16_t cum[NP];
+    static constexpr int NLUT = N >= 256 ? 256 : 0;
+    typedef typename std::conditional<(N > 256), uint16_t, uint8_t>::type lut_t;
+    alignas(16) uint16_t cum[NP + 8];
     alignas(16) uint16_t fr[NP];
     alignas(16) uint16_t cnt[NP];
     uint8_t dec[32];
     uint32_t cntsum;
     uint32_t pad[3];
+    alignas(16) lut_t lut[NLUT ? NLUT : 16];
 };
 
+// The tables a coded I frame uses come first: the I-frame kernel keeps only that prefix in shared memory (7 CTAs per SM).
 struct AnsSmall {
-    FxTab<256> ntab[6], xxtab, ntab2;
+    FxTab<256> ntab[6];
+    FxTab<6> ptypetab[6];
+    // ---- P frames only ----
+    FxTab<256> xxtab, ntab2;
     FxTab<512> mvtab[2];
     FxTab<16> sxytab[4];
-    FxTab<6> ptypetab[6];
     FxTab<5> bttab;
 };
+constexpr uint32_t ANS_SMALL_I_BYTES = (uint32_t)offsetof(AnsSmall, xxtab);
+static_assert(ANS_SMALL_I_BYTES % 16 == 0 && sizeof(AnsSmall) % 16 == 0, "tables are copied in 16-byte units");
 
 struct alignas(16) CxHdr {
     uint32_t gen;          // generation the slab belongs to; any other value reads as "no context yet"
@@ -88,12 +101,16 @@ struct alignas(16) AnsSlot {
     uint8_t body[512];
 };
 
-struct AnsShared {
-    AnsSmall small;
+constexpr uint32_t ANS_WIN = 256;                  // bitstream window (bytes)
+struct AnsWork {                                   // everything but the small tables
     AnsSlot cache[ANS_CACHE_SLOTS];
     alignas(16) uint8_t big[ANS_BODY_BYTES];       // Cx7 under construction / Cx6 rescale temporaries
-    alignas(16) uint8_t win[128];                  // bitstream window
+    alignas(16) uint8_t win[ANS_WIN];
     int res_c, res_freq, res_cum, res_wb;          // lane 0 -> warp
+};
+struct AnsShared {
+    AnsSmall small;
+    AnsWork work;
 };
 
 struct CxRes { int c, freq, cum; };
@@ -607,6 +624,58 @@ __device__ __forceinline__ int update_raw(CxHdr &H, uint8_t *B, uint8_t *big, in
 
 }  // namespace cx
 
+// The symbol that triggers a table's rebuild (ANS.hx:89-102): warp-parallel register path, a lane owns K consecutive symbols.
+// Out of line on purpose (scalar arguments, result in registers: {symbol, freq | cumFreq << 16}): one copy per table size.
+template <int N>
+static __device__ __noinline__ uint2 fx_rebuild_symbol(FxTab<N> *tp, int f)
+{
+        FxTab<N> &t = *tp;
+        constexpr int K = FxTab<N>::K;
+        const int lane = (int)lane_id(), j0 = lane * K;
+        uint32_t cum[K], fr[K], cnt[K];
+        ld_u16<K>(t.cum + j0, cum); ld_u16<K>(t.fr + j0, fr); ld_u16<K>(t.cnt + j0, cnt);
+        uint32_t cs = t.cntsum;
+        int freq, cumf, owner; bool rebuilt;
+        const int c = fx_core<N, K>(cum, fr, cnt, t.dec, cs, f, freq, cumf, rebuilt, owner);
+        __syncwarp();
+        if constexpr (K == 1) { if (j0 < N) st_u16<K>(t.cum + j0, cum); }   // entries >= N stay sentinels
+        else st_u16<K>(t.cum + j0, cum);
+        st_u16<K>(t.fr + j0, fr); st_u16<K>(t.cnt + j0, cnt);
+        t.cntsum = cs;                                                 // every lane stores the same value
+        if constexpr (FxTab<N>::NLUT != 0) {
+            // lut[b] = the symbol holding slot 16 * b: every symbol marks the first bucket start inside its interval, a prefix
+            // maximum spreads the marks (symbol indices grow with the slot)
+            static_assert(FxTab<N>::NLUT == 256, "8 buckets per lane");
+            typedef typename FxTab<N>::lut_t lt;
+            lt *lut = t.lut;
+#pragma unroll
+            for (int i = 0; i < 8; i++) lut[8 * lane + i] = 0;
+            __syncwarp();
+            if (rebuilt) {
+#pragma unroll
+                for (int q = 0; q < K; q++) {
+                    const uint32_t cf = cum[q], b0 = (cf + 15u) >> 4;
+                    if (j0 + q < N && b0 < 256u && (b0 << 4) < cf + fr[q]) lut[b0] = (lt)(j0 + q);
+                }
+            }
+            __syncwarp();
+            uint32_t m[8], run = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { run = max(run, (uint32_t)lut[8 * lane + i]); m[i] = run; }
+            uint32_t incl = run;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(FULLMASK, incl, dd); if (lane >= dd) incl = max(incl, o); }
+            uint32_t excl = __shfl_up_sync(FULLMASK, incl, 1);
+            if (lane == 0) excl = 0;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; i++) lut[8 * lane + i] = (lt)max(m[i], excl);
+        }
+        __syncwarp();
+        return make_uint2((uint32_t)c, (uint32_t)freq | ((uint32_t)cumf << 16));
+}
+
+
 #ifdef JSP_PROFILE_SECTIONS
 __device__ unsigned long long g_ans_prof[16];
 #define JSP_AT(k) { const long long _n = clock64(); aprof[k] += _n - _at; aprof[8 + (k)]++; _at = _n; }
@@ -616,7 +685,10 @@ __device__ unsigned long long g_ans_prof[16];
 
 struct AnsCoder {
     static constexpr bool kCanDecodeBool = true;                      // EntroCoders.hx:257
-    AnsShared *sm;
+    static constexpr bool kUnrollChannels = false;                    // one copy of decodeClr per kernel (sp2_decode.cu)
+    AnsSmall *small;                                                  // shared memory (the I-frame kernel maps only the I-frame prefix)
+    AnsWork *wk;
+    uint32_t small_bytes;                                             // how much of AnsSmall is mapped
     uint4 *hdrs, *bodies;
     int my_tag;                                                       // lane < ANS_CACHE_SLOTS: context held by slot `lane`, -1 = empty
     uint32_t my_age, tick;                                            // LRU stamps
@@ -637,49 +709,74 @@ struct AnsCoder {
     // so this coder simply goes on until the loop's next check, exactly as the oracle does.)
     __device__ __forceinline__ void fail_frame() { fail = true; }
 
+    __device__ __forceinline__ void refill(uint32_t at)              // window <- the ANS_WIN bytes around `at` (one coalesced warp load)
+    {
+        __syncwarp();
+        wbase = at & ~7u;                                             // the window starts (almost) at the read position
+        const int lane = (int)lane_id();
+        uint32_t w[2] = {0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t p = wbase + 8u * lane + k;
+            if (p < len) w[k >> 2] |= (uint32_t)__ldg(data + p) << (8 * (k & 3));
+        }
+        reinterpret_cast<uint2 *>(wk->win)[lane] = make_uint2(w[0], w[1]);
+        __syncwarp();
+    }
     __device__ __forceinline__ uint32_t rbyte()                       // data[pos++]; out of bounds reads as 0 after `|`
     {
         uint32_t b = 0;
         if (pos < len) {
-            if (pos - wbase >= 128u) {
-                __syncwarp();
-                wbase = pos & ~127u;
-                const int lane = (int)lane_id();
-                uint32_t w = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t p = wbase + 4u * lane + k;
-                    if (p < len) w |= (uint32_t)__ldg(data + p) << (8 * k);
-                }
-                reinterpret_cast<uint32_t *>(sm->win)[lane] = w;
-                __syncwarp();
-            }
-            b = sm->win[pos - wbase];
+            if (pos - wbase >= ANS_WIN) refill(pos);
+            b = wk->win[pos - wbase];
         } else overrun = true;
         pos++;
         return b;
     }
-    __device__ void reinit(uint32_t i)                                // Rans.reinitImpl, ANS.hx:22-31
+    __device__ __forceinline__ void reinit(uint32_t i)                                // Rans.reinitImpl, ANS.hx:22-31
     {
         pos = i;
         uint32_t v = rbyte();
         v |= rbyte() << 8; v |= rbyte() << 16; v |= rbyte() << 24;
         x = v;
     }
-    __device__ void decodeBegin(const uint8_t *src, uint32_t n, uint32_t pos0)   // EntroCoders.hx:229-233
+    __device__ __forceinline__ void decodeBegin(const uint8_t *src, uint32_t n, uint32_t pos0)   // EntroCoders.hx:229-233
     {
         data = src; len = n; overrun = false; wbase = 0x80000000u;
         reinit(pos0);
         nDec = 0;
     }
     __device__ __forceinline__ int get() { if (overrun) fail = true; return (int)(x & 4095u); }   // decGet, ANS.hx:35
-    __device__ __forceinline__ void advance(int start, int freq)      // decAdvance, ANS.hx:37-44
+    // decAdvance, ANS.hx:37-44.  Everything a valid stream does between two symbols, behind ONE test: the state is normalised
+    // (2^23 <= x < 2^31), the interval is sane, and the two bytes a renormalisation can need (x' >= freq * 2^11 >= 2^11, so two
+    // bytes reach 2^23) are in the window and in the stream.  Then `while (x < L) x = x << 8 | byte` is two compares and two
+    // selects -- no loop and no per-byte bounds checks on the symbol chain.
+    __device__ __forceinline__ bool try_advance(int start, int freq)
     {
+        const uint32_t off = pos - wbase, f = x & 4095u;
+        if ((x - ANS_L) < (0x80000000u - ANS_L) && off < ANS_WIN - 2u && pos + 2u <= len &&
+            (uint32_t)(freq - 1) < (uint32_t)ANS_SCALE && f >= (uint32_t)start && !overrun) {
+            const uint32_t b0 = wk->win[off], b1 = wk->win[off + 1u];
+            const uint32_t v = (uint32_t)freq * (x >> 12) + (f - (uint32_t)start);
+            const uint32_t v1 = (v << 8) | b0, v2 = (v << 16) | (b0 << 8) | b1;
+            const bool one = v < ANS_L, two = v < (ANS_L >> 8);
+            x = two ? v2 : (one ? v1 : v);
+            pos += (one ? 1u : 0u) + (two ? 1u : 0u);
+            return true;
+        }
+        return false;
+    }
+    __device__ __forceinline__ void advance(int start, int freq) { if (!try_advance(start, freq)) advance_slow(start, freq); }
+    __device__ __forceinline__ void advance_slow(int start, int freq)
+    {
+        if (pos - wbase >= ANS_WIN - 2u && pos + 2u <= len) {          // only the window was in the way: move it and try again
+            refill(pos);
+            if (try_advance(start, freq)) return;
+        }
         const int32_t r = (int32_t)x;
         if (r >= 0 && (uint32_t)freq <= (uint32_t)ANS_SCALE && (r & 4095) >= start) {
             // every state a valid stream reaches: the product fits 32 bits (freq <= 2^12, r >> 12 < 2^19)
             uint32_t v = (uint32_t)freq * ((uint32_t)r >> 12) + (uint32_t)((r & 4095) - start);
-            if (v >= ANS_L) { x = v; return; }                          // most symbols cost less than a byte
             int guard = 0;
             while (v < ANS_L) {
                 if (overrun || ++guard > 8) { fail = true; break; }
@@ -703,92 +800,149 @@ struct AnsCoder {
     }
 
     template <int N>
-    __device__ void fx_renew(FxTab<N> &t)                             // FixedSizeRansCtx.renew, ANS.hx:128-144
+    __device__ __forceinline__ void fx_renew(FxTab<N> &t)                             // FixedSizeRansCtx.renew, ANS.hx:128-144
     {
         const int lane = (int)lane_id();
         const int fr = ANS_SCALE / N, c0 = fr - (fr >> 1);
-        for (int i = lane; i < FxTab<N>::NP; i += 32) {
-            t.cum[i] = i < N ? (uint16_t)(i * fr) : 0; t.fr[i] = i < N ? (uint16_t)fr : 0; t.cnt[i] = i < N ? (uint16_t)c0 : 0;
+        for (int i = lane; i < FxTab<N>::NP + 8; i += 32) {
+            t.cum[i] = i < N ? (uint16_t)(i * fr) : (uint16_t)0xFFFFu;  // sentinels behind the table end every forward scan
+            if (i < FxTab<N>::NP) { t.fr[i] = i < N ? (uint16_t)fr : 0; t.cnt[i] = i < N ? (uint16_t)c0 : 0; }
         }
         const int i = (lane * 128) / fr;                              // the symbol whose interval holds 128 * lane
         if (i < N) t.dec[lane] = (uint8_t)i;
+        if constexpr (FxTab<N>::NLUT != 0)
+            for (int b = lane; b < FxTab<N>::NLUT; b += 32) t.lut[b] = (typename FxTab<N>::lut_t)((16 * b) / fr);
         if (lane == 0) t.cntsum = (uint32_t)(c0 * N);
     }
-    __device__ void renewI()                                          // EntroCoders.hx:216-227
+    // EntroCoders.hx:216-227.  `ponly` = where the tables only P frames use live right now: the shared-memory copy, or (I-frame
+    // kernel, which maps only the I-frame prefix) the stream's state in HBM.
+    __device__ __forceinline__ void renewI(AnsSmall *ponly)
     {
         gen = gen + 1;
-        AnsSmall &s = sm->small;
+        AnsSmall &s = *small;
         for (int i = 0; i < 6; i++) { fx_renew(s.ntab[i]); fx_renew(s.ptypetab[i]); }
-        fx_renew(s.xxtab); fx_renew(s.ntab2); fx_renew(s.bttab);
-        for (int i = 0; i < 4; i++) fx_renew(s.sxytab[i]);
-        fx_renew(s.mvtab[0]); fx_renew(s.mvtab[1]);
+        AnsSmall &p = *ponly;
+        fx_renew(p.xxtab); fx_renew(p.ntab2); fx_renew(p.bttab);
+        for (int i = 0; i < 4; i++) fx_renew(p.sxytab[i]);
+        fx_renew(p.mvtab[0]); fx_renew(p.mvtab[1]);
         __syncwarp();
     }
+    __device__ __forceinline__ void renewI() { renewI(small); }
 
-    // FixedSizeRansCtx.decode + incrCnt on a shared-memory table (decodeF, EntroCoders.hx:271-280).  Only the cumFreq
-    // vector is searched (a lane owns K consecutive symbols); the symbol's freq / cumFreq / count are then three
-    // scalar shared-memory reads and the update one scalar write.  The periodic rebuild (ANS.hx:89-102, every ~128
-    // symbols) takes the full register path of fx_core.
-    template <int N>
-    __device__ int decodeF(FxTab<N> &t)
+    // FixedSizeRansCtx.decode + incrCnt on a shared-memory table (decodeF, EntroCoders.hx:271-280).
+    // The symbol chain of a warp is latency-bound: every warp collective costs 25-45 cycles on it, every shared-memory round
+    // trip ~30, every branch ~15 (tools/microbench).  So the common case is ONE branch and no collectives: all loads the symbol
+    // can need are issued before the test (table sums, the cumulative frequencies or the lut entry, the next two bitstream
+    // bytes), the test checks everything the straight-line code assumes (no rebuild due, state normalised, bytes in the
+    // window, no reload of the state due), and every lane then runs the same scalar search -- small tables compare all
+    // cumulative frequencies at once and pick freq / count out of registers, big ones start from lut[f >> 4] and scan forward
+    // four entries at a time (sentinels end the scan).  Anything else -- the periodic rebuild (ANS.hx:89-102, every ~128
+    // symbols of a table), the end of the stream, corrupt states -- takes decodeF_slow.
+    static __device__ __forceinline__ uint32_t pick16(const uint4 &v, int c)      // u16 element c (0..7) of a packed vector
     {
-        constexpr int K = FxTab<N>::K;
-        const int lane = (int)lane_id(), j0 = lane * K;
-        const int f = get();
-        uint32_t cum[K];
-        ld_u16<K>(t.cum + j0, cum);
+        const uint32_t lo = (c & 2) ? v.y : v.x, hi = (c & 2) ? v.w : v.z;
+        const uint32_t w = (c & 4) ? hi : lo;
+        return (c & 1) ? (w >> 16) : (w & 0xFFFFu);
+    }
+    static __device__ __forceinline__ int rank8(const uint4 &v, uint32_t f)       // how many of elements 1..7 are <= f
+    {
+        return (int)((v.x >> 16) <= f) + (int)((v.y & 0xFFFFu) <= f) + (int)((v.y >> 16) <= f) + (int)((v.z & 0xFFFFu) <= f) +
+               (int)((v.z >> 16) <= f) + (int)((v.w & 0xFFFFu) <= f) + (int)((v.w >> 16) <= f);
+    }
+    template <int N>
+    __device__ __forceinline__ int decodeF(FxTab<N> &t)
+    {
+        const uint32_t off = pos - wbase, offc = min(off, ANS_WIN - 2u);
+        const uint32_t b0 = wk->win[offc], b1 = wk->win[offc + 1u];
+        const uint32_t cs = t.cntsum;
+        const uint32_t f = x & 4095u;
+        uint4 vc, vf, vn;
+        uint32_t c0 = 0;
+        if constexpr (N <= 8) {
+            vc = *reinterpret_cast<const uint4 *>(t.cum);             // cum[0..7]; entries >= N are 0xFFFF
+            vf = *reinterpret_cast<const uint4 *>(t.fr);
+            vn = *reinterpret_cast<const uint4 *>(t.cnt);
+        } else if constexpr (FxTab<N>::NLUT != 0) {
+            c0 = t.lut[f >> 4];                                       // the symbol that holds slot f & ~15: at most 15 short
+        }
+        const bool ok = (x - ANS_L) < (0x80000000u - ANS_L) && off < ANS_WIN - 2u && pos + 2u <= len && !overrun &&
+                        cs + 32u <= (uint32_t)ANS_SCALE && nDec + 1 != ANS_B;
+        if (!ok) return decodeF_slow(t);
+        int c;
+        uint32_t freq, cumf, cn;
+        if constexpr (N <= 8) {
+            c = rank8(vc, f);
+            freq = pick16(vf, c); cumf = pick16(vc, c); cn = pick16(vn, c);
+        } else {
+            c = (int)c0;
+            const uint16_t *cp = t.cum + c + 1;
+            for (;;) {
+                const uint32_t a0 = cp[0], a1 = cp[1], a2 = cp[2], a3 = cp[3];
+                const int k = (int)(a0 <= f) + (int)(a1 <= f) + (int)(a2 <= f) + (int)(a3 <= f);
+                c += k;
+                if (k < 4) break;
+                cp += 4;
+            }
+            freq = t.fr[c]; cumf = t.cum[c]; cn = t.cnt[c];
+        }
+        __syncwarp();                                                  // every lane has read the table
+        t.cnt[c] = (uint16_t)(cn + 16u);                               // every lane stores the same values: no divergence
+        t.cntsum = cs + 16u;
+        const uint32_t v = freq * (x >> 12) + (f - cumf);              // decAdvance, ANS.hx:37-44 (see try_advance)
+        const uint32_t v1 = (v << 8) | b0, v2 = (v << 16) | (b0 << 8) | b1;
+        const bool one = v < ANS_L, two = v < (ANS_L >> 8);
+        x = two ? v2 : (one ? v1 : v);
+        pos += (one ? 1u : 0u) + (two ? 1u : 0u);
+        nDec++; nsym++;
+        return c;
+    }
+    // the same symbol without assumptions: rebuild when due, generic advance (window refills, failures), state reloads
+    template <int N>
+    __device__ __forceinline__ int decodeF_slow(FxTab<N> &t)
+    {
         const uint32_t cntsum = t.cntsum + 16u;
-        if (cntsum + 16u > (uint32_t)ANS_SCALE) {                      // this symbol triggers the rebuild: slow path
-            uint32_t fr[K], cnt[K];
-            ld_u16<K>(t.fr + j0, fr); ld_u16<K>(t.cnt + j0, cnt);
-            uint32_t cs = t.cntsum;
-            int freq, cumf, owner; bool rebuilt;
-            const int c = fx_core<N, K>(cum, fr, cnt, t.dec, cs, f, freq, cumf, rebuilt, owner);
-            __syncwarp();
-            st_u16<K>(t.cum + j0, cum); st_u16<K>(t.fr + j0, fr); st_u16<K>(t.cnt + j0, cnt);
-            t.cntsum = cs;                                             // every lane stores the same value
-            __syncwarp();
-            advance(cumf, freq);
-            count();
-            return c;
-        }
-        const int c0 = t.dec[(f >> 7) & 31];
-        const uint32_t nxt = __shfl_down_sync(FULLMASK, cum[0], 1);
-        uint32_t mask = 0;
-#pragma unroll
-        for (int q = 0; q < K; q++) {
-            const int j = j0 + q;
-            const uint32_t cn = q + 1 < K ? cum[(q + 1) % K] : nxt;
-            if (j >= c0 && j < N - 1 && (int)cn > f) mask |= 1u << q;
-        }
-        const uint32_t ball = __ballot_sync(FULLMASK, mask != 0);
-        int c = N - 1;
-        if (ball) {
-            const int lw = __ffs(ball) - 1;
-            const uint32_t m = __shfl_sync(FULLMASK, mask, lw);
-            c = lw * K + __ffs(m) - 1;
+        if (cntsum + 16u > (uint32_t)ANS_SCALE) return decodeF_rebuild(t);
+        const uint32_t f = (uint32_t)get();
+        int c = 0;
+        if constexpr (FxTab<N>::NLUT != 0) c = (int)t.lut[f >> 4];
+        const uint16_t *cp = t.cum + c + 1;
+        for (;;) {
+            const uint32_t a0 = cp[0], a1 = cp[1], a2 = cp[2], a3 = cp[3];
+            const int k = (int)(a0 <= f) + (int)(a1 <= f) + (int)(a2 <= f) + (int)(a3 <= f);
+            c += k;
+            if (k < 4) break;
+            cp += 4;
         }
         const int freq = t.fr[c], cumf = t.cum[c];
         const uint32_t cn = t.cnt[c];
-        __syncwarp();                                                  // every lane has read the table
-        t.cnt[c] = (uint16_t)(cn + 16u);                               // every lane stores the same values: no divergence
+        __syncwarp();
+        t.cnt[c] = (uint16_t)(cn + 16u);
         t.cntsum = cntsum;
         __syncwarp();
         advance(cumf, freq);
         count();
         return c;
     }
+    // the symbol that triggers the rebuild (fx_rebuild_symbol: out of line, shared by every call site of a table size)
+    template <int N>
+    __device__ __forceinline__ int decodeF_rebuild(FxTab<N> &t)
+    {
+        const uint2 r = fx_rebuild_symbol<N>(&t, get());
+        advance((int)(r.y >> 16), (int)(r.y & 0xFFFFu));
+        count();
+        return (int)r.x;
+    }
 
     __device__ __forceinline__ void slot_writeback(int slot, int tag)
     {
         const int lane = (int)lane_id();
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(&sm->cache[slot]);
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(&wk->cache[slot]);
         uint4 *gh = hdrs + (size_t)tag * (ANS_HDR_BYTES / 16);
         uint4 *gb = bodies + (size_t)tag * (ANS_BODY_BYTES / 16);
         if (lane < 4) gh[lane] = s4[lane];
         gb[lane] = s4[4 + lane];
     }
-    __device__ void flush_slots()
+    __device__ __forceinline__ void flush_slots()
     {
         for (int k = 0; k < ANS_CACHE_SLOTS; k++) {
             const int t = __shfl_sync(FULLMASK, my_tag, k);
@@ -803,10 +957,10 @@ struct AnsCoder {
     __device__ __forceinline__ int decode_cx7(uint4 *gh, uint4 *gb, const uint4 &hv, const uint4 &bv, int f)
     {
         const int lane = (int)lane_id();
-        uint4 *sh4 = reinterpret_cast<uint4 *>(sm->big);               // the header's working copy (decTable lives in it)
+        uint4 *sh4 = reinterpret_cast<uint4 *>(wk->big);               // the header's working copy (decTable lives in it)
         if (lane < 4) sh4[lane] = hv;
         __syncwarp();
-        CxHdr &H = *reinterpret_cast<CxHdr *>(sm->big);
+        CxHdr &H = *reinterpret_cast<CxHdr *>(wk->big);
         uint32_t cum[8], fr[8], cnt[8];
         {
             const uint4 fv = gb[32 + lane], cv = gb[64 + lane];
@@ -832,7 +986,7 @@ struct AnsCoder {
         return c;
     }
 
-    __device__ int decodeClr(int cxi)                                 // EntroCoders.hx:235-255
+    __device__ __forceinline__ int decodeClr(int cxi)                                 // EntroCoders.hx:235-255
     {
         const int lane = (int)lane_id();
 #ifdef JSP_PROFILE_SECTIONS
@@ -863,7 +1017,7 @@ struct AnsCoder {
             const int old = __shfl_sync(FULLMASK, my_tag, slot);
             if (old >= 0) slot_writeback(slot, old);
             __syncwarp();
-            uint4 *s4 = reinterpret_cast<uint4 *>(&sm->cache[slot]);
+            uint4 *s4 = reinterpret_cast<uint4 *>(&wk->cache[slot]);
             if (lane < 4) s4[lane] = hv;
             s4[4 + lane] = bv;
             if (lane == slot) my_tag = cxi;
@@ -871,7 +1025,7 @@ struct AnsCoder {
         }
         if (lane == slot) my_age = tick;
         if (hit) { JSP_AT(0) } else { JSP_AT(5) }
-        AnsSlot &S = sm->cache[slot];
+        AnsSlot &S = wk->cache[slot];
         CxHdr &H = S.hdr;
         const int kind = H.gen == gen ? H.kind : CXK_NONE;
         int c;
@@ -934,27 +1088,27 @@ struct AnsCoder {
         if (kind >= CXK_4) {
             if (lane == 0) {
                 CxRes r; r.c = 0; r.freq = 1; r.cum = 0;
-                sm->res_wb = cx::decode_small(H, S.body, sm->big, f, r);
-                sm->res_c = r.c; sm->res_freq = r.freq; sm->res_cum = r.cum;
+                wk->res_wb = cx::decode_small(H, S.body, wk->big, f, r);
+                wk->res_c = r.c; wk->res_freq = r.freq; wk->res_cum = r.cum;
             }
             __syncwarp();
-            c = sm->res_c; wb = sm->res_wb;
-            const int freq = sm->res_freq, cumf = sm->res_cum;
+            c = wk->res_c; wb = wk->res_wb;
+            const int freq = wk->res_freq, cumf = wk->res_cum;
             advance(cumf, freq);
             if (c > 255) { fail = true; c &= 255; }                   // escape interval past symbol 255: not a valid stream
             JSP_AT(2)
         } else {
             c = (int)rbyte();                                         // Rans.raw, ANS.hx:46-48
-            if (lane == 0) sm->res_wb = cx::update_raw(H, S.body, sm->big, c, f0, gen);
+            if (lane == 0) wk->res_wb = cx::update_raw(H, S.body, wk->big, c, f0, gen);
             __syncwarp();
-            wb = sm->res_wb;
+            wb = wk->res_wb;
             JSP_AT(3)
         }
         if (wb < 0) {
             // the context has just become a Cx7 (built in `big`): it moves out to global memory and leaves the cache
             uint4 *gh = hdrs + (size_t)cxi * (ANS_HDR_BYTES / 16);
             uint4 *gb = bodies + (size_t)cxi * (ANS_BODY_BYTES / 16);
-            const uint4 *big4 = reinterpret_cast<const uint4 *>(sm->big);
+            const uint4 *big4 = reinterpret_cast<const uint4 *>(wk->big);
             const uint4 *s4 = reinterpret_cast<const uint4 *>(&S);
             gb[lane] = big4[lane]; gb[32 + lane] = big4[32 + lane]; gb[64 + lane] = big4[64 + lane];
             if (lane < 4) gh[lane] = s4[lane];
@@ -965,12 +1119,16 @@ struct AnsCoder {
         return c;
     }
 
-    // ---- per-frame set-up / tear-down for the second-generation kernels (sp2_decode.cu) ----
-    __device__ __forceinline__ void begin_iframe(const SpJob &) { renewI(); }
-    __device__ __forceinline__ void open(const SpJob &J, AnsShared &shared)
+    // ---- per-frame set-up / tear-down: the first `small_bytes` of the stream's small tables move to shared memory and back ----
+    __device__ __forceinline__ void begin_iframe(const SpJob &J)
+    {
+        renewI(small_bytes == (uint32_t)sizeof(AnsSmall) ? small : &reinterpret_cast<AnsState *>(J.state)->small);
+    }
+    __device__ __forceinline__ void open(const SpJob &J, AnsSmall *small_sh, AnsWork *work_sh, uint32_t nbytes)
     {
         AnsState *st = reinterpret_cast<AnsState *>(J.state);
-        sm = &shared; hdrs = st->hdrs; bodies = st->bodies; gen = st->gen;
+        small = small_sh; wk = work_sh; small_bytes = nbytes;
+        hdrs = st->hdrs; bodies = st->bodies; gen = st->gen;
         f0 = (J.flags & SPJ_ANS_V3) ? 64 : 32;                       // Cx6.f0, EntroCoders.hx:210 / ScreenPressor.hx:69-72
         fail = false; overrun = false; x = 0; data = J.src; len = J.len; pos = 0; wbase = 0x80000000u; nDec = 0; nsym = 0;
         my_tag = -1; my_age = 0; tick = 0;
@@ -978,8 +1136,8 @@ struct AnsCoder {
         for (int k = 0; k < 16; k++) aprof[k] = 0;
 #endif
         const uint4 *g = reinterpret_cast<const uint4 *>(&st->small);
-        uint4 *s = reinterpret_cast<uint4 *>(&shared.small);
-        for (int i = (int)lane_id(); i < (int)(sizeof(AnsSmall) / 16); i += 32) s[i] = g[i];
+        uint4 *s = reinterpret_cast<uint4 *>(small_sh);
+        for (int i = (int)lane_id(); i < (int)(nbytes / 16); i += 32) s[i] = g[i];
         __syncwarp();
     }
     __device__ __forceinline__ void close(const SpJob &J)
@@ -988,12 +1146,12 @@ struct AnsCoder {
         flush_slots();
         __syncwarp();
         uint4 *g = reinterpret_cast<uint4 *>(&st->small);
-        const uint4 *s = reinterpret_cast<const uint4 *>(&sm->small);
-        for (int i = (int)lane_id(); i < (int)(sizeof(AnsSmall) / 16); i += 32) g[i] = s[i];
+        const uint4 *s = reinterpret_cast<const uint4 *>(small);
+        for (int i = (int)lane_id(); i < (int)(small_bytes / 16); i += 32) g[i] = s[i];
         if (lane_id() == 0) st->gen = gen;
     }
 
-    __device__ bool decodeBool()                                      // EntroCoders.hx:259-269
+    __device__ __forceinline__ bool decodeBool()                                      // EntroCoders.hx:259-269
     {
         const int f = get();
         const bool flag = f >= (ANS_SCALE >> 1);
@@ -1001,35 +1159,22 @@ struct AnsCoder {
         count();
         return flag;
     }
-    __device__ int decodeN(int ptype) { return decodeF(sm->small.ntab[ptype]); }
-    __device__ int decodeP(int ptype) { return decodeF(sm->small.ptypetab[ptype]); }
-    __device__ int decodeX() { return decodeF(sm->small.xxtab); }
-    __device__ int decodeBT() { return decodeF(sm->small.bttab); }
-    __device__ int decodeBN() { return decodeF(sm->small.ntab2); }
-    __device__ int decodeSXY(int n) { return decodeF(sm->small.sxytab[n]); }
-    __device__ int decodeMX() { return decodeF(sm->small.mvtab[0]); }
-    __device__ int decodeMY() { return decodeF(sm->small.mvtab[1]); }
+    __device__ __forceinline__ int decodeN(int ptype) { return decodeF(small->ntab[ptype]); }
+    __device__ __forceinline__ int decodeP(int ptype) { return decodeF(small->ptypetab[ptype]); }
+    __device__ __forceinline__ int decodeX() { return decodeF(small->xxtab); }
+    __device__ __forceinline__ int decodeBT() { return decodeF(small->bttab); }
+    __device__ __forceinline__ int decodeBN() { return decodeF(small->ntab2); }
+    __device__ __forceinline__ int decodeSXY(int n) { return decodeF(small->sxytab[n]); }
+    __device__ __forceinline__ int decodeMX() { return decodeF(small->mvtab[0]); }
+    __device__ __forceinline__ int decodeMY() { return decodeF(small->mvtab[1]); }
 };
 
-// one frame of one rANS stream; `sm` = this warp's shared memory
+// one frame of one rANS stream; `sm` = this warp's shared memory (first-generation kernel: one warp does everything)
 __device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm, uint32_t *ring, uint32_t *ptile)
 {
-    AnsState *st = reinterpret_cast<AnsState *>(J.state);
     const int lane = (int)lane_id();
     AnsCoder ec;
-    ec.sm = &sm; ec.hdrs = st->hdrs; ec.bodies = st->bodies; ec.gen = st->gen;
-    ec.f0 = (J.flags & SPJ_ANS_V3) ? 64 : 32;                         // Cx6.f0, EntroCoders.hx:210 / ScreenPressor.hx:69-72
-    ec.fail = false; ec.overrun = false; ec.x = 0; ec.data = J.src; ec.len = J.len; ec.pos = 0; ec.wbase = 0x80000000u; ec.nDec = 0; ec.nsym = 0;
-    ec.my_tag = -1; ec.my_age = 0; ec.tick = 0;
-#ifdef JSP_PROFILE_SECTIONS
-    for (int k = 0; k < 16; k++) ec.aprof[k] = 0;
-#endif
-    {
-        const uint4 *g = reinterpret_cast<const uint4 *>(&st->small);
-        uint4 *s = reinterpret_cast<uint4 *>(&sm.small);
-        for (int i = lane; i < (int)(sizeof(AnsSmall) / 16); i += 32) s[i] = g[i];
-    }
-    __syncwarp();
+    ec.open(J, &sm.small, &sm.work, (uint32_t)sizeof(AnsSmall));
     uint32_t bits = 0;
     if (J.flags & SPJ_RENEW) {
         ec.renewI();
@@ -1039,18 +1184,13 @@ __device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm, uint32
     } else {
         sp_decode_pframe(ec, J, bits, ptile);
     }
-    ec.flush_slots();
+    ec.close(J);
     if (ec.failed()) {
         bits = ST_ERROR;
         if (!(J.flags & SPJ_RENEW)) sp_undo_frame(J, (J.flags & SPJ_IFRAME) != 0);
     }
     __syncwarp();
-    {
-        uint4 *g = reinterpret_cast<uint4 *>(&st->small);
-        const uint4 *s = reinterpret_cast<const uint4 *>(&sm.small);
-        for (int i = lane; i < (int)(sizeof(AnsSmall) / 16); i += 32) g[i] = s[i];
-    }
-    if (lane == 0) { st->gen = ec.gen; if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
+    if (lane == 0) { if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
     sp_signal_done(J);
 #ifdef JSP_PROFILE_SECTIONS
     if (lane == 0) for (int k = 0; k < 16; k++) atomicAdd(&g_ans_prof[k], (unsigned long long)ec.aprof[k]);

@@ -304,10 +304,10 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
                               atomicMax(&g_spp_prof[8], (unsigned long long)a[4]); } } } _pflush{_pacc, _pall};
 #endif
     ec.decodeBegin(J.src, J.len, 1);
-    int t = ec.decodeX();
-    int xx1 = ec.decodeX(); xx1 = (xx1 << 8) + t;
-    t = ec.decodeX();
-    int xx2 = ec.decodeX(); xx2 = (xx2 << 8) + t;
+    uint32_t xw = 0;                               // four decodeX symbols: xx1 = lo | hi << 8, xx2 likewise (:322-327); one call site
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) xw |= (uint32_t)(ec.decodeX() & 0xFF) << (8 * i);
+    const int xx1 = (int)(xw & 0xFFFFu), xx2 = (int)(xw >> 16);
     for (int i = lane; i < nb; i += 32) bts[i] = 0;
     __syncwarp();
     bool signif = false;
@@ -361,10 +361,13 @@ __device__ void sp_decode_pframe(Coder &ec, const SpJob &J, uint32_t &status_bit
         if (y2 > Y) y2 = (int)Y;
         JSP_PT0
         if (((bt - 1) & 1) > 0) {                  // sub-rectangle (:375-386); the block itself is already copied
-            x1 = ec.decodeSXY(0) + x16;
-            y1 = ec.decodeSXY(1) + y16;
-            x2 = ec.decodeSXY(2) + x16 + 1;
-            y2 = ec.decodeSXY(3) + y16 + 1;
+            uint32_t sw = 0;                       // four decodeSXY symbols (0..15 each); one call site
+#pragma unroll 1
+            for (int i = 0; i < 4; i++) sw |= (uint32_t)(ec.decodeSXY(i) & 0xFF) << (8 * i);
+            x1 = (int)(sw & 0xFFu) + x16;
+            y1 = (int)((sw >> 8) & 0xFFu) + y16;
+            x2 = (int)((sw >> 16) & 0xFFu) + x16 + 1;
+            y2 = (int)(sw >> 24) + y16 + 1;
         }
         if (((bt - 1) & 2) > 0) {                  // motion vector (:388-405)
             int mx, my;

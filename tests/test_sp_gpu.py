@@ -284,3 +284,12 @@ def test_fuzzed_batches_match_the_oracle(version, bpp):
                 if not err:
                     assert bool(flags[k] & _lib.JSP_FRAME_CHANGED) == bool(ch[i]), (w, h, trial, i)
                 k += 1
+
+
+@pytest.mark.parametrize("version", [2, 4])
+def test_pictures_wider_than_the_shared_memory_ring(version):
+    """A picture wider than 16 318 pixels: the last X + 1 pixels no longer fit the I-frame kernels' shared-memory ring (64 KB),
+    so the reconstruction warp reads the row above from the picture in HBM.  Same kernels, same model-state layout."""
+    w, h = 16400, 24
+    frames, keys, pics = synth.sp_stream(w, h, 3, seed=99 + version, version=version, gop=2, change_permille=30)
+    check(w, h, 24, frames, keys)
