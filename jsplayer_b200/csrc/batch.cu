@@ -262,13 +262,18 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
         // longest frames first: when a launch has more warps than the device holds, the late starters are the short ones
         std::vector<int64_t> order(by_level[lv]);
         std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return b->frames[x].len > b->frames[y].len; });
-        // range-coder frames first (the kernel deals the two coders to different SMs when both are present), and among them
-        // the coded I frames first (second-generation kernels: one launch per coder and frame type)
-        std::stable_partition(order.begin(), order.end(), [&](int64_t x) { return b->sp_hosts[b->frames[x].stream].version <= 2; });
-        {
-            auto rc_end = std::stable_partition(order.begin(), order.end(), [&](int64_t x) { return b->sp_hosts[b->frames[x].stream].version <= 2; });
-            std::stable_partition(order.begin(), rc_end, [&](int64_t x) { return b->frames[x].kind == FK_SP_I; });
-            std::stable_partition(rc_end, order.end(), [&](int64_t x) { return b->frames[x].kind == FK_SP_I; });
+        // second-generation kernels (sp2_decode.cu): [range-coder I | rANS I | range-coder P and resets | rANS P and resets] -- one
+        // launch for the coded I frames, one for the rest, each dealing its two coders to different SMs;
+        // first generation (JSP_SP_GEN=1): range-coder frames first
+        const bool gen2 = sp_generation() >= 2;
+        auto is_rc = [&](int64_t x) { return b->sp_hosts[b->frames[x].stream].version <= 2; };
+        auto is_i = [&](int64_t x) { return b->frames[x].kind == FK_SP_I; };
+        if (gen2) {
+            auto i_end = std::stable_partition(order.begin(), order.end(), is_i);
+            std::stable_partition(order.begin(), i_end, is_rc);
+            std::stable_partition(i_end, order.end(), is_rc);
+        } else {
+            std::stable_partition(order.begin(), order.end(), is_rc);
         }
         int n_rc_i = 0, n_ans_i = 0;
         for (int64_t f : order) {
@@ -298,7 +303,7 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             const int kclass = n_ans == 0 ? JSP_K_SP_ENTROPY_RC : (n_rc == 0 ? JSP_K_SP_ENTROPY_ANS : JSP_K_SP_ENTROPY_MIXED);
             Launch L{kclass, FK_SP_I, first, (uint32_t)(T.spjobs.size() - first), max_w, (uint32_t)ticket_cursor};
             L.n_rc = (uint32_t)n_rc; L.n_rc_i = (uint32_t)n_rc_i; L.n_ans_i = (uint32_t)n_ans_i;
-            ticket_cursor += 2;
+            ticket_cursor += 4;                   // two job queues per launch, two launches (I frames, the rest)
             plan.launches.push_back(L);
             plan.finished.push_back(std::move(fin));
         }
@@ -409,9 +414,12 @@ template <class F> static bool run_plan_with(jsp_batch *b, const Plan &P, cudaSt
                                b->d_tile_map, b->d_tile_cnt, b->d_tickets + L.ticket, b->sm_count, st);
             break;
         case JSP_K_SP_ENTROPY_RC: case JSP_K_SP_ENTROPY_ANS: case JSP_K_SP_ENTROPY_MIXED:
-            if (sp_generation() < 2 ||
-                !launch_sp2_level(b->d_spjobs + L.first, L.n_rc_i, L.n_rc - L.n_rc_i, L.n_ans_i, L.count - L.n_rc - L.n_ans_i, L.max_vec4, st))
+            if (sp_generation() < 2)
                 launch_sp_decode(b->d_spjobs + L.first, L.count, L.max_vec4, L.n_rc, b->d_tickets + L.ticket, st);
+            else if (!launch_sp2_level(b->d_spjobs + L.first, L.n_rc_i, L.n_ans_i, L.n_rc - L.n_rc_i, L.count - L.n_rc - L.n_ans_i,
+                                       L.max_vec4, b->d_tickets + L.ticket, st)) {
+                set_error("ScreenPressor launch: no side stream on this device"); return false;
+            }
             break;
         default: break;
         }

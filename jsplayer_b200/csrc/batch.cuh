@@ -49,7 +49,8 @@ int bind_thread_to_device(int device);                     // numa_bind.cpp
 int sp_generation();
 size_t sp2_rc_state_bytes();
 void sp2_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t st);
-bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_rc_p, uint32_t n_ans_i, uint32_t n_ans_p, uint32_t max_width, cudaStream_t st);
+bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_ans_i, uint32_t n_rc_p, uint32_t n_ans_p, uint32_t max_width,
+                      uint32_t *d_queue, cudaStream_t st);
 
 struct StreamRec {
     int codec, w, h, bpp;

@@ -94,15 +94,25 @@ __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+__device__ __forceinline__ uint32_t mad_hi_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// Five instructions per colour: red and blue are expanded by ONE multiply -- (R << 10 | B) * 0x208 = R << 19 | B << 3 plus two
+// stray copies (B << 9, R << 13) that lie between the wanted fields and cannot carry into them (their sum stays below 2^19),
+// so one mask cleans up -- and green is positioned by the multiply-add that also merges it.  The colour in the HIGH half of a
+// word takes the same five through multiply-high (no shift down first).
 __device__ __forceinline__ uint32_t rgb15(uint32_t c)
 {
-    // measured alternative: isolating the fields with multiply / multiply-high pairs (no ALU-pipe masks at all) costs
-    // two more instructions per colour and is 5 % slower -- the kernel is bound by issue slots, not by one pipe
-    return mad_u32(c & 0x7C00u, 512u, mad_u32(c & 0x3E0u, 64u, (c & 0x1Fu) * 8u));
+    const uint32_t rb = ((c & 0x7C1Fu) * 0x208u) & 0x00F800F8u;
+    return mad_u32(c & 0x3E0u, 64u, rb);
 }
 __device__ __forceinline__ uint32_t rgb15_hi(uint32_t x)
 {
-    return rgb15(x >> 16);
+    const uint32_t rb = __umulhi(x & 0x7C1F0000u, 0x02080000u) & 0x00F800F8u;
+    return mad_hi_u32(x & 0x03E00000u, 1u << 22, rb);
 }
 
 __device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b, uint32_t cap)
@@ -292,6 +302,14 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
                                     ? min((uint32_t)MSV1_TILE_WORDS, n_words - tile * MSV1_TILE_WORDS) : 0u;
     const bool vec_ok = ((X & 3u) == 0) && ((reinterpret_cast<uintptr_t>(F.out) & 15u) == 0) &&
                         ((reinterpret_cast<uintptr_t>(F.prev) & 15u) == 0);
+    // The two look-backs below usually find their predecessor's state already published (tiles are ticketed tile-major, the
+    // predecessor started a whole round of frames earlier): load both words NOW, so that the L2 round trips run under the scan
+    // instead of in the two single-thread sections the other 127 threads wait for.  A word that is not there yet is polled later.
+    u64 pf_map = 0, pf_cnt = 0;
+    if (tid == 0 && tile > 0) {
+        pf_map = ld_state(tile_map + F.state_base + tile - 1);
+        pf_cnt = ld_state(tile_cnt + F.state_base + tile - 1);
+    }
     if (IS8) {
         for (int i = tid; i < 256; i += MSV1_THREADS) sm.pal[i] = F.pal ? F.pal[i] : 0;
         __syncthreads();
@@ -316,25 +334,58 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
         const uint4 v1 = *reinterpret_cast<const uint4 *>(sw + 4);
         const uint32_t r[9] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, sw[8]};
 #define JSP_NEXT(L) ((p + (L) < MSV1_SEG_WORDS) ? R[(p + (L)) & (MSV1_SEG_WORDS - 1)] : (uint32_t)((p + (L) - MSV1_SEG_WORDS) << 16))
+        if constexpr (!IS8) {
+            // RGB555: an opcode's length depends on two bits -- bit 15 of its own word (1 colour or skip run: 1 word) and bit 15 of
+            // the NEXT word (8 colours: 9 words, else 3) -- and a skip run on its high byte.  Both are classified for all 16 words
+            // at once: PRMT gathers the four high bytes of two registers, a multiply gathers one bit per byte into a nibble.
+            uint32_t G = 0, S = 0;                 // bit p: word p has bit 15 set / word p is a skip run ((b & 0xFC) == 0x84, :131)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t hb = __byte_perm(r[2 * i], r[2 * i + 1], 0x7531);
+                G |= ((((hb >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * i);
+                const uint32_t z = (hb ^ 0x84848484u) & 0xFCFCFCFCu;             // a zero byte = a skip-run word
+                const uint32_t nz = (((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & 0x80808080u;
+                S |= (((((nz ^ 0x80808080u) >> 7)) * 0x01020408u) >> 24) << (4 * i);
+            }
+            G |= ((r[8] >> 15) & 1u) << 16;
+            uint32_t T = 0;                        // skip count 0: the rest of the frame is copied (:132, :124) -- word 0x8400
+            for (uint32_t m = S; m; m &= m - 1) {
+                const int p = __ffs(m) - 1;
+                if (reinterpret_cast<const uint16_t *>(sbytes)[tid * MSV1_SEG_WORDS + p] == 0x8400u) T |= 1u << p;
+            }
+            skipmask = S; termmask = T;
+            if (T == 0) {
+#pragma unroll
+                for (int p = MSV1_SEG_WORDS - 1; p >= 0; --p) {
+                    const bool one = (G >> p) & 1u, eight = (G >> (p + 1)) & 1u;
+                    const uint32_t nxt = one ? JSP_NEXT(1) : (eight ? JSP_NEXT(9) : JSP_NEXT(3));
+                    R[p] = nxt | (1u << p);
+                }
+            } else {
+#pragma unroll
+                for (int p = MSV1_SEG_WORDS - 1; p >= 0; --p) {
+                    const bool one = (G >> p) & 1u, eight = (G >> (p + 1)) & 1u;
+                    uint32_t nxt = one ? JSP_NEXT(1) : (eight ? JSP_NEXT(9) : JSP_NEXT(3));
+                    if ((T >> p) & 1u) nxt = TERM << 16;
+                    R[p] = nxt | (1u << p);
+                }
+            }
+        } else {
 #pragma unroll
         for (int p = MSV1_SEG_WORDS - 1; p >= 0; --p) {
-            uint32_t a, b, h;
-            if (p & 1) { a = (r[p >> 1] >> 16) & 0xFFu; b = r[p >> 1] >> 24; h = r[(p >> 1) + 1] & 0x8000u; }
-            else       { a = r[p >> 1] & 0xFFu; b = (r[p >> 1] >> 8) & 0xFFu; h = r[p >> 1] & 0x80000000u; }
-            bool isrun = (b & 0xFCu) == 0x84u;                     // skip run (MSVideo1.hx:131 / :315)
-            bool term = (b == 0x84u) && (a == 0u);                 // skip count 0: rest of the frame is copied (:132,124)
-            uint32_t nxt;
-            if (IS8) {
-                const bool t8 = (a + b == 0u);                     // terminator (MSVideo1.hx:313)
-                term = term || t8; isrun = isrun || t8;
-                nxt = (b < 0x80u) ? JSP_NEXT(2) : (b >= 0x90u ? JSP_NEXT(5) : JSP_NEXT(1));
-            } else {
-                nxt = (b < 0x80u) ? (h ? JSP_NEXT(9) : JSP_NEXT(3)) : JSP_NEXT(1);
-            }
+            uint32_t a, b;
+            if (p & 1) { a = (r[p >> 1] >> 16) & 0xFFu; b = r[p >> 1] >> 24; }
+            else       { a = r[p >> 1] & 0xFFu; b = (r[p >> 1] >> 8) & 0xFFu; }
+            bool isrun = (b & 0xFCu) == 0x84u;                     // skip run (MSVideo1.hx:315)
+            bool term = (b == 0x84u) && (a == 0u);                 // skip count 0: rest of the frame is copied (:124)
+            const bool t8 = (a + b == 0u);                         // terminator (MSVideo1.hx:313)
+            term = term || t8; isrun = isrun || t8;
+            uint32_t nxt = (b < 0x80u) ? JSP_NEXT(2) : (b >= 0x90u ? JSP_NEXT(5) : JSP_NEXT(1));
             if (term) nxt = TERM << 16;
             R[p] = nxt | (1u << p);
             if (isrun) skipmask |= 1u << p;
             if (term) termmask |= 1u << p;
+        }
         }
 #undef JSP_NEXT
         uint32_t lo = 0;
@@ -389,9 +440,9 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
             u64 acc = MAP_IDENT;
             int j = (int)tile - 1;
             for (;;) {
-                u64 st;
+                u64 st = (j == (int)tile - 1) ? pf_map : 0ull;
                 uint32_t spins = 0;
-                do { st = ld_state(tile_map + F.state_base + j); } while ((st & FLAG_MASK) == 0 && ++spins < MSV1_SPIN_LIMIT);
+                while ((st & FLAG_MASK) == 0 && ++spins < MSV1_SPIN_LIMIT) st = ld_state(tile_map + F.state_base + j);
                 if ((st & FLAG_MASK) == 0) { stalled = true; e0 = TERM; break; }      // watchdog: see MSV1_SPIN_LIMIT
                 if ((st & FLAG_MASK) == FLAG_INCL) { e0 = nib(acc, (uint32_t)st & 15u); break; }
                 acc = compose<NENT>((st & 0xFFFFFFFFFull) | MAP_TERM, acc);
@@ -461,9 +512,10 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
             if (publish) st_state(slot, FLAG_AGG | tot);
             int j = (int)tile - 1;
             for (;;) {
-                u64 st;
+                // the prefetched word may hold the predecessor's AGGREGATE where its inclusive sum has arrived since: both are valid
+                u64 st = (j == (int)tile - 1) ? pf_cnt : 0ull;
                 uint32_t spins = 0;
-                do { st = ld_state(tile_cnt + F.state_base + j); } while ((st & FLAG_MASK) == 0 && ++spins < MSV1_SPIN_LIMIT);
+                while ((st & FLAG_MASK) == 0 && ++spins < MSV1_SPIN_LIMIT) st = ld_state(tile_cnt + F.state_base + j);
                 if ((st & FLAG_MASK) == 0) { atomicOr(F.status, ST_ERROR); first = nblocks; break; }   // watchdog: decode nothing
                 first = sat_add(first, (uint32_t)st, nblocks);
                 if ((st & FLAG_MASK) == FLAG_INCL || j == 0) break;

@@ -280,22 +280,43 @@ __device__ __forceinline__ void sp2_entropy_iframe(Coder &ec, Producer &pq, cons
     P2_FLUSH
 }
 
-template <bool HBM>
-__global__ void __launch_bounds__(64)
-sp2_rc_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
+// ---- job pick-up: one CTA per job; in a launch that holds both coders every SM prefers ONE of them ----------------------
+// The two coders' hot loops do not fit an SM's instruction cache together: with range-coder and rANS warps interleaved on
+// every SM, C3's mixed launch took 147 ms where the slower coder alone takes 104 ms (round 1 saw the same: 190 vs 143 ms).
+// So the jobs of a launch form two queues -- [0, n_rc) range coder, [n_rc, n_rc + n_ans) rANS -- and a CTA takes its job from
+// the queue its SM prefers (SM ids below the range coder's share of the jobs prefer the range coder), falling back to the
+// other queue when its own is empty.  Returns the job index, or -1 (never happens: there is one CTA per job).
+__device__ __forceinline__ int sp2_take_job(uint32_t n_rc, uint32_t n_ans, uint32_t *queue)
 {
-    __shared__ alignas(16) uint8_t shm_bytes[RC_SHARED_I_BYTES];   // RcShared without the tables only P frames use
-    __shared__ RunQueue rq;
-    extern __shared__ uint32_t ring[];                     // the last X + 1 pixels (power of two > X + 65 words)
-    RcShared *shm = reinterpret_cast<RcShared *>(shm_bytes);
-    const SpJob J = jobs[blockIdx.x];
+    if (n_rc == 0u || n_ans == 0u || queue == nullptr) return (int)blockIdx.x;
+    __shared__ int s_job;
+    if (threadIdx.x == 0) {
+        uint32_t smid, nsm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        const bool prefer_rc = (unsigned long long)smid * (n_rc + n_ans) < (unsigned long long)n_rc * nsm;
+        int job = -1;
+        for (int attempt = 0; attempt < 2 && job < 0; attempt++) {
+            const bool rc = (attempt == 0) == prefer_rc;
+            const uint32_t i = atomicAdd(&queue[rc ? 0 : 1], 1u);
+            if (i < (rc ? n_rc : n_ans)) job = (int)(rc ? i : n_rc + i);
+        }
+        s_job = job;
+    }
+    __syncthreads();
+    return s_job;
+}
+
+// ---- coded I frames: entropy warp + reconstruction warp (see the header of this file) ----------------------------------
+template <class Coder, bool HBM>
+__device__ __forceinline__ void sp2_iframe_body(const SpJob &J, Coder &ec, RunQueue &rq, uint32_t *ring)
+{
     const RingRef<HBM> rr = HBM ? RingRef<HBM>{reinterpret_cast<uint32_t *>(J.dst), 0xFFFFFFFFu} : RingRef<HBM>{ring, sp_ring_size(J.X) - 1u};
     const int lane = threadIdx.x & 31;
     const int warp = sp2_pick_roles(&rq);                  // 0 = entropy, 1 = reconstruction
-    RcCoder ec;
     bool failed = false;
     if (warp == 0) {
-        ec.open(J, shm, RC_SMALL_I_BYTES);
+        ec.open_iframe(J);
         Producer pq{&rq, 0u, 0u};
         sp2_entropy_iframe(ec, pq, J, rr);
         pq.push(RQ_END, 0u, 0u);
@@ -305,7 +326,7 @@ sp2_rc_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
     }
     __syncthreads();                                       // R has written every pixel E queued
     if (warp == 0) {
-        ec.close(J, RC_SMALL_I_BYTES);
+        ec.close_frame(J);
         uint32_t bits = ST_CHANGED;
         if (failed) { bits = ST_ERROR; sp_undo_frame(J, true); }
         if (lane == 0) { atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
@@ -317,80 +338,39 @@ sp2_rc_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
     }
 }
 
-__global__ void __launch_bounds__(32)
-sp2_rc_p_kernel(const SpJob *__restrict__ jobs, uint32_t tile_words)
-{
-    __shared__ RcShared shm;
-    extern __shared__ uint32_t ptile_mem[];
-    const SpJob J = jobs[blockIdx.x];
-    uint32_t *ptile = tile_words >= SP_PTILE_WORDS ? ptile_mem : nullptr;
-    RcCoder ec;
-    ec.open(J, &shm, (uint32_t)sizeof(RcSmall));
-    uint32_t bits = 0;
-    if (J.flags & SPJ_RENEW) ec.renewI(&shm.small);
-    else sp_decode_pframe(ec, J, bits, ptile);
-    ec.close(J, (uint32_t)sizeof(RcSmall));
-    if (ec.failed()) {
-        bits = ST_ERROR;
-        if (!(J.flags & SPJ_RENEW)) sp_undo_frame(J, false);
-    }
-    __syncwarp();
-    if (lane_id() == 0) { if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
-    sp_signal_done(J);
-}
+constexpr uint32_t SP2_ANS_I_BYTES = ANS_SMALL_I_BYTES + (uint32_t)sizeof(AnsWork);
+constexpr uint32_t SP2_I_BYTES = RC_SHARED_I_BYTES > SP2_ANS_I_BYTES ? RC_SHARED_I_BYTES : SP2_ANS_I_BYTES;
 
-
-// ---- rANS streams (v3 / v4): the same two kernels on the rANS coder (sp_ans.cuh) ----
 template <bool HBM>
 __global__ void __launch_bounds__(64)
-sp2_ans_i_kernel(const SpJob *__restrict__ jobs, uint32_t ring_words)
+sp2_i_kernel(const SpJob *__restrict__ jobs, uint32_t n_rc, uint32_t n_ans, uint32_t *queue, uint32_t ring_words)
 {
-    __shared__ alignas(16) uint8_t small_bytes[ANS_SMALL_I_BYTES];   // AnsSmall without the tables only P frames use
-    __shared__ AnsWork work;
+    __shared__ alignas(16) uint8_t shm[SP2_I_BYTES];       // one coder's tables: without those only P frames use
     __shared__ RunQueue rq;
-    extern __shared__ uint32_t ring[];
-    const SpJob J = jobs[blockIdx.x];
-    const RingRef<HBM> rr = HBM ? RingRef<HBM>{reinterpret_cast<uint32_t *>(J.dst), 0xFFFFFFFFu} : RingRef<HBM>{ring, sp_ring_size(J.X) - 1u};
-    const int lane = threadIdx.x & 31;
-    const int warp = sp2_pick_roles(&rq);
-    AnsCoder ec;
-    bool failed = false;
-    if (warp == 0) {
-        ec.open(J, reinterpret_cast<AnsSmall *>(small_bytes), &work, ANS_SMALL_I_BYTES);
-        Producer pq{&rq, 0u, 0u};
-        sp2_entropy_iframe(ec, pq, J, rr);
-        pq.push(RQ_END, 0u, 0u);
-        failed = ec.failed();
+    extern __shared__ uint32_t ring[];                     // the last X + 1 pixels (power of two > X + 65 words)
+    const int job = sp2_take_job(n_rc, n_ans, queue);
+    if (job < 0) return;
+    const SpJob J = jobs[job];
+    if (J.flags & SPJ_ANS) {
+        AnsCoder ec;
+        ec.small = reinterpret_cast<AnsSmall *>(shm); ec.wk = reinterpret_cast<AnsWork *>(shm + ANS_SMALL_I_BYTES); ec.small_bytes = ANS_SMALL_I_BYTES;
+        sp2_iframe_body<AnsCoder, HBM>(J, ec, rq, ring);
     } else {
-        sp2_recon_iframe(&rq, J, rr);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        ec.close(J);
-        uint32_t bits = ST_CHANGED;
-        if (failed) { bits = ST_ERROR; sp_undo_frame(J, true); }
-        if (lane == 0) { atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
-    }
-    if (J.done) {
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t *>(J.done) = 1u;
+        RcCoder ec;
+        ec.bind(reinterpret_cast<RcShared *>(shm), RC_SMALL_I_BYTES);
+        sp2_iframe_body<RcCoder, HBM>(J, ec, rq, ring);
     }
 }
 
-__global__ void __launch_bounds__(32)
-sp2_ans_p_kernel(const SpJob *__restrict__ jobs, uint32_t tile_words)
+// ---- P frames and model resets of flat frames: one warp, round 1's frame loop (sp_common.cuh) on the new symbol decoders ----
+template <class Coder>
+__device__ __forceinline__ void sp2_pframe_body(const SpJob &J, Coder &ec, uint32_t *ptile)
 {
-    __shared__ AnsShared shm;
-    extern __shared__ uint32_t ptile_mem[];
-    const SpJob J = jobs[blockIdx.x];
-    uint32_t *ptile = tile_words >= SP_PTILE_WORDS ? ptile_mem : nullptr;
-    AnsCoder ec;
-    ec.open(J, &shm.small, &shm.work, (uint32_t)sizeof(AnsSmall));
+    ec.open_pframe(J);
     uint32_t bits = 0;
     if (J.flags & SPJ_RENEW) ec.renewI();
     else sp_decode_pframe(ec, J, bits, ptile);
-    ec.close(J);
+    ec.close_frame(J);
     if (ec.failed()) {
         bits = ST_ERROR;
         if (!(J.flags & SPJ_RENEW)) sp_undo_frame(J, false);
@@ -398,6 +378,29 @@ sp2_ans_p_kernel(const SpJob *__restrict__ jobs, uint32_t tile_words)
     __syncwarp();
     if (lane_id() == 0) { if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
     sp_signal_done(J);
+}
+
+constexpr uint32_t SP2_P_BYTES = sizeof(RcShared) > sizeof(AnsShared) ? (uint32_t)sizeof(RcShared) : (uint32_t)sizeof(AnsShared);
+
+__global__ void __launch_bounds__(32)
+sp2_p_kernel(const SpJob *__restrict__ jobs, uint32_t n_rc, uint32_t n_ans, uint32_t *queue, uint32_t tile_words)
+{
+    __shared__ alignas(16) uint8_t shm[SP2_P_BYTES];
+    extern __shared__ uint32_t ptile_mem[];
+    const int job = sp2_take_job(n_rc, n_ans, queue);
+    if (job < 0) return;
+    const SpJob J = jobs[job];
+    uint32_t *ptile = tile_words >= SP_PTILE_WORDS ? ptile_mem : nullptr;
+    if (J.flags & SPJ_ANS) {
+        AnsCoder ec;
+        AnsShared *sh = reinterpret_cast<AnsShared *>(shm);
+        ec.small = &sh->small; ec.wk = &sh->work; ec.small_bytes = (uint32_t)sizeof(AnsSmall);
+        sp2_pframe_body(J, ec, ptile);
+    } else {
+        RcCoder ec;
+        ec.bind(reinterpret_cast<RcShared *>(shm), (uint32_t)sizeof(RcSmall));
+        sp2_pframe_body(J, ec, ptile);
+    }
 }
 
 }  // namespace g2
@@ -453,10 +456,8 @@ DevAux *aux_for_current_device()
             ok = ok && cudaEventCreateWithFlags(&A.join[i], cudaEventDisableTiming) == cudaSuccess;
         }
         ok = ok && cudaEventCreateWithFlags(&A.fork, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(g2::sp2_rc_i_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(g2::sp2_rc_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(g2::sp2_ans_i_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(g2::sp2_ans_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(g2::sp2_i_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(g2::sp2_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
         A.ok = ok;
         g_aux_ready.fetch_or(bit, std::memory_order_release);
     }
@@ -464,45 +465,28 @@ DevAux *aux_for_current_device()
 }
 }  // namespace
 
-// Jobs of one dependency level, ordered by the planner: [range-coder I frames | range-coder P frames and model resets |
-// rANS I frames | rANS P frames and model resets].  The groups run as concurrent launches (the level lasts as long as its
-// slowest frame).
-bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_rc_p, uint32_t n_ans_i, uint32_t n_ans_p, uint32_t max_width, cudaStream_t st)
+// Jobs of one dependency level, ordered by the planner: [range-coder I frames | rANS I frames | range-coder P frames and
+// model resets | rANS P frames and model resets].  I frames and P frames are two concurrent launches (the level lasts as long
+// as its slowest frame); d_queue = four zeroed counters (two per launch) for the per-SM coder preference.
+bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_ans_i, uint32_t n_rc_p, uint32_t n_ans_p, uint32_t max_width,
+                      uint32_t *d_queue, cudaStream_t st)
 {
     DevAux *A = aux_for_current_device();
     uint32_t words = 1024;                                             // at least the P-frame block tile (SP_PTILE_WORDS)
     while (words <= max_width + 65u) words <<= 1;                      // >= sp_ring_size(max_width)
     if (!A) return false;                                              // caller falls back to the first-generation kernel
-    if (words > 16384u) words = 0;                                     // > 64 KB (pictures wider than 16 318): the I-frame kernels
-                                                                       // read the row above from the picture in HBM instead
-    const uint32_t n[4] = {n_rc_i, n_rc_p, n_ans_i, n_ans_p};
-    int groups = 0;
-    for (int g = 0; g < 4; g++) groups += n[g] ? 1 : 0;
-    const bool fork = groups > 1;
-    if (fork) cudaEventRecord(A->fork, st);
-    int side = 0; bool first = true;
-    uint32_t off = 0;
-    for (int g = 0; g < 4; g++) {
-        if (!n[g]) continue;
-        cudaStream_t s = st;
-        if (!first) { s = A->s[side]; cudaStreamWaitEvent(s, A->fork, 0); }
-        const SpJob *jobs = d_jobs + off;
-        switch (g) {
-        case 0:
-            if (words) g2::sp2_rc_i_kernel<false><<<n[g], 64, (size_t)words * 4, s>>>(jobs, words);
-            else g2::sp2_rc_i_kernel<true><<<n[g], 64, 0, s>>>(jobs, 0);
-            break;
-        case 1: g2::sp2_rc_p_kernel<<<n[g], 32, (size_t)1024 * 4, s>>>(jobs, 1024); break;
-        case 2:
-            if (words) g2::sp2_ans_i_kernel<false><<<n[g], 64, (size_t)words * 4, s>>>(jobs, words);
-            else g2::sp2_ans_i_kernel<true><<<n[g], 64, 0, s>>>(jobs, 0);
-            break;
-        default: g2::sp2_ans_p_kernel<<<n[g], 32, (size_t)1024 * 4, s>>>(jobs, 1024); break;
-        }
-        if (!first) { cudaEventRecord(A->join[side], s); cudaStreamWaitEvent(st, A->join[side], 0); side++; }
-        first = false;
-        off += n[g];
+    if (words > 16384u) words = 0;                                     // > 64 KB (pictures wider than 16 318): the I-frame kernel
+                                                                       // reads the row above from the picture in HBM instead
+    const uint32_t n_i = n_rc_i + n_ans_i, n_p = n_rc_p + n_ans_p;
+    cudaStream_t sp = st;
+    const bool fork = n_i && n_p;
+    if (fork) { cudaEventRecord(A->fork, st); sp = A->s[0]; cudaStreamWaitEvent(sp, A->fork, 0); }
+    if (n_i) {
+        if (words) g2::sp2_i_kernel<false><<<n_i, 64, (size_t)words * 4, st>>>(d_jobs, n_rc_i, n_ans_i, d_queue, words);
+        else g2::sp2_i_kernel<true><<<n_i, 64, 0, st>>>(d_jobs, n_rc_i, n_ans_i, d_queue, 0);
     }
+    if (n_p) g2::sp2_p_kernel<<<n_p, 32, (size_t)1024 * 4, sp>>>(d_jobs + n_i, n_rc_p, n_ans_p, d_queue ? d_queue + 2 : nullptr, 1024);
+    if (fork) { cudaEventRecord(A->join[0], sp); cudaStreamWaitEvent(st, A->join[0], 0); }
     return true;
 }
 

@@ -548,6 +548,13 @@ struct RcCoder {
         for (int i = (int)lane_id(); i < (int)(bytes / 16); i += 32) g[i] = s[i];
         if (lane_id() == 0) st->gen = gen;
     }
+    // the interface the kernels of sp2_decode.cu use for both coders
+    RcShared *bound; uint32_t bound_bytes;
+    __device__ __forceinline__ void bind(RcShared *shared, uint32_t small_bytes) { bound = shared; bound_bytes = small_bytes; }
+    __device__ __forceinline__ void open_iframe(const SpJob &J) { open(J, bound, bound_bytes); }
+    __device__ __forceinline__ void open_pframe(const SpJob &J) { open(J, bound, bound_bytes); }
+    __device__ __forceinline__ void close_frame(const SpJob &J) { close(J, bound_bytes); }
+    __device__ __forceinline__ void renewI() { renewI(sm); }          // P-frame kernel: every table is in shared memory
 };
 
 }  // namespace g2

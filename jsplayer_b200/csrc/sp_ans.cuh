@@ -1140,6 +1140,10 @@ struct AnsCoder {
         for (int i = (int)lane_id(); i < (int)(nbytes / 16); i += 32) s[i] = g[i];
         __syncwarp();
     }
+    // the interface the kernels of sp2_decode.cu use for both coders (small / wk / small_bytes are set by the kernel)
+    __device__ __forceinline__ void open_iframe(const SpJob &J) { open(J, small, wk, small_bytes); }
+    __device__ __forceinline__ void open_pframe(const SpJob &J) { open(J, small, wk, small_bytes); }
+    __device__ __forceinline__ void close_frame(const SpJob &J) { close(J); }
     __device__ __forceinline__ void close(const SpJob &J)
     {
         AnsState *st = reinterpret_cast<AnsState *>(J.state);
