@@ -124,6 +124,16 @@ enum { JSP_DISPLAY_FLIP = 1 };
 JSP_API int        jsp_batch_download_display(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags, int display_flags);
 /* upload + run + download, chunked and double-buffered over PCIe (the end-to-end path). */
 JSP_API int        jsp_batch_decode_host(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags);
+/* Opt-in end-to-end path for a host that keeps ONE picture per stream and updates it in place -- what a player holding
+ * PreviousFrame() does (Manager.hx:470-477).  The batch is decoded on the device as usual; then, frame index by frame index,
+ * only the 16x16 blocks of a picture that differ from the stream's previous picture cross PCIe (a stream's first frame sends
+ * every block) and host threads patch them into stream_pictures[s] (width*height int32, one per stream, NULL = skip the
+ * stream).  on_frame (may be NULL) is called once per frame, in frame order per stream, when stream_pictures[stream] holds
+ * exactly that frame; flags as jsp_batch_results.  Exact: a block is sent iff one of its pixels differs.  The default
+ * contract -- one whole picture per frame -- stays jsp_batch_decode_host. */
+typedef void (*jsp_frame_fn)(void *user, int32_t stream, int32_t frame, const int32_t *picture, uint8_t flags);
+JSP_API int        jsp_batch_decode_host_delta(jsp_batch *b, int32_t *const *stream_pictures, uint8_t *flags,
+                                               jsp_frame_fn on_frame, void *user);
 /* device pointer (as integer) of output picture i and of the output arena; for device-resident consumers */
 JSP_API uint64_t   jsp_batch_device_frame(jsp_batch *b, int64_t i);
 /* Times `iters` back-to-back jsp_batch_run() passes with CUDA events on the batch's own stream after

@@ -13,6 +13,9 @@ JSP_FRAME_CHANGED, JSP_FRAME_SIGNIFICANT, JSP_FRAME_ERROR, JSP_FRAME_DIFFERS = 1
 JSP_DISPLAY_FLIP = 1
 
 
+FRAME_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint8)      # jsp_frame_fn
+
+
 class PFrameResultC(C.Structure):
     _fields_ = [("data_pnt", C.c_void_p), ("significant_changes", C.c_int32)]
 
@@ -61,6 +64,7 @@ PROTOTYPES = {
     "jsp_batch_results": (C.c_int, [C.c_void_p, C.c_void_p]),
     "jsp_batch_next_significant": (C.c_int64, [C.c_void_p, C.c_int, C.c_int64]),
     "jsp_batch_decode_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jsp_batch_decode_host_delta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jsp_batch_device_frame": (C.c_uint64, [C.c_void_p, C.c_int64]),
     "jsp_batch_time_runs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jsp_batch_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -233,6 +233,38 @@ class BatchDecoder:
         self._check(self._lib.jsp_batch_decode_host(self._h, self._out_ptrs(outs), flags.ctypes.data), "jsp_batch_decode_host")
         return outs, flags
 
+    def alloc_stream_pictures(self, pinned=False):
+        """One picture per STREAM (for decode_host_delta)."""
+        shapes = [(sp.height, sp.width) for sp in self.specs]
+        if pinned:
+            pb = PinnedBuffer(sum(h * w for h, w in shapes) * 4, np.int32)
+            self._keep.append(pb)
+            out, cur = [], 0
+            for h, w in shapes:
+                out.append(pb.array[cur:cur + h * w].reshape(h, w)); cur += h * w
+            return out
+        return [np.zeros(s, dtype=np.int32) for s in shapes]
+
+    def decode_host_delta(self, pictures=None, on_frame=None):
+        """Opt-in end-to-end path (jsp_batch_decode_host_delta): one picture per stream, updated in place frame by frame from
+        the 16x16 blocks that changed; on_frame(stream, frame, picture, flags) sees every frame in order.  Returns
+        (pictures, flags): the pictures hold every stream's LAST frame."""
+        if pictures is None:
+            pictures = self.alloc_stream_pictures()
+        ptrs = (C.c_void_p * len(self.specs))()
+        for i, a in enumerate(pictures):
+            if a is not None:
+                assert a.dtype == np.int32 and a.flags.c_contiguous
+                ptrs[i] = a.ctypes.data
+        flags = np.zeros(self.n_frames, dtype=np.uint8)
+        cb = None
+        if on_frame is not None:
+            def _cb(user, stream, frame, pic, fl):
+                on_frame(int(stream), int(frame), pictures[stream], int(fl))
+            cb = _lib.FRAME_FN(_cb)
+        self._check(self._lib.jsp_batch_decode_host_delta(self._h, ptrs, flags.ctypes.data, cb, None), "jsp_batch_decode_host_delta")
+        return pictures, flags
+
     def decode(self, specs, significance=None):
         self.configure(specs)
         return self.decode_host()

@@ -551,6 +551,7 @@ void jsp_batch_destroy(jsp_batch *b)
     if (!b) return;
     cudaSetDevice(b->device);
     cudaDeviceSynchronize();
+    delta_release(b);
     for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : b->ev_sync) cudaEventDestroy(e);
 

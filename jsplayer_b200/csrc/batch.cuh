@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+struct jsp_batch;
 namespace jsp {
 
 void set_error(const char *fmt, ...);
@@ -52,6 +53,7 @@ void sp2_rc_state_init(void *d_state, void *d_rows, uint32_t gen0, cudaStream_t 
 bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_ans_i, uint32_t n_rc_p, uint32_t n_ans_p, uint32_t max_width,
                       uint32_t *d_queue, cudaStream_t st);
 
+struct DeltaStages;
 struct StreamRec {
     int codec, w, h, bpp;
     int n_frames;
@@ -107,6 +109,7 @@ struct Plan {
     size_t spjob_off = 0, n_spjobs = 0;            // slice of d_spjobs
 };
 
+void delta_release(struct ::jsp_batch *b);                  // delta.cu
 }  // namespace jsp
 
 struct jsp_batch {
@@ -157,6 +160,8 @@ struct jsp_batch {
 
     uint32_t *h_status = nullptr; size_t h_status_cap = 0;   // pinned
     uint32_t *h_done = nullptr, *d_done = nullptr; size_t done_cap = 0;   // mapped pinned: per-frame completion flags of ScreenPressor frames
+
+    jsp::DeltaStages *delta = nullptr;   // staging of jsp_batch_decode_host_delta (delta.cu)
 
     const int32_t *ext_prev = nullptr;   // previous picture held outside the batch (per-stream drop-in)
     int ext_has_prev = 0;                // codec's prevFrame was non-null before the batch's first frame
