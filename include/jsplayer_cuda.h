@@ -134,6 +134,7 @@ JSP_API int        jsp_batch_decode_host(jsp_batch *b, int32_t *const *out_frame
 typedef void (*jsp_frame_fn)(void *user, int32_t stream, int32_t frame, const int32_t *picture, uint8_t flags);
 JSP_API int        jsp_batch_decode_host_delta(jsp_batch *b, int32_t *const *stream_pictures, uint8_t *flags,
                                                jsp_frame_fn on_frame, void *user);
+JSP_API uint64_t   jsp_batch_delta_bytes(jsp_batch *b);     /* bytes the last jsp_batch_decode_host_delta moved device -> host */
 /* device pointer (as integer) of output picture i and of the output arena; for device-resident consumers */
 JSP_API uint64_t   jsp_batch_device_frame(jsp_batch *b, int64_t i);
 /* Times `iters` back-to-back jsp_batch_run() passes with CUDA events on the batch's own stream after

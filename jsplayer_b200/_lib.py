@@ -65,6 +65,7 @@ PROTOTYPES = {
     "jsp_batch_next_significant": (C.c_int64, [C.c_void_p, C.c_int, C.c_int64]),
     "jsp_batch_decode_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "jsp_batch_decode_host_delta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jsp_batch_delta_bytes": (C.c_uint64, [C.c_void_p]),
     "jsp_batch_device_frame": (C.c_uint64, [C.c_void_p, C.c_int64]),
     "jsp_batch_time_runs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jsp_batch_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

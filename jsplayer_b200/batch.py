@@ -265,6 +265,10 @@ class BatchDecoder:
         self._check(self._lib.jsp_batch_decode_host_delta(self._h, ptrs, flags.ctypes.data, cb, None), "jsp_batch_decode_host_delta")
         return pictures, flags
 
+    def delta_bytes(self):
+        """Bytes the last decode_host_delta moved device -> host."""
+        return int(self._lib.jsp_batch_delta_bytes(self._h))
+
     def decode(self, specs, significance=None):
         self.configure(specs)
         return self.decode_host()

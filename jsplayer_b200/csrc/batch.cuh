@@ -162,6 +162,7 @@ struct jsp_batch {
     uint32_t *h_done = nullptr, *d_done = nullptr; size_t done_cap = 0;   // mapped pinned: per-frame completion flags of ScreenPressor frames
 
     jsp::DeltaStages *delta = nullptr;   // staging of jsp_batch_decode_host_delta (delta.cu)
+    uint64_t delta_d2h_bytes = 0;        // bytes the last jsp_batch_decode_host_delta moved device -> host
 
     const int32_t *ext_prev = nullptr;   // previous picture held outside the batch (per-stream drop-in)
     int ext_has_prev = 0;                // codec's prevFrame was non-null before the batch's first frame

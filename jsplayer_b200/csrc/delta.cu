@@ -12,6 +12,9 @@
 #include <algorithm>
 #include <atomic>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
 #include <vector>
 #include <cstring>
 
@@ -98,6 +101,9 @@ delta_pack_kernel(const DeltaJob *__restrict__ jobs, DeltaEntry *__restrict__ en
 using namespace jsp;
 
 extern "C" __attribute__((visibility("default")))
+uint64_t jsp_batch_delta_bytes(jsp_batch *b) { return b ? b->delta_d2h_bytes : 0; }
+
+extern "C" __attribute__((visibility("default")))
 int jsp_batch_decode_host_delta(jsp_batch *b, int32_t *const *stream_pictures, uint8_t *flags, jsp_frame_fn on_frame, void *user)
 {
     if (!b || !stream_pictures) { set_error("jsp_batch_decode_host_delta: bad arguments"); return -1; }
@@ -130,6 +136,7 @@ int jsp_batch_decode_host_delta(jsp_batch *b, int32_t *const *stream_pictures, u
             max_jobs = std::max(max_jobs, (size_t)(s - s_lo));
         }
     }
+    b->delta_d2h_bytes = 0;
     if (units.empty()) return 0;
     // two staging sets (device + pinned host), kept with the batch: unit u packs while unit u-1 crosses PCIe and is patched in
     if (!b->delta) b->delta = new DeltaStages();
@@ -150,7 +157,7 @@ int jsp_batch_decode_host_delta(jsp_batch *b, int32_t *const *stream_pictures, u
     DeltaStage *st = DS.st;
     typedef DeltaStage Stage;
     const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    auto pack = [&](size_t u) {                                // queue the pack kernel + the count copy of unit u
+    auto pack = [&](size_t u) {                                // A(u): queue the pack kernel + the count copy of unit u
         const Unit &U = units[u]; Stage &S = st[u & 1];
         uint32_t nj = 0, max_groups = 0;
         for (int s = U.s_lo; s < U.s_hi; s++) {
@@ -165,7 +172,7 @@ int jsp_batch_decode_host_delta(jsp_batch *b, int32_t *const *stream_pictures, u
             max_groups = std::max(max_groups, (J.nb + DELTA_WARPS - 1) / DELTA_WARPS);
             S.h_jobs[nj++] = J;
         }
-        if (!nj) { *S.h_cnt = 0; cudaEventRecord(S.packed, b->st_compute); return true; }
+        if (!nj) { *S.h_cnt = 0; return JSP_CUDA(cudaEventRecord(S.packed, b->st_compute)); }
         bool r = JSP_CUDA(cudaMemcpyAsync(S.d_jobs, S.h_jobs, nj * sizeof(DeltaJob), cudaMemcpyHostToDevice, b->st_compute));
         r = r && JSP_CUDA(cudaMemsetAsync(S.d_cnt, 0, 4, b->st_compute));
         delta_pack_kernel<<<dim3(max_groups, nj), DELTA_WARPS * 32, 0, b->st_compute>>>(S.d_jobs, S.d_ent, S.d_pix, S.d_cnt, (uint32_t)worst_unit);
@@ -174,27 +181,64 @@ int jsp_batch_decode_host_delta(jsp_batch *b, int32_t *const *stream_pictures, u
         r = r && JSP_CUDA(cudaEventRecord(S.packed, b->st_compute));
         return r;
     };
-    if (ok) ok = pack(0);
-    for (size_t u = 0; ok && u < units.size(); u++) {
+    std::vector<uint32_t> counts(units.size(), 0);
+    auto fetch = [&](size_t u) {                               // B(u): the count is known -> queue the D2H of exactly that many blocks
+        Stage &S = st[u & 1];
+        bool r = JSP_CUDA(cudaEventSynchronize(S.packed));
+        const uint32_t n = r ? std::min<uint32_t>(*S.h_cnt, (uint32_t)worst_unit) : 0;
+        counts[u] = n;
+        b->delta_d2h_bytes += 4 + (uint64_t)n * (sizeof(DeltaEntry) + 1024);
+        if (r && n) {
+            r = r && JSP_CUDA(cudaStreamWaitEvent(b->st_out, S.packed, 0));
+            r = r && JSP_CUDA(cudaMemcpyAsync(S.h_ent, S.d_ent, (size_t)n * sizeof(DeltaEntry), cudaMemcpyDeviceToHost, b->st_out));
+            r = r && JSP_CUDA(cudaMemcpyAsync(S.h_pix, S.d_pix, (size_t)n * 1024, cudaMemcpyDeviceToHost, b->st_out));
+        }
+        return r && JSP_CUDA(cudaEventRecord(S.copied, b->st_out));
+    };
+    // host threads that patch blocks into the stream pictures (started once per call; entries of a unit are unique
+    // (stream, block) pairs, so any split of the entry list is race-free)
+    struct Pool {
+        std::vector<std::thread> th;
+        std::mutex mu; std::condition_variable cv_go, cv_done;
+        std::function<void(unsigned)> fn; unsigned gen = 0, pending = 0; bool stop = false;
+        void start(unsigned n) {
+            for (unsigned t = 0; t < n; t++) th.emplace_back([this, t] {
+                unsigned seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_go.wait(lk, [&] { return stop || gen != seen; });
+                    if (stop) return;
+                    seen = gen;
+                    auto f = fn;
+                    lk.unlock();
+                    f(t + 1);
+                    lk.lock();
+                    if (--pending == 0) cv_done.notify_one();
+                }
+            });
+        }
+        void run(const std::function<void(unsigned)> &f) {      // f(0) on the caller, f(1..n) on the pool
+            { std::lock_guard<std::mutex> lk(mu); fn = f; pending = (unsigned)th.size(); gen++; }
+            cv_go.notify_all();
+            f(0);
+            std::unique_lock<std::mutex> lk(mu);
+            cv_done.wait(lk, [&] { return pending == 0; });
+        }
+        ~Pool() { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv_go.notify_all(); for (auto &t : th) t.join(); }
+    } pool;
+    pool.start(hw - 1);
+    std::vector<int> jmap;
+    auto apply = [&](size_t u) {                               // C(u): the blocks are on the host -> patch them in, report the frames
         const Unit &U = units[u]; Stage &S = st[u & 1];
-        ok = ok && JSP_CUDA(cudaEventSynchronize(S.packed));   // the count is on the host
-        const uint32_t n = ok ? *S.h_cnt : 0;
-        if (ok && n) {
-            ok = ok && JSP_CUDA(cudaStreamWaitEvent(b->st_out, S.packed, 0));
-            ok = ok && JSP_CUDA(cudaMemcpyAsync(S.h_ent, S.d_ent, (size_t)n * sizeof(DeltaEntry), cudaMemcpyDeviceToHost, b->st_out));
-            ok = ok && JSP_CUDA(cudaMemcpyAsync(S.h_pix, S.d_pix, (size_t)n * 1024, cudaMemcpyDeviceToHost, b->st_out));
-        }
-        ok = ok && JSP_CUDA(cudaEventRecord(S.copied, b->st_out));
-        if (ok && u + 1 < units.size()) {
-            // the next unit packs into the OTHER staging set, whose previous contents were patched in an iteration ago
-            ok = pack(u + 1);
-        }
-        ok = ok && JSP_CUDA(cudaEventSynchronize(S.copied));
-        if (ok && n) {
-            // patch the blocks into the stream pictures: entries are unique (stream, block) pairs, any split is race-free
-            std::vector<int> jmap;                              // job -> stream
+        if (!JSP_CUDA(cudaEventSynchronize(S.copied))) return false;
+        const uint32_t n = counts[u];
+        if (n) {
+            jmap.clear();                                       // job -> stream
             for (int s = U.s_lo; s < U.s_hi; s++) if (b->streams[s].n_frames > U.k) jmap.push_back(s);
-            auto work = [&](uint32_t lo, uint32_t hi) {
+            const unsigned T = n < 2048 ? 1u : hw;
+            auto work = [&](unsigned t) {
+                if (t >= T) return;
+                const uint32_t lo = (uint32_t)((uint64_t)n * t / T), hi = (uint32_t)((uint64_t)n * (t + 1) / T);
                 for (uint32_t e = lo; e < hi; e++) {
                     const DeltaEntry E = S.h_ent[e];
                     const StreamRec &R = b->streams[jmap[E.job]];
@@ -206,20 +250,28 @@ int jsp_batch_decode_host_delta(jsp_batch *b, int32_t *const *stream_pictures, u
                     const int cols = std::min(16, W - bx * 16), rows = std::min(16, H - by * 16);
                     if (cols <= 0) continue;
                     const int32_t *src = S.h_pix + (size_t)e * 256;
-                    for (int r = 0; r < rows; r++) memcpy(pic + (size_t)(by * 16 + r) * R.w + bx * 16, src + r * 16, (size_t)cols * 4);
+                    int32_t *dst = pic + (size_t)(by * 16) * R.w + bx * 16;
+                    if (cols == 16) for (int r = 0; r < rows; r++) memcpy(dst + (size_t)r * R.w, src + r * 16, 64);
+                    else for (int r = 0; r < rows; r++) memcpy(dst + (size_t)r * R.w, src + r * 16, (size_t)cols * 4);
                 }
             };
-            const unsigned T = n < 4096 ? 1u : hw;
-            std::vector<std::thread> th;
-            for (unsigned t = 1; t < T; t++) th.emplace_back(work, (uint32_t)((uint64_t)n * t / T), (uint32_t)((uint64_t)n * (t + 1) / T));
-            work(0, (uint32_t)((uint64_t)n / T));
-            for (auto &t : th) t.join();
+            if (T == 1) work(0); else pool.run(work);
         }
-        if (ok && on_frame) {                                  // a stream has one unit per frame index: its frame k is complete
+        if (on_frame)                                          // a stream has one unit per frame index: its frame k is complete
             for (int s = U.s_lo; s < U.s_hi; s++)
                 if (b->streams[s].n_frames > U.k && stream_pictures[s])
                     on_frame(user, s, U.k, stream_pictures[s], fl[(size_t)(b->streams[s].first_frame + U.k)]);
-        }
+        return true;
+    };
+    // software pipeline over the two staging sets: while unit u is patched in on the host, unit u+1 crosses PCIe and -- once
+    // u is done with its set -- unit u+2 is packed on the device
+    const size_t nu = units.size();
+    ok = ok && pack(0) && fetch(0);
+    if (ok && nu > 1) ok = pack(1);
+    for (size_t u = 0; ok && u < nu; u++) {
+        if (u + 1 < nu) ok = ok && fetch(u + 1);
+        ok = ok && apply(u);
+        if (u + 2 < nu) ok = ok && pack(u + 2);
     }
     cudaStreamSynchronize(b->st_compute); cudaStreamSynchronize(b->st_out);
     return ok ? 0 : -1;
