@@ -1027,15 +1027,22 @@ struct AnsCoder {
         if (hit) { JSP_AT(0) } else { JSP_AT(5) }
         AnsSlot &S = wk->cache[slot];
         CxHdr &H = S.hdr;
-        const int kind = H.gen == gen ? H.kind : CXK_NONE;
+        // everything the Cx4 fast path reads, loaded at once BEFORE the kind is tested (one shared-memory round trip on the
+        // symbol chain instead of two), plus the next two bitstream bytes for its renormalisation
+        const uint2 hw = *reinterpret_cast<const uint2 *>(&H);          // gen | d, kind, maxpos
+        const uint32_t *bw = reinterpret_cast<const uint32_t *>(S.body);
+        const uint32_t symw = bw[0];
+        const uint2 fw = *reinterpret_cast<const uint2 *>(bw + B_SC_FR / 4);
+        const uint32_t woff = pos - wbase, woffc = min(woff, ANS_WIN - 2u);
+        const uint32_t wb0 = wk->win[woffc], wb1 = wk->win[woffc + 1u];
+        const int kind = hw.x == gen ? (int)((hw.y >> 16) & 0xFFu) : CXK_NONE;
         int c;
         // ---- fast path: a Cx4 context (<= 4 symbols met: the common case on screen content) that HITS one of its
         //      symbols.  SmallContext.decodeSC (ANS.hx:263-309) for S = 4, run by every lane from three shared-memory
         //      words -- no divergence; lane 0 stores the two words that change. ----
         if (kind == CXK_4) {
-            const uint32_t *bw = reinterpret_cast<const uint32_t *>(S.body);
-            const uint32_t symw = bw[0], f01 = bw[B_SC_FR / 4], f23 = bw[B_SC_FR / 4 + 1];
-            const int d = H.d, mp = H.maxpos;
+            const uint32_t f01 = fw.x, f23 = fw.y;
+            const int d = (int)(hw.y & 0xFFFFu), mp = (int)(hw.y >> 24);
             const int q0 = (int)(f01 & 0xFFFFu), q1 = (int)(f01 >> 16), q2 = (int)(f23 & 0xFFFFu), q3 = (int)(f23 >> 16);
             const int tot0 = q0 + q1 + q2 + q3 + 256 - d;                                      // Cx4.decode, :320
             // `while (tot <= PROB_SCALE / 2) { tot <<= 1; shift++; }` in closed form (tot0 is 257 .. 4096 + 3 * 50)
@@ -1077,7 +1084,21 @@ struct AnsCoder {
                     H.maxpos = (uint8_t)nmp;
                 }
                 __syncwarp();
-                advance(hstart << shift, hfr << shift);
+                // decAdvance + the symbol count (ANS.hx:37-44, EntroCoders.hx:249-253): straight-line when the state is normalised,
+                // the two bytes are in the window and no state reload is due -- see try_advance; else the generic pair
+                const uint32_t start = (uint32_t)(hstart << shift), freq = (uint32_t)(hfr << shift), f12 = x & 4095u;
+                if ((x - ANS_L) < (0x80000000u - ANS_L) && woff < ANS_WIN - 2u && pos + 2u <= len && !overrun &&
+                    (freq - 1u) < (uint32_t)ANS_SCALE && f12 >= start && nDec + 1 != ANS_B) {
+                    const uint32_t v = freq * (x >> 12) + (f12 - start);
+                    const uint32_t v1 = (v << 8) | wb0, v2 = (v << 16) | (wb0 << 8) | wb1;
+                    const bool one = v < ANS_L, two = v < (ANS_L >> 8);
+                    x = two ? v2 : (one ? v1 : v);
+                    pos += (one ? 1u : 0u) + (two ? 1u : 0u);
+                    nDec++; nsym++;
+                    JSP_AT(1)
+                    return c;
+                }
+                advance((int)start, (int)freq);
                 JSP_AT(1)
                 count();
                 return c;

@@ -174,11 +174,18 @@ size_t jsp_sp_enc_pframe(sp_enc *e, const int32_t *px, const int32_t *prev, int 
     }
     e->cx = e->cx1 = 0;
     int lastmx = 0, lastmy = 0, have_last = 0;
+    /* What the DECODER has in its destination while it decodes a block: the previous picture (ScreenPressor.hx:468-474 copies
+     * unchanged blocks; DESIGN.md section 2 defines the start of a P frame as the previous picture) with the blocks decoded
+     * so far replaced.  The predictors read neighbours from there -- at a picture's first column "left" and "above-left"
+     * wrap to the previous row's LAST pixel, which belongs to a block decoded later and so still shows the previous frame. */
+    int32_t *dv = (int32_t *)malloc((size_t)X * Y * sizeof(int32_t));
+    memcpy(dv, prev, (size_t)X * Y * sizeof(int32_t));
     for (int bi = first; bi <= last; bi++) {
         const int bt = e->bts[bi];
         if (!bt) continue;
         const int bx = bi % nbx, by = bi / nbx, x16 = bx * 16, y16 = by * 16;
         const int x1 = rect[bi * 4], y1 = rect[bi * 4 + 1], x2 = rect[bi * 4 + 2], y2 = rect[bi * 4 + 3];
+        for (int y = y1; y < y2; y++) memcpy(dv + (long)y * X + x1, px + (long)y * X + x1, (size_t)(x2 - x1) * sizeof(int32_t));
         if ((bt - 1) & 1) {
             ec->sxy(ec, 0, x1 - x16); ec->sxy(ec, 1, y1 - y16); ec->sxy(ec, 2, x2 - 1 - x16); ec->sxy(ec, 3, y2 - 1 - y16);
         }
@@ -199,15 +206,15 @@ size_t jsp_sp_enc_pframe(sp_enc *e, const int32_t *px, const int32_t *prev, int 
         while (pos < total) {
             const int lim = total - pos < 255 ? total - pos : 255;
             int best = 0, bestn = 0, n;
-            for (n = 0; n < lim; n++) { long i = PIX(pos + n); if (i < 1 || px[i] != px[i - 1]) break; }
+            for (n = 0; n < lim; n++) { long i = PIX(pos + n); if (i < 1 || px[i] != dv[i - 1]) break; }
             if (n > bestn) { bestn = n; best = 1; }
-            for (n = 0; n < lim; n++) { long i = PIX(pos + n); if (i - X < 0 || px[i] != px[i - X]) break; }
+            for (n = 0; n < lim; n++) { long i = PIX(pos + n); if (i - X < 0 || px[i] != dv[i - X]) break; }
             if (n > bestn) { bestn = n; best = 2; }
             for (n = 0; n < lim; n++) { long i = PIX(pos + n); if (px[i] != prev[i]) break; }
             if (n > bestn) { bestn = n; best = 3; }
-            for (n = 0; n < lim; n++) { long i = PIX(pos + n); if (i - X - 1 < 0 || px[i] != grad(px[i - 1], px[i - X], px[i - X - 1])) break; }
+            for (n = 0; n < lim; n++) { long i = PIX(pos + n); if (i - X - 1 < 0 || px[i] != grad(dv[i - 1], dv[i - X], dv[i - X - 1])) break; }
             if (n > bestn) { bestn = n; best = 4; }
-            for (n = 0; n < lim; n++) { long i = PIX(pos + n); if (i - X - 1 < 0 || px[i] != px[i - X - 1]) break; }
+            for (n = 0; n < lim; n++) { long i = PIX(pos + n); if (i - X - 1 < 0 || px[i] != dv[i - X - 1]) break; }
             if (n > bestn) { bestn = n; best = 5; }
             if (bestn == 0) {
                 best = 0; clr = px[PIX(pos)];
@@ -222,7 +229,7 @@ size_t jsp_sp_enc_pframe(sp_enc *e, const int32_t *px, const int32_t *prev, int 
         }
 #undef PIX
     }
-    free(rect);
+    free(rect); free(dv);
     size_t n = ec->finish(ec, out + 1, cap - 1);
     return n ? n + 1 : 0;
 }
