@@ -709,17 +709,18 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
     }
     myflags = __reduce_or_sync(FULL, myflags);
     if (lane == 0 && myflags) atomicOr(&sm.flags, myflags);
+    uint32_t *const status_ptr = F.status; // read now: the next tile's descriptor is staged over this one right after the barrier
     if (tid == 0) sm.tk[3] = tk3;
-    __syncthreads();                       // also: every thread is done with this tile's shared-memory buffers
-    if (tid == 0 && sm.flags) atomicOr(F.status, sm.flags);
-    // ---- rotate the pipeline ----
+    __syncthreads();                       // every thread is done with this tile's shared-memory buffers
+    if (tid == 0 && sm.flags) atomicOr(status_ptr, sm.flags);
+    // ---- rotate the pipeline ----  (no second barrier: thread 0 rewrites sm.tk[3] only after the next tile's barriers, and
+    //      the words it resets at the top of the loop are read by the others only before the barrier above)
     tk0 = tk1; e0 = e1;
     tk1 = tk2; e1 = e2;
     tk2 = sm.tk[3];
     if (tk0 >= n_tiles) break;
     if (tk2 < n_tiles) e2 = tiles[tk2];
     cur ^= 1;
-    __syncthreads();                       // sm.tk[3] and sm.flags are rewritten by thread 0 at the top of the loop
   }
     cp_async_wait<0>();
 }

@@ -40,6 +40,9 @@ __device__ unsigned long long g_sp2_prof[16];
 #define P2_FLUSH
 #endif
 
+// how long the reconstruction warp sleeps between two looks at an empty queue (JSP_SP2_POLL_NS overrides: tuning knob)
+__device__ unsigned int g_sp2_poll_ns = 32;
+
 // ---- E -> R run queue (shared memory, single producer / single consumer) -------------------------------------------
 // One entry = two words, BOTH carrying generation bits of the slot (run index / RQ_N + 1), so a torn read can never pass
 // for a complete entry:  w0 = colour | type << 24 | (gen & 31) << 27,  w1 = length | (gen & 0xFFFF) << 16.
@@ -161,7 +164,7 @@ __device__ __forceinline__ void sp2_recon_iframe(RunQueue *q, const SpJob &J, co
         for (;;) {
             e = ld_volatile_v2(&q->e[consumed % RQ_N]);
             if (((e.x >> 27) == (gen & 31u)) && ((e.y >> 16) == (gen & 0xFFFFu))) break;
-            __nanosleep(32);
+            __nanosleep(g_sp2_poll_ns);
         }
         P2_T(8)
         const uint32_t type = (e.x >> 24) & 7u, clr = e.x & 0xFFFFFFu;
@@ -341,24 +344,31 @@ __device__ __forceinline__ void sp2_iframe_body(const SpJob &J, Coder &ec, RunQu
 constexpr uint32_t SP2_ANS_I_BYTES = ANS_SMALL_I_BYTES + (uint32_t)sizeof(AnsWork);
 constexpr uint32_t SP2_I_BYTES = RC_SHARED_I_BYTES > SP2_ANS_I_BYTES ? RC_SHARED_I_BYTES : SP2_ANS_I_BYTES;
 
-template <bool HBM>
+// CODERS: 1 = the launch holds range-coder frames only, 2 = rANS only, 3 = both (a kernel that holds one coder keeps that
+// coder's registers and code layout: the range coder is 7 % slower per symbol inside the two-coder kernel)
+template <bool HBM, int CODERS>
 __global__ void __launch_bounds__(64)
 sp2_i_kernel(const SpJob *__restrict__ jobs, uint32_t n_rc, uint32_t n_ans, uint32_t *queue, uint32_t ring_words)
 {
-    __shared__ alignas(16) uint8_t shm[SP2_I_BYTES];       // one coder's tables: without those only P frames use
+    constexpr uint32_t BYTES = CODERS == 1 ? RC_SHARED_I_BYTES : (CODERS == 2 ? SP2_ANS_I_BYTES : SP2_I_BYTES);
+    __shared__ alignas(16) uint8_t shm[BYTES];             // one coder's tables: without those only P frames use
     __shared__ RunQueue rq;
     extern __shared__ uint32_t ring[];                     // the last X + 1 pixels (power of two > X + 65 words)
     const int job = sp2_take_job(n_rc, n_ans, queue);
     if (job < 0) return;
     const SpJob J = jobs[job];
-    if (J.flags & SPJ_ANS) {
-        AnsCoder ec;
-        ec.small = reinterpret_cast<AnsSmall *>(shm); ec.wk = reinterpret_cast<AnsWork *>(shm + ANS_SMALL_I_BYTES); ec.small_bytes = ANS_SMALL_I_BYTES;
-        sp2_iframe_body<AnsCoder, HBM>(J, ec, rq, ring);
+    if (CODERS == 2 || (CODERS == 3 && (J.flags & SPJ_ANS))) {
+        if constexpr (CODERS != 1) {
+            AnsCoder ec;
+            ec.small = reinterpret_cast<AnsSmall *>(shm); ec.wk = reinterpret_cast<AnsWork *>(shm + ANS_SMALL_I_BYTES); ec.small_bytes = ANS_SMALL_I_BYTES;
+            sp2_iframe_body<AnsCoder, HBM>(J, ec, rq, ring);
+        }
     } else {
-        RcCoder ec;
-        ec.bind(reinterpret_cast<RcShared *>(shm), RC_SMALL_I_BYTES);
-        sp2_iframe_body<RcCoder, HBM>(J, ec, rq, ring);
+        if constexpr (CODERS != 2) {
+            RcCoder ec;
+            ec.bind(reinterpret_cast<RcShared *>(shm), RC_SMALL_I_BYTES);
+            sp2_iframe_body<RcCoder, HBM>(J, ec, rq, ring);
+        }
     }
 }
 
@@ -382,24 +392,30 @@ __device__ __forceinline__ void sp2_pframe_body(const SpJob &J, Coder &ec, uint3
 
 constexpr uint32_t SP2_P_BYTES = sizeof(RcShared) > sizeof(AnsShared) ? (uint32_t)sizeof(RcShared) : (uint32_t)sizeof(AnsShared);
 
+template <int CODERS>
 __global__ void __launch_bounds__(32)
 sp2_p_kernel(const SpJob *__restrict__ jobs, uint32_t n_rc, uint32_t n_ans, uint32_t *queue, uint32_t tile_words)
 {
-    __shared__ alignas(16) uint8_t shm[SP2_P_BYTES];
+    constexpr uint32_t BYTES = CODERS == 1 ? (uint32_t)sizeof(RcShared) : (CODERS == 2 ? (uint32_t)sizeof(AnsShared) : SP2_P_BYTES);
+    __shared__ alignas(16) uint8_t shm[BYTES];
     extern __shared__ uint32_t ptile_mem[];
     const int job = sp2_take_job(n_rc, n_ans, queue);
     if (job < 0) return;
     const SpJob J = jobs[job];
     uint32_t *ptile = tile_words >= SP_PTILE_WORDS ? ptile_mem : nullptr;
-    if (J.flags & SPJ_ANS) {
-        AnsCoder ec;
-        AnsShared *sh = reinterpret_cast<AnsShared *>(shm);
-        ec.small = &sh->small; ec.wk = &sh->work; ec.small_bytes = (uint32_t)sizeof(AnsSmall);
-        sp2_pframe_body(J, ec, ptile);
+    if (CODERS == 2 || (CODERS == 3 && (J.flags & SPJ_ANS))) {
+        if constexpr (CODERS != 1) {
+            AnsCoder ec;
+            AnsShared *sh = reinterpret_cast<AnsShared *>(shm);
+            ec.small = &sh->small; ec.wk = &sh->work; ec.small_bytes = (uint32_t)sizeof(AnsSmall);
+            sp2_pframe_body(J, ec, ptile);
+        }
     } else {
-        RcCoder ec;
-        ec.bind(reinterpret_cast<RcShared *>(shm), (uint32_t)sizeof(RcSmall));
-        sp2_pframe_body(J, ec, ptile);
+        if constexpr (CODERS != 2) {
+            RcCoder ec;
+            ec.bind(reinterpret_cast<RcShared *>(shm), (uint32_t)sizeof(RcSmall));
+            sp2_pframe_body(J, ec, ptile);
+        }
     }
 }
 
@@ -456,8 +472,13 @@ DevAux *aux_for_current_device()
             ok = ok && cudaEventCreateWithFlags(&A.join[i], cudaEventDisableTiming) == cudaSuccess;
         }
         ok = ok && cudaEventCreateWithFlags(&A.fork, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(g2::sp2_i_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(g2::sp2_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(g2::sp2_i_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(g2::sp2_i_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(g2::sp2_i_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess;
+        if (const char *e = getenv("JSP_SP2_POLL_NS")) {
+            const unsigned int ns = (unsigned int)atoi(e);
+            ok = ok && cudaMemcpyToSymbol(g2::g_sp2_poll_ns, &ns, sizeof ns) == cudaSuccess;
+        }
         A.ok = ok;
         g_aux_ready.fetch_or(bit, std::memory_order_release);
     }
@@ -482,10 +503,20 @@ bool launch_sp2_level(const SpJob *d_jobs, uint32_t n_rc_i, uint32_t n_ans_i, ui
     const bool fork = n_i && n_p;
     if (fork) { cudaEventRecord(A->fork, st); sp = A->s[0]; cudaStreamWaitEvent(sp, A->fork, 0); }
     if (n_i) {
-        if (words) g2::sp2_i_kernel<false><<<n_i, 64, (size_t)words * 4, st>>>(d_jobs, n_rc_i, n_ans_i, d_queue, words);
-        else g2::sp2_i_kernel<true><<<n_i, 64, 0, st>>>(d_jobs, n_rc_i, n_ans_i, d_queue, 0);
+        const int coders = (n_rc_i ? 1 : 0) | (n_ans_i ? 2 : 0);
+        const size_t dyn = (size_t)words * 4;
+#define JSP_LAUNCH_I(HBM, C) g2::sp2_i_kernel<HBM, C><<<n_i, 64, dyn, st>>>(d_jobs, n_rc_i, n_ans_i, d_queue, words)
+        if (words) { if (coders == 1) JSP_LAUNCH_I(false, 1); else if (coders == 2) JSP_LAUNCH_I(false, 2); else JSP_LAUNCH_I(false, 3); }
+        else       { if (coders == 1) JSP_LAUNCH_I(true, 1);  else if (coders == 2) JSP_LAUNCH_I(true, 2);  else JSP_LAUNCH_I(true, 3); }
+#undef JSP_LAUNCH_I
     }
-    if (n_p) g2::sp2_p_kernel<<<n_p, 32, (size_t)1024 * 4, sp>>>(d_jobs + n_i, n_rc_p, n_ans_p, d_queue ? d_queue + 2 : nullptr, 1024);
+    if (n_p) {
+        const int coders = (n_rc_p ? 1 : 0) | (n_ans_p ? 2 : 0);
+        uint32_t *q = d_queue ? d_queue + 2 : nullptr;
+        if (coders == 1) g2::sp2_p_kernel<1><<<n_p, 32, (size_t)1024 * 4, sp>>>(d_jobs + n_i, n_rc_p, n_ans_p, q, 1024);
+        else if (coders == 2) g2::sp2_p_kernel<2><<<n_p, 32, (size_t)1024 * 4, sp>>>(d_jobs + n_i, n_rc_p, n_ans_p, q, 1024);
+        else g2::sp2_p_kernel<3><<<n_p, 32, (size_t)1024 * 4, sp>>>(d_jobs + n_i, n_rc_p, n_ans_p, q, 1024);
+    }
     if (fork) { cudaEventRecord(A->join[0], sp); cudaStreamWaitEvent(st, A->join[0], 0); }
     return true;
 }
