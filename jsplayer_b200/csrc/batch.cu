@@ -177,10 +177,16 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
             std::vector<int64_t> fin;
             for (int64_t f : by_level[lv]) {
                 FrameRec &R = b->frames[f];
-                if (R.kind != FK_COPY && R.kind != FK_SP_P && R.kind != FK_SP_FLAT) continue;
                 const StreamRec &S = b->streams[R.stream];
+                // A sparse MSVideo1 inter frame (mostly skip runs: fewer than 3 bytes per block) starts as a wide copy of the
+                // previous picture; its decode then only writes the coded blocks.  Inside the decode kernel the skipped blocks
+                // are copied by the CTA that owns the bitstream tile -- a 320x240 frame is ONE tile, so one CTA would copy the
+                // whole picture (C1: 37 us per frame); many CTAs of the copy kernel do it in a few.
+                R.precopy = (R.kind == FK_MSV16 || R.kind == FK_MSV8) && !R.key && R.prev >= 0 && R.level > 0 &&
+                            (uint64_t)R.len < 3ull * (uint64_t)(S.w >> 2) * (uint64_t)(S.h >> 2);
+                if (R.kind != FK_COPY && R.kind != FK_SP_P && R.kind != FK_SP_FLAT && !R.precopy) continue;
                 if (S.codec == JSP_CODEC_SCREENPRESSOR) continue;          // ScreenPressor levels are planned below
-                fin.push_back(f);
+                if (!R.precopy) fin.push_back(f);                          // a pre-copied picture is final after its decode
                 CopyJob J;
                 J.dst = b->d_out + R.out_off;
                 J.src = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
@@ -355,7 +361,7 @@ static void fill_mframes(jsp_batch *b, HostTables &T)
         M.n_tiles = R.n_tiles;
         M.state_base = R.state_base;
         M.insign_blocks = (uint32_t)std::max(0, (b->insign_lines + 3) >> 2);
-        M.flags = R.prev >= 0 ? MSV1_F_HAS_PRED : 0u;
+        M.flags = (R.prev >= 0 ? MSV1_F_HAS_PRED : 0u) | (R.precopy ? MSV1_F_PRECOPIED : 0u);
         M.inv_nbx = M.nbx > 1 ? (uint32_t)(0x100000000ull / M.nbx) : 0xFFFFFFFFu;
         if (!b->chunks.empty()) { T.mframes[N + f] = M; T.mframes[N + f].state_base = R.state_base2; }
     }
@@ -658,7 +664,7 @@ static int64_t batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_st
             // per kernel class (DESIGN.md "Algorithmic bytes"): what each kernel must move for this frame
             const int kent = (S.codec == JSP_CODEC_SCREENPRESSOR && b->sp_hosts[s].version > 2) ? JSP_K_SP_ENTROPY_ANS : JSP_K_SP_ENTROPY_RC;
             switch (R.kind) {
-            case FK_MSV16: case FK_MSV8: b->stat_k_bytes[JSP_K_MSV1_DECODE] += npix * 4 + R.len; break;
+            case FK_MSV16: case FK_MSV8: b->stat_k_bytes[JSP_K_MSV1_DECODE] += npix * 4 + R.len; break;   // (+ 8 B / pixel in frame_copy for pre-copied sparse frames, not counted)
             case FK_COPY:    b->stat_k_bytes[JSP_K_FRAME_COPY] += npix * 8; break;
             case FK_SP_FLAT: b->stat_k_bytes[JSP_K_FRAME_COPY] += npix * 4; break;
             case FK_SP_P:    b->stat_k_bytes[JSP_K_FRAME_COPY] += npix * 8; b->stat_k_bytes[kent] += R.len; break;

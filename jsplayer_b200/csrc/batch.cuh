@@ -73,6 +73,7 @@ struct FrameRec {
     int level;
     int kind;
     uint8_t key;
+    bool precopy = false;           // sparse MSVideo1 inter frame: the level's copy launch writes the previous picture first
     uint8_t key_in;                 // the caller's key flag (key may be demoted: a "key" frame that copies from its predecessor)
     uint32_t n_tiles, state_base;
     uint32_t state_base2;           // the frame's tile-state slice in the chunked (pipelined) plans

@@ -21,6 +21,7 @@ enum : uint32_t {
 // ---- MSVideo1 ----
 enum : uint32_t {
     MSV1_F_HAS_PRED = 1u << 0,   // the stream has an earlier frame (prev == nullptr then means "not ordered", not "none")
+    MSV1_F_PRECOPIED = 1u << 1,  // the output already holds the previous picture: skip runs need no copy
 };
 
 struct Msv1Frame {

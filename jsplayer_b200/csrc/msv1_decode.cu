@@ -674,7 +674,8 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
         }
 
         // ---- skip runs: warp per run, 16-byte copies from the previous picture ----
-        const uint32_t nruns = sm.nruns;
+        const bool precopied = (F.flags & MSV1_F_PRECOPIED) != 0;     // skipped blocks already hold the previous picture
+        const uint32_t nruns = precopied ? 0u : sm.nruns;
         for (uint32_t r = warp; r < nruns; r += 4) {
             const uint32_t op = sm.runs[r];
             const uint32_t blk0 = sm.blk[op];
@@ -688,7 +689,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
             if (n && !F.prev && (F.flags & MSV1_F_HAS_PRED)) myflags |= ST_NEEDS_PREV;
         }
         // ---- "rest of the frame is copied" (skip count 0 / 8-bit terminator): whole CTA ----
-        const uint32_t big0 = sm.big_blk0;
+        const uint32_t big0 = precopied ? 0xFFFFFFFFu : sm.big_blk0;
         if (big0 < nblocks) {
             for (uint32_t blk = big0 + tid; blk < nblocks; blk += MSV1_THREADS) {
                 const uint32_t by = blk / nbx, bx = blk - by * nbx;
