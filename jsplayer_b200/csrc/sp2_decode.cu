@@ -431,6 +431,17 @@ extern "C" __attribute__((visibility("default"))) int jsp_debug_sp2_profile(unsi
 }
 #endif
 
+#ifdef JSP_PROFILE_SECTIONS
+// the colour-decoder section timers of sp_ans.cuh as THIS translation unit's kernels accumulated them
+extern "C" __attribute__((visibility("default"))) int jsp_debug_ans2_profile(unsigned long long *out, int reset)
+{
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyFromSymbol(out, g_ans_prof, sizeof z) != cudaSuccess) return -1;
+    if (reset) cudaMemcpyToSymbol(g_ans_prof, z, sizeof z);
+    return 0;
+}
+#endif
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 int sp_generation()
 {

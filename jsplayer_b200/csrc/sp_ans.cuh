@@ -1037,6 +1037,10 @@ struct AnsCoder {
         const uint32_t wb0 = wk->win[woffc], wb1 = wk->win[woffc + 1u];
         const int kind = hw.x == gen ? (int)((hw.y >> 16) & 0xFFu) : CXK_NONE;
         int c;
+        // (Measured dead end: keeping the interval arithmetic of this path as a "decode-ready" record beside the context -- four
+        // scaled starts and frequencies, rebuilt after every update -- shortens the symbol chain to a load and four compares, but
+        // the rebuild costs as many instructions as it saves and an in-order warp pays for them all the same: 574 -> 627 cycles
+        // per symbol.)
         // ---- fast path: a Cx4 context (<= 4 symbols met: the common case on screen content) that HITS one of its
         //      symbols.  SmallContext.decodeSC (ANS.hx:263-309) for S = 4, run by every lane from three shared-memory
         //      words -- no divergence; lane 0 stores the two words that change. ----
@@ -1174,6 +1178,9 @@ struct AnsCoder {
         const uint4 *s = reinterpret_cast<const uint4 *>(small);
         for (int i = (int)lane_id(); i < (int)(small_bytes / 16); i += 32) g[i] = s[i];
         if (lane_id() == 0) st->gen = gen;
+#ifdef JSP_PROFILE_SECTIONS
+        if (lane_id() == 0) for (int k = 0; k < 16; k++) atomicAdd(&g_ans_prof[k], (unsigned long long)aprof[k]);
+#endif
     }
 
     __device__ __forceinline__ bool decodeBool()                                      // EntroCoders.hx:259-269
@@ -1217,9 +1224,6 @@ __device__ __forceinline__ void sp_ans_run(const SpJob &J, AnsShared &sm, uint32
     __syncwarp();
     if (lane == 0) { if (bits) atomicOr(J.status, bits); if (J.symbols) *J.symbols = ec.nsym; }
     sp_signal_done(J);
-#ifdef JSP_PROFILE_SECTIONS
-    if (lane == 0) for (int k = 0; k < 16; k++) atomicAdd(&g_ans_prof[k], (unsigned long long)ec.aprof[k]);
-#endif
 }
 
 }  // namespace jsp
