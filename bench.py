@@ -85,7 +85,7 @@ class C2(Workload):
 class MSV1Streams(Workload):
     """MSVideo1 streams with P frames: a key frame, then P frames whose blocks are skipped in runs (SURVEY.md 8d C1 recipe:
     85 % skipped, geometric runs of mean 40 carried across rows, coded blocks 40/40/20 % 1-/2-/8-colour)."""
-    dominant = 0
+    dominant = -1                                 # whichever kernel takes most of the step (the wide copy of sparse P frames)
 
     def __init__(self, name, is8, width, height, streams, frames_per_stream, seed, metric, desc):
         self.name, self.is8, self.W, self.H, self.n, self.fps, self.seed = name, is8, width, height, streams, frames_per_stream, seed
@@ -520,7 +520,7 @@ def measure(wl, args, rank, local_rank, world, dist, torch, with_e2e=True, with_
         from jsplayer_b200 import _lib
         peak, peak_src = hbm_peak()
         k = wl.dominant
-        if kcnt[k] == 0:                              # e.g. a rANS-only or mixed-coder ScreenPressor run
+        if k < 0 or kcnt[k] == 0:                     # e.g. a mixed-coder ScreenPressor run, or inter-frame MSVideo1 (wide copy + decode)
             k = max(range(len(kcnt)), key=lambda i: kms[i])
         n_launch = max(1, kcnt[k])
         k_ms = kms[k] / n_launch                      # average launch duration of the dominant kernel
@@ -543,7 +543,7 @@ def measure(wl, args, rank, local_rank, world, dist, torch, with_e2e=True, with_
             "kernels": {_lib.KERNEL_NAMES[i]: {"launches": int(kcnt[i]), "ms": round(kms[i], 4)} for i in range(len(kcnt)) if kcnt[i]},
             "clocks": clocks,
         }
-        hbm = {"bound": "hbm", "kernel": _lib.KERNEL_NAMES[k] if not wl.dominant_name.startswith("msv1") else wl.dominant_name,
+        hbm = {"bound": "hbm", "kernel": wl.dominant_name if (wl.dominant_name.startswith("msv1") and k == 0) else _lib.KERNEL_NAMES[k],
                "achieved": achieved, "peak": peak, "unit": "GB/s",
                "frac": achieved / peak, "traffic": ncu_traffic(_lib.KERNEL_NAMES[k] + "_bytes_per_launch"),
                "peak_source": peak_src, "alg_bytes_per_launch": alg_launch, "launch_ms": k_ms,

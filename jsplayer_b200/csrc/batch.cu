@@ -468,6 +468,15 @@ static bool plan_and_upload(jsp_batch *b)
     HostTables T;
     size_t state_cursor = 0, ticket_cursor = 0;
     build_plan(b, b->whole, 0, (int)b->streams.size(), T, state_cursor, ticket_cursor);
+    // algorithmic bytes per kernel class: a pre-copied sparse MSVideo1 frame is written by the copy kernel (8 B / pixel: read the
+    // previous picture, write this one); its decode launch reads the bitstream and rewrites only the coded blocks (not counted)
+    memcpy(b->stat_k_bytes, b->stat_k_bytes_base, sizeof b->stat_k_bytes);
+    for (const FrameRec &R : b->frames)
+        if (R.precopy) {
+            const uint64_t npix = (uint64_t)b->streams[R.stream].w * b->streams[R.stream].h;
+            b->stat_k_bytes[JSP_K_MSV1_DECODE] -= npix * 4;
+            b->stat_k_bytes[JSP_K_FRAME_COPY] += npix * 8;
+        }
     // End-to-end path: when the batch is transfer-bound (MSVideo1 only: one wide launch per level, no per-stream
     // serial chains to keep busy) the streams are also cut into chunks of whole streams so that the upload of
     // chunk k+1, the decode of chunk k and the download of chunk k-1 overlap on three CUDA streams.
@@ -664,7 +673,7 @@ static int64_t batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_st
             // per kernel class (DESIGN.md "Algorithmic bytes"): what each kernel must move for this frame
             const int kent = (S.codec == JSP_CODEC_SCREENPRESSOR && b->sp_hosts[s].version > 2) ? JSP_K_SP_ENTROPY_ANS : JSP_K_SP_ENTROPY_RC;
             switch (R.kind) {
-            case FK_MSV16: case FK_MSV8: b->stat_k_bytes[JSP_K_MSV1_DECODE] += npix * 4 + R.len; break;   // (+ 8 B / pixel in frame_copy for pre-copied sparse frames, not counted)
+            case FK_MSV16: case FK_MSV8: b->stat_k_bytes[JSP_K_MSV1_DECODE] += npix * 4 + R.len; break;
             case FK_COPY:    b->stat_k_bytes[JSP_K_FRAME_COPY] += npix * 8; break;
             case FK_SP_FLAT: b->stat_k_bytes[JSP_K_FRAME_COPY] += npix * 4; break;
             case FK_SP_P:    b->stat_k_bytes[JSP_K_FRAME_COPY] += npix * 8; b->stat_k_bytes[kent] += R.len; break;
@@ -752,6 +761,7 @@ static int64_t batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_st
             }
         }
     }
+    memcpy(b->stat_k_bytes_base, b->stat_k_bytes, sizeof b->stat_k_bytes);
     if (!plan_and_upload(b)) return -1;
 
     // status post-pass tables

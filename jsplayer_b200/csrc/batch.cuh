@@ -170,5 +170,6 @@ struct jsp_batch {
     int rerun_count = 0;
 
     uint64_t stat_pixels = 0, stat_alg_bytes = 0, stat_in_bytes = 0, stat_out_bytes = 0;
-    uint64_t stat_k_bytes[JSP_N_KERNELS] = {0};    // algorithmic bytes per run, per kernel class
+    uint64_t stat_k_bytes[JSP_N_KERNELS] = {0};    // algorithmic bytes per run, per kernel class (as planned)
+    uint64_t stat_k_bytes_base[JSP_N_KERNELS] = {0};   // ... before the planner moved pre-copied frames to the copy kernel
 };
