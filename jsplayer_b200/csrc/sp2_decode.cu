@@ -153,6 +153,7 @@ __device__ __forceinline__ void sp2_recon_iframe(RunQueue *q, const SpJob &J, co
     const int chunk = X < 32 ? (int)X : 32;          // a chunk never reads pixels it writes itself (the row above is X away)
     long di = 0;
     uint32_t lastval = 0, consumed = 0;
+    const unsigned int poll_ns = g_sp2_poll_ns;
     P2_DECL
 #ifdef JSP_SP2_PROF
     const long long _r0 = clock64();
@@ -164,7 +165,7 @@ __device__ __forceinline__ void sp2_recon_iframe(RunQueue *q, const SpJob &J, co
         for (;;) {
             e = ld_volatile_v2(&q->e[consumed % RQ_N]);
             if (((e.x >> 27) == (gen & 31u)) && ((e.y >> 16) == (gen & 0xFFFFu))) break;
-            __nanosleep(g_sp2_poll_ns);
+            __nanosleep(poll_ns);
         }
         P2_T(8)
         const uint32_t type = (e.x >> 24) & 7u, clr = e.x & 0xFFFFFFu;
