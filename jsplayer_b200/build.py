@@ -77,15 +77,34 @@ def build_cuda(force=False, verbose=False):
             return CUDA_LIB
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         tmp = CUDA_LIB + ".tmp%d" % os.getpid()
-        cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
+        # one nvcc per translation unit, in parallel (no relocatable device code: the units share nothing on the device),
+        # then one link -- the ScreenPressor kernels alone take two minutes
+        import tempfile
+        from concurrent.futures import ThreadPoolExecutor
+        objdir = tempfile.mkdtemp(prefix="jsp_build_")
+        cflags = [f for f in flags if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+        def compile_one(src):
+            obj = os.path.join(objdir, os.path.basename(src) + ".o")
+            r = subprocess.run([nvcc] + cflags + ["-c", "-o", obj, src], capture_output=True, text=True)
+            return obj, r
+        with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+            results = list(ex.map(compile_one, srcs))
+        log = "".join(r.stdout + r.stderr for _, r in results)
+        if any(r.returncode != 0 for _, r in results):
+            sys.stderr.write(log)
             raise RuntimeError("nvcc failed building libjsplayer_cuda.so")
+        r = subprocess.run([nvcc] + flags + ["-o", tmp] + [o for o, _ in results], capture_output=True, text=True)
+        for o, _ in results:
+            os.unlink(o)
+        os.rmdir(objdir)
+        if r.returncode != 0:
+            sys.stderr.write(log + r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed linking libjsplayer_cuda.so")
         os.replace(tmp, CUDA_LIB)
         _stamp(CUDA_LIB, deps, flags)
         if verbose:
-            sys.stderr.write(r.stderr)
+            sys.stderr.write(log)
     return CUDA_LIB
 
 
