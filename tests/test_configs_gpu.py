@@ -99,27 +99,101 @@ def test_c5_mixed_4k_corpus_full_gops(tmp_path):
     assert i == n * len(files)
 
 
-def test_c4_at_512_streams_spot_checked():
-    """configs[3] at its stream count: 512 ScreenPressor 1080p streams of 1 I + 31 P frames in ONE batch (136 GB of pictures
-    stay in HBM; 16 distinct streams, v2 and v4 alternating, repeated -- every copy decodes with its own model state).
-    Spot check: six streams spread over the batch, all 32 frames, against the oracle; no frame of the batch may fail."""
-    w, h, n_streams, n_frames, distinct = 1920, 1080, 512, 32, 16
-    base = [synth.sp_stream(w, h, n_frames, seed=0xC0DEC4 + i, version=(2, 4)[i % 2], change_permille=20)[:2] for i in range(distinct)]
-    specs = [StreamSpec(CodecType.codec_screenpressor, w, h, 24, frames=base[i % distinct][0], keys=base[i % distinct][1])
-             for i in range(n_streams)]
+def test_c4_at_512_streams_every_frame():
+    """configs[3] at its stream count: 512 DISTINCT ScreenPressor 1080p streams of 1 I + 31 P frames (v2 and v4 alternating) in
+    ONE batch -- 136 GB of pictures stay in HBM -- and every one of the 16 384 pictures compared with the oracle (downloaded
+    16 streams at a time; the oracle decodes on 16 host threads)."""
+    from concurrent.futures import ThreadPoolExecutor
+    w, h, n_streams, n_frames = 1920, 1080, 512, 32
+
+    def make(i):
+        return synth.sp_stream(w, h, n_frames, seed=0xC4000 + i, version=(2, 4)[i % 2], change_permille=20)[:2]
+    with ThreadPoolExecutor(max_workers=16) as ex:
+        streams = list(ex.map(make, range(n_streams)))
     bd = BatchDecoder(insignificant_lines=36)
-    bd.configure(specs, pinned=True)
+    bd.configure([StreamSpec(CodecType.codec_screenpressor, w, h, 24, frames=fr, keys=k) for fr, k in streams], pinned=True)
     bd.upload(); bd.run(); bd.sync()
-    check = [0, 1, 130, 259, 388, 511]
-    outs = [None] * bd.n_frames
-    for s in check:
-        for f in range(n_frames):
-            outs[s * n_frames + f] = np.empty((h, w), dtype=np.int32)
-    _, flags = bd.download(outs)
-    bd.close()
+    flags = bd.results()
     assert not (flags & _lib.JSP_FRAME_ERROR).any()
-    for s in check:
-        fr, keys = base[s % distinct]
-        exp = O.decode_stream(O.CODEC_SCREENPRESSOR, w, h, 24, fr, keys=keys, insignificant_lines=36)[0]
-        for f in range(n_frames):
-            assert (outs[s * n_frames + f] == exp[f]).all(), "stream %d frame %d" % (s, f)
+    group = 16
+    bufs = [np.empty((h, w), dtype=np.int32) for _ in range(group * n_frames)]
+    for lo in range(0, n_streams, group):
+        outs = [None] * bd.n_frames
+        for i in range(group * n_frames):
+            outs[lo * n_frames + i] = bufs[i]
+        bd.download(outs)
+
+        def check(s):
+            fr, keys = streams[lo + s]
+            exp = O.decode_stream(O.CODEC_SCREENPRESSOR, w, h, 24, fr, keys=keys, insignificant_lines=36)[0]
+            return [f for f in range(n_frames) if not (bufs[s * n_frames + f] == exp[f]).all()]
+        with ThreadPoolExecutor(max_workers=16) as ex:
+            bad = list(ex.map(check, range(group)))
+        for s, b in enumerate(bad):
+            assert not b, "stream %d frames %s" % (lo + s, b)
+    bd.close()
+
+
+def _oracle_all(specs_args, threads=16):
+    """Oracle pictures of many streams, one stream per worker thread (the C oracle releases the GIL inside ctypes calls)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(a):
+        codec, w, h, bpp, frames, keys = a
+        return O.decode_stream(codec, w, h, bpp, frames, keys=keys, insignificant_lines=36)[0]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        return list(ex.map(one, specs_args))
+
+
+def test_c2_full_batch_every_frame_against_the_oracle():
+    """configs[1] at its full size -- 1024 MSVideo1 RGB555 1920x1080 key frames in ONE batch (the bench's headline launch) -- and
+    EVERY picture compared with the oracle, not a sample: pictures are downloaded 64 at a time."""
+    from concurrent.futures import ThreadPoolExecutor
+    w, h, n = 1920, 1080, 1024
+    with ThreadPoolExecutor(max_workers=16) as ex:
+        frames = list(ex.map(lambda i: synth.msv1_frame(False, w, h, 0xC0DEC2 + i, mix=(25, 50, 25)), range(n)))
+    bd = BatchDecoder(insignificant_lines=36)
+    bd.configure([StreamSpec(CodecType.codec_msvc16, w, h, 16, frames=[f]) for f in frames], pinned=True)
+    bd.upload(); bd.run(); bd.sync()
+    flags = bd.results()
+    assert not (flags & _lib.JSP_FRAME_ERROR).any()
+    assert (flags & _lib.JSP_FRAME_CHANGED).all()
+    bufs = [np.empty((h, w), dtype=np.int32) for _ in range(64)]
+    for lo in range(0, n, 64):
+        outs = [None] * n
+        for i in range(64):
+            outs[lo + i] = bufs[i]
+        bd.download(outs)
+        exp = _oracle_all([(O.CODEC_MSVC16, w, h, 16, [frames[lo + i]], None) for i in range(64)])
+        for i in range(64):
+            assert (bufs[i] == exp[i][0]).all(), "frame %d" % (lo + i)
+    bd.close()
+
+
+def test_c3_full_batch_every_frame_against_the_oracle():
+    """configs[2] at its full size -- 256 ScreenPressor 1280x720 streams of 4 I frames, range-coder and rANS streams alternating,
+    256 DISTINCT streams (the bench repeats 32) in one batch of 1024 independent frames -- every picture against the oracle."""
+    from concurrent.futures import ThreadPoolExecutor
+    w, h, n_streams = 1280, 720, 256
+
+    def make(i):
+        fr, keys, _ = synth.sp_stream(w, h, 4, seed=0xC3000 + i, version=(2, 4, 3, 2)[i % 4], gop=1, change_permille=40)
+        return fr, keys
+    with ThreadPoolExecutor(max_workers=16) as ex:
+        streams = list(ex.map(make, range(n_streams)))
+    bd = BatchDecoder(insignificant_lines=36)
+    bd.configure([StreamSpec(CodecType.codec_screenpressor, w, h, 24, frames=fr, keys=k) for fr, k in streams], pinned=True)
+    bd.upload(); bd.run(); bd.sync()
+    flags = bd.results()
+    assert not (flags & _lib.JSP_FRAME_ERROR).any()
+    bufs = [np.empty((h, w), dtype=np.int32) for _ in range(128)]
+    for lo in range(0, n_streams, 32):                       # 32 streams = 128 pictures at a time
+        outs = [None] * (4 * n_streams)
+        for i in range(128):
+            outs[4 * lo + i] = bufs[i]
+        bd.download(outs)
+        exp = _oracle_all([(O.CODEC_SCREENPRESSOR, w, h, 24, streams[lo + s][0], streams[lo + s][1]) for s in range(32)])
+        for s in range(32):
+            for f in range(4):
+                assert (bufs[4 * s + f] == exp[s][f]).all(), "stream %d frame %d" % (lo + s, f)
+    bd.close()
