@@ -11,8 +11,9 @@ collective).  A step = one decode pass over the whole batch.
   cpu_baseline the CPU oracle (port of the reference decoder) on this box's host cores, bounded sample
   codecs       (rank 0, N = 1 only, --no-codecs to skip) the same measurement for the other BASELINE configs at their
                stated sizes: configs[0] (c1: MSVideo1 8-bit 320x240, 300 frames), configs[2] (c3: ScreenPressor 1280x720
-               keyframe-only, 256 streams), configs[3] (c4: ScreenPressor 1080p, 512 streams of 1 I + 31 P) and two
-               MSVideo1 inter-frame legs (c2p / c2p8: RGB555 and 8-bit 1080p, key + 15 P frames with 85 % skipped blocks)
+               keyframe-only, 256 streams), configs[3] (c4: ScreenPressor 1080p, 512 streams of 1 I + 31 P), configs[4]
+               (c5: the mixed 4K AVI corpus, this GPU's 8 of the 64 files) and two MSVideo1 inter-frame legs (c2p / c2p8:
+               RGB555 and 8-bit 1080p, key + 15 P frames with 85 % skipped blocks)
 
 `--workload c1|c2p|c2p8|c3|c4|c5` makes another config the timed workload instead (same JSON contract).
 `--impl reference` times the reference's CPU algorithm (the oracle port; the Haxe/JS original cannot run
@@ -650,7 +651,7 @@ def main():
     #      at its stated size, plus MSVideo1 inter-frame legs (the headline config is key frames only) ----
     if rank == 0 and world == 1 and args.workload == "c2" and not args.no_codecs:
         codecs = {}
-        for name, steps in (("c1", 5), ("c2p", 5), ("c2p8", 5), ("c3", 5), ("c4", 3)):
+        for name, steps in (("c1", 5), ("c2p", 5), ("c2p8", 5), ("c3", 5), ("c4", 3), ("c5", 2)):
             a2 = argparse.Namespace(**vars(args))
             a2.streams, a2.steps, a2.e2e_steps = 0, min(args.steps, steps), -1
             try:
