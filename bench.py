@@ -569,6 +569,11 @@ def measure(wl, args, rank, local_rank, world, dist, torch, with_e2e=True, with_
             lat.update(committed_json("r02_entropy_counters.json"))
             line["roofline"] = lat
         else:
+            if hbm["frac"] < 0.02:
+                # a handful of CTAs per launch and hundreds of dependent launches (one stream: every P frame waits for its
+                # predecessor): the step is bound by launch latency, not by bytes -- say so instead of a meaningless fraction
+                hbm["bound_note"] = "launch-latency bound: %d dependent launches of %.1f us each per step" % (
+                    int(sum(kcnt) / args.steps), 1e3 * ms_per_step / max(1.0, sum(kcnt) / args.steps))
             line["roofline"] = hbm
         line["e2e"] = e2e if e2e else {"value": None, "unit": "Mpixel/s", "skipped": "--e2e-steps 0"}
         if e2e_inplace:
