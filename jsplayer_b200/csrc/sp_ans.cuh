@@ -31,6 +31,30 @@ constexpr int ANS_NCTX = 3 * 4096;
 constexpr int ANS_HDR_BYTES = 64, ANS_BODY_BYTES = 1536;
 enum { CXK_NONE = 0, CXK_1, CXK_2, CXK_3, CXK_4, CXK_5, CXK_6, CXK_7 };
 
+// Shared memory on the symbol chain is addressed by 32-bit shared-window addresses kept in registers.  A C++ access through a
+// pointer the compiler can trace back to a __shared__ symbol re-derives the window address at the point of use -- S2R
+// SR_CgaCtaId + LEA, ~30 cycles of latency in front of the load; the rANS I-frame kernel had 197 of them -- so the hot paths
+// use explicit ld.shared / st.shared on an address made opaque once per frame.  The asm statements keep program order.
+__device__ __forceinline__ uint32_t a_lds8(uint32_t a)  { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t a_lds16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t a_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint2 a_lds64(uint32_t a)    { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint4 a_lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void a_sts8(uint32_t a, uint32_t v)  { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void a_sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void a_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t a_opaque_smem(const void *p)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));             // opaque: the compiler must not re-derive it from the symbol
+    return a;
+}
+
 // ---- fixed-size adaptive table: separate arrays instead of the reference's (freq, cumFreq) pairs ----
 // cum[] carries 8 sentinel entries (0xFFFF: above every slot value) behind the table, so a forward scan needs no bound check.
 // Tables of 256 / 512 symbols also carry `lut`: the symbol that holds slot 16 * b, for b = 0..255 -- a finer decTable
@@ -689,6 +713,7 @@ struct AnsCoder {
     AnsSmall *small;                                                  // shared memory (the I-frame kernel maps only the I-frame prefix)
     AnsWork *wk;
     uint32_t small_bytes;                                             // how much of AnsSmall is mapped
+    uint32_t sa_small, sa_wk;                                         // the same two as shared-window addresses (see a_lds8)
     uint4 *hdrs, *bodies;
     int my_tag;                                                       // lane < ANS_CACHE_SLOTS: context held by slot `lane`, -1 = empty
     uint32_t my_age, tick;                                            // LRU stamps
@@ -756,7 +781,8 @@ struct AnsCoder {
         const uint32_t off = pos - wbase, f = x & 4095u;
         if ((x - ANS_L) < (0x80000000u - ANS_L) && off < ANS_WIN - 2u && pos + 2u <= len &&
             (uint32_t)(freq - 1) < (uint32_t)ANS_SCALE && f >= (uint32_t)start && !overrun) {
-            const uint32_t b0 = wk->win[off], b1 = wk->win[off + 1u];
+            const uint32_t wa = sa_wk + (uint32_t)offsetof(AnsWork, win) + off;
+            const uint32_t b0 = a_lds8(wa), b1 = a_lds8(wa + 1u);
             const uint32_t v = (uint32_t)freq * (x >> 12) + (f - (uint32_t)start);
             const uint32_t v1 = (v << 8) | b0, v2 = (v << 16) | (b0 << 8) | b1;
             const bool one = v < ANS_L, two = v < (ANS_L >> 8);
@@ -846,24 +872,32 @@ struct AnsCoder {
     }
     static __device__ __forceinline__ int rank8(const uint4 &v, uint32_t f)       // how many of elements 1..7 are <= f
     {
-        return (int)((v.x >> 16) <= f) + (int)((v.y & 0xFFFFu) <= f) + (int)((v.y >> 16) <= f) + (int)((v.z & 0xFFFFu) <= f) +
-               (int)((v.z >> 16) <= f) + (int)((v.w & 0xFFFFu) <= f) + (int)((v.w >> 16) <= f);
+        // a balanced tree: written as one sum the compiler emits a chain of seven dependent conditional increments
+        const int a = (int)((v.x >> 16) <= f) + (int)((v.y & 0xFFFFu) <= f), b = (int)((v.y >> 16) <= f) + (int)((v.z & 0xFFFFu) <= f);
+        const int c = (int)((v.z >> 16) <= f) + (int)((v.w & 0xFFFFu) <= f), d = (int)((v.w >> 16) <= f);
+        return (a + b) + (c + d);
     }
     template <int N>
-    __device__ __forceinline__ int decodeF(FxTab<N> &t)
+    __device__ __forceinline__ int decodeF(uint32_t small_off)
     {
+        typedef FxTab<N> T;
+        const uint32_t ta = sa_small + small_off;                      // the table as a shared-window address
+        T &t = *reinterpret_cast<T *>(reinterpret_cast<uint8_t *>(small) + small_off);
         const uint32_t off = pos - wbase, offc = min(off, ANS_WIN - 2u);
-        const uint32_t b0 = wk->win[offc], b1 = wk->win[offc + 1u];
-        const uint32_t cs = t.cntsum;
+        const uint32_t wa = sa_wk + (uint32_t)offsetof(AnsWork, win) + offc;
+        const uint32_t b0 = a_lds8(wa), b1 = a_lds8(wa + 1u);
+        const uint32_t cs = a_lds32(ta + (uint32_t)offsetof(T, cntsum));
         const uint32_t f = x & 4095u;
         uint4 vc, vf, vn;
         uint32_t c0 = 0;
         if constexpr (N <= 8) {
-            vc = *reinterpret_cast<const uint4 *>(t.cum);             // cum[0..7]; entries >= N are 0xFFFF
-            vf = *reinterpret_cast<const uint4 *>(t.fr);
-            vn = *reinterpret_cast<const uint4 *>(t.cnt);
-        } else if constexpr (FxTab<N>::NLUT != 0) {
-            c0 = t.lut[f >> 4];                                       // the symbol that holds slot f & ~15: at most 15 short
+            vc = a_lds128(ta + (uint32_t)offsetof(T, cum));            // cum[0..7]; entries >= N are 0xFFFF
+            vf = a_lds128(ta + (uint32_t)offsetof(T, fr));
+            vn = a_lds128(ta + (uint32_t)offsetof(T, cnt));
+        } else if constexpr (T::NLUT != 0) {
+            // the symbol that holds slot f & ~15: at most 15 short
+            c0 = sizeof(typename T::lut_t) == 1 ? a_lds8(ta + (uint32_t)offsetof(T, lut) + (f >> 4))
+                                                 : a_lds16(ta + (uint32_t)offsetof(T, lut) + 2u * (f >> 4));
         }
         const bool ok = (x - ANS_L) < (0x80000000u - ANS_L) && off < ANS_WIN - 2u && pos + 2u <= len && !overrun &&
                         cs + 32u <= (uint32_t)ANS_SCALE && nDec + 1 != ANS_B;
@@ -875,19 +909,21 @@ struct AnsCoder {
             freq = pick16(vf, c); cumf = pick16(vc, c); cn = pick16(vn, c);
         } else {
             c = (int)c0;
-            const uint16_t *cp = t.cum + c + 1;
+            uint32_t cp = ta + (uint32_t)offsetof(T, cum) + 2u * (uint32_t)(c + 1);
             for (;;) {
-                const uint32_t a0 = cp[0], a1 = cp[1], a2 = cp[2], a3 = cp[3];
+                const uint32_t a0 = a_lds16(cp), a1 = a_lds16(cp + 2u), a2 = a_lds16(cp + 4u), a3 = a_lds16(cp + 6u);
                 const int k = (int)(a0 <= f) + (int)(a1 <= f) + (int)(a2 <= f) + (int)(a3 <= f);
                 c += k;
                 if (k < 4) break;
-                cp += 4;
+                cp += 8u;
             }
-            freq = t.fr[c]; cumf = t.cum[c]; cn = t.cnt[c];
+            freq = a_lds16(ta + (uint32_t)offsetof(T, fr) + 2u * (uint32_t)c);
+            cumf = a_lds16(ta + (uint32_t)offsetof(T, cum) + 2u * (uint32_t)c);
+            cn = a_lds16(ta + (uint32_t)offsetof(T, cnt) + 2u * (uint32_t)c);
         }
         __syncwarp();                                                  // every lane has read the table
-        t.cnt[c] = (uint16_t)(cn + 16u);                               // every lane stores the same values: no divergence
-        t.cntsum = cs + 16u;
+        a_sts16(ta + (uint32_t)offsetof(T, cnt) + 2u * (uint32_t)c, (cn + 16u) & 0xFFFFu);   // every lane stores the same values
+        a_sts32(ta + (uint32_t)offsetof(T, cntsum), cs + 16u);
         const uint32_t v = freq * (x >> 12) + (f - cumf);              // decAdvance, ANS.hx:37-44 (see try_advance)
         const uint32_t v1 = (v << 8) | b0, v2 = (v << 16) | (b0 << 8) | b1;
         const bool one = v < ANS_L, two = v < (ANS_L >> 8);
@@ -1029,12 +1065,12 @@ struct AnsCoder {
         CxHdr &H = S.hdr;
         // everything the Cx4 fast path reads, loaded at once BEFORE the kind is tested (one shared-memory round trip on the
         // symbol chain instead of two), plus the next two bitstream bytes for its renormalisation
-        const uint2 hw = *reinterpret_cast<const uint2 *>(&H);          // gen | d, kind, maxpos
-        const uint32_t *bw = reinterpret_cast<const uint32_t *>(S.body);
-        const uint32_t symw = bw[0];
-        const uint2 fw = *reinterpret_cast<const uint2 *>(bw + B_SC_FR / 4);
+        const uint32_t ss = sa_wk + (uint32_t)offsetof(AnsWork, cache) + (uint32_t)slot * (uint32_t)sizeof(AnsSlot);   // the slot, shared-window address
+        const uint2 hw = a_lds64(ss);                                   // gen | d, kind, maxpos
+        const uint32_t symw = a_lds32(ss + (uint32_t)offsetof(AnsSlot, body));
+        const uint2 fw = a_lds64(ss + (uint32_t)offsetof(AnsSlot, body) + (uint32_t)B_SC_FR);
         const uint32_t woff = pos - wbase, woffc = min(woff, ANS_WIN - 2u);
-        const uint32_t wb0 = wk->win[woffc], wb1 = wk->win[woffc + 1u];
+        const uint32_t wb0 = a_lds8(sa_wk + (uint32_t)offsetof(AnsWork, win) + woffc), wb1 = a_lds8(sa_wk + (uint32_t)offsetof(AnsWork, win) + woffc + 1u);
         const int kind = hw.x == gen ? (int)((hw.y >> 16) & 0xFFu) : CXK_NONE;
         int c;
         // (Measured dead end: keeping the interval arithmetic of this path as a "decode-ready" record beside the context -- four
@@ -1082,11 +1118,10 @@ struct AnsCoder {
                     n2 = d > 2 ? (n2 - (n2 >> 1)) & 0xFFFF : n2; n3 = d > 3 ? (n3 - (n3 >> 1)) & 0xFFFF : n3;
                 }
                 __syncwarp();                                          // every lane has read the slot
-                if (lane == 0) {
-                    uint32_t *bwr = reinterpret_cast<uint32_t *>(S.body);
-                    bwr[B_SC_FR / 4] = (uint32_t)n0 | ((uint32_t)n1 << 16); bwr[B_SC_FR / 4 + 1] = (uint32_t)n2 | ((uint32_t)n3 << 16);
-                    H.maxpos = (uint8_t)nmp;
-                }
+                // every lane stores the same three values (no divergent region on the chain)
+                a_sts32(ss + (uint32_t)offsetof(AnsSlot, body) + (uint32_t)B_SC_FR, (uint32_t)n0 | ((uint32_t)n1 << 16));
+                a_sts32(ss + (uint32_t)offsetof(AnsSlot, body) + (uint32_t)B_SC_FR + 4u, (uint32_t)n2 | ((uint32_t)n3 << 16));
+                a_sts8(ss + (uint32_t)offsetof(CxHdr, maxpos), (uint32_t)nmp);
                 __syncwarp();
                 // decAdvance + the symbol count (ANS.hx:37-44, EntroCoders.hx:249-253): straight-line when the state is normalised,
                 // the two bytes are in the window and no state reload is due -- see try_advance; else the generic pair
@@ -1153,6 +1188,7 @@ struct AnsCoder {
     {
         AnsState *st = reinterpret_cast<AnsState *>(J.state);
         small = small_sh; wk = work_sh; small_bytes = nbytes;
+        sa_small = a_opaque_smem(small_sh); sa_wk = a_opaque_smem(work_sh);
         hdrs = st->hdrs; bodies = st->bodies; gen = st->gen;
         f0 = (J.flags & SPJ_ANS_V3) ? 64 : 32;                       // Cx6.f0, EntroCoders.hx:210 / ScreenPressor.hx:69-72
         fail = false; overrun = false; x = 0; data = J.src; len = J.len; pos = 0; wbase = 0x80000000u; nDec = 0; nsym = 0;
@@ -1191,14 +1227,14 @@ struct AnsCoder {
         count();
         return flag;
     }
-    __device__ __forceinline__ int decodeN(int ptype) { return decodeF(small->ntab[ptype]); }
-    __device__ __forceinline__ int decodeP(int ptype) { return decodeF(small->ptypetab[ptype]); }
-    __device__ __forceinline__ int decodeX() { return decodeF(small->xxtab); }
-    __device__ __forceinline__ int decodeBT() { return decodeF(small->bttab); }
-    __device__ __forceinline__ int decodeBN() { return decodeF(small->ntab2); }
-    __device__ __forceinline__ int decodeSXY(int n) { return decodeF(small->sxytab[n]); }
-    __device__ __forceinline__ int decodeMX() { return decodeF(small->mvtab[0]); }
-    __device__ __forceinline__ int decodeMY() { return decodeF(small->mvtab[1]); }
+    __device__ __forceinline__ int decodeN(int ptype) { return decodeF<256>((uint32_t)offsetof(AnsSmall, ntab) + (uint32_t)ptype * (uint32_t)sizeof(FxTab<256>)); }
+    __device__ __forceinline__ int decodeP(int ptype) { return decodeF<6>((uint32_t)offsetof(AnsSmall, ptypetab) + (uint32_t)ptype * (uint32_t)sizeof(FxTab<6>)); }
+    __device__ __forceinline__ int decodeX() { return decodeF<256>((uint32_t)offsetof(AnsSmall, xxtab)); }
+    __device__ __forceinline__ int decodeBT() { return decodeF<5>((uint32_t)offsetof(AnsSmall, bttab)); }
+    __device__ __forceinline__ int decodeBN() { return decodeF<256>((uint32_t)offsetof(AnsSmall, ntab2)); }
+    __device__ __forceinline__ int decodeSXY(int n) { return decodeF<16>((uint32_t)offsetof(AnsSmall, sxytab) + (uint32_t)n * (uint32_t)sizeof(FxTab<16>)); }
+    __device__ __forceinline__ int decodeMX() { return decodeF<512>((uint32_t)offsetof(AnsSmall, mvtab)); }
+    __device__ __forceinline__ int decodeMY() { return decodeF<512>((uint32_t)offsetof(AnsSmall, mvtab) + (uint32_t)sizeof(FxTab<512>)); }
 };
 
 // one frame of one rANS stream; `sm` = this warp's shared memory (first-generation kernel: one warp does everything)
