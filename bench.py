@@ -477,10 +477,17 @@ def measure(wl, args, rank, local_rank, world, dist, torch, with_e2e=True, with_
                "d2h_gbs_all_ranks": st["out_bytes"] * world / e2e_s / 1e9,
                "host_buffers": ("pinned ring of %.0f GB (pictures recycled as a player's buffer ring does; every byte still crosses PCIe)" % (RING_BYTES / 2**30))
                if ring else "one pinned picture per frame"}
-        ceil = committed_json("r02_d2h_ceiling.json").get(str(world))
-        if ceil:
-            # what N ranks doing nothing but cudaMemcpyAsync D2H into pinned memory reached on the 8-GPU box (tools/d2h_ceiling.py)
-            e2e["host_ceiling_gbs"] = ceil
+        # What THIS box's host takes: all ranks at once do nothing but device -> pinned-host copies (1 GiB x 4 each).  Boxes of the
+        # pool differ (two GPUs reached 70 GB/s together on one box and 107 on another; profiles/r02_d2h_ceiling.txt holds one
+        # 8-GPU box: 55.8 / 69.8 / 71.1 / 92.0 GB/s at N = 1 / 2 / 4 / 8), so the ceiling is measured live beside the number.
+        from jsplayer_b200 import _lib as _L
+        barrier()
+        mine = _L.load().jsp_host_d2h_gbs(local_rank, 1 << 30, 4)
+        c_local = torch.tensor([mine], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(c_local, op=dist.ReduceOp.SUM)
+        e2e["host_ceiling_gbs"] = float(c_local.item())
+        e2e["host_ceiling_how"] = "all %d ranks at once: 4 device->pinned-host copies of 1 GiB each, summed" % world
 
     # ---- opt-in in-place end-to-end path (inter-frame workloads): one pinned picture per STREAM, only changed blocks cross PCIe ----
     e2e_inplace = None

@@ -44,6 +44,9 @@ JSP_API void  jsp_host_free(void *p);
  * for threads the caller owns (returns the node, -1 = nothing changed) */
 JSP_API int   jsp_numa_node_of_device(int device);
 JSP_API int   jsp_numa_bind_thread(int device);
+/* `reps` device -> pinned-host copies of `bytes` each from `device`: GB/s (0 on failure).  Called by N ranks at the same time it
+ * measures what this box's host takes from N GPUs at once -- the ceiling of the end-to-end path (4 bytes per decoded pixel). */
+JSP_API double jsp_host_d2h_gbs(int device, size_t bytes, int reps);
 
 /* ---- per-stream drop-in: one stateful codec per stream, frames in order, host buffers ----
  * new MSVideo1_16bit(w,h) MSVideo1.hx:20-31 | new MSVideo1_8bit(w,h,palette) :267-274 |

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "jsp_host_free": (None, [C.c_void_p]),
     "jsp_numa_node_of_device": (C.c_int, [C.c_int]),
     "jsp_numa_bind_thread": (C.c_int, [C.c_int]),
+    "jsp_host_d2h_gbs": (C.c_double, [C.c_int, C.c_size_t, C.c_int]),
     "jsp_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "jsp_destroy": (None, [C.c_void_p]),
     "jsp_preinit": (None, [C.c_void_p, C.c_int]),

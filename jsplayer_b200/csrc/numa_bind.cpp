@@ -109,7 +109,39 @@ int bind_thread_to_device(int device)
 
 }  // namespace jsp
 
+// What this host takes from `device` over PCIe: `reps` device -> pinned-host copies of `bytes` each, GB/s (0 on failure).  Ranks
+// that call it at the same time (after a barrier) measure the box's ceiling for N concurrent streams -- the bound of every
+// end-to-end number of this library (4 bytes per decoded pixel), and different from box to box.
+static double host_d2h_gbs(int device, size_t bytes, int reps)
+{
+    if (bytes == 0 || reps <= 0 || cudaSetDevice(device) != cudaSuccess) return 0.0;
+    void *d = nullptr, *h = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    double gbs = 0.0;
+    if (cudaMalloc(&d, bytes) == cudaSuccess && cudaHostAlloc(&h, bytes, cudaHostAllocDefault) == cudaSuccess &&
+        cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreate(&e0) == cudaSuccess &&
+        cudaEventCreate(&e1) == cudaSuccess) {
+        cudaMemsetAsync(d, 1, bytes, st);
+        cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);      // touches every page once
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < reps; i++) cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(e1, st);
+        float ms = 0.f;
+        if (cudaStreamSynchronize(st) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && ms > 0.f)
+            gbs = (double)bytes * reps / (ms * 1e-3) / 1e9;
+    }
+    cudaGetLastError();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    if (h) cudaFreeHost(h);
+    if (d) cudaFree(d);
+    return gbs;
+}
+
 extern "C" {
+__attribute__((visibility("default"))) double jsp_host_d2h_gbs(int device, size_t bytes, int reps) { return host_d2h_gbs(device, bytes, reps); }
 __attribute__((visibility("default"))) int jsp_numa_node_of_device(int device) { return jsp::device_numa_node(device); }
 __attribute__((visibility("default"))) int jsp_numa_bind_thread(int device) { return jsp::bind_thread_to_device(device); }
 }
