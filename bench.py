@@ -590,7 +590,7 @@ def measure(wl, args, rank, local_rank, world, dist, torch, with_e2e=True, with_
         if with_cpu and not args.no_cpu_baseline:
             n_s = sample_size(wl, cores, len(specs))
             v, t, reps = cpu_baseline(specs[:n_s], cores, budget_s=cpu_budget or args.cpu_budget)
-            line["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", "cores": min(cores, n_s), "kind": "port",
+            line["cpu_baseline"] = {"value": v, "unit": "Mpixel/s", "cores": min(cores, len(specs[:n_s])), "kind": "port",
                                     "sample": "%d of the %d streams, one stream per thread at a time, pictures into a 2-buffer scratch ring per thread; median of %d passes (%.3f s each, ~%.0f s of CPU wall time)" % (n_s, len(specs), reps, t, reps * t)}
     bd.close()
     return line
@@ -646,7 +646,7 @@ def main():
         line = {"impl": "reference", "metric": wl.metric, "value": v, "unit": "Mpixel/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
-                "cpu_baseline": {"value": v, "unit": "Mpixel/s", "cores": min(cores, n_s), "kind": "port",
+                "cpu_baseline": {"value": v, "unit": "Mpixel/s", "cores": min(cores, len(specs)), "kind": "port",
                                  "sample": "%d of the workload's streams, one stream per thread at a time; a step repeats the sample for ~1 s (median pass), median of %d steps" % (n_s, args.steps)},
                 "e2e": {"value": v, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
