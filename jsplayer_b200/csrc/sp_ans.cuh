@@ -1097,10 +1097,10 @@ struct AnsCoder {
             const int r0 = (q0 + (mp == 0 ? bonus : 0)) & 0xFFFF, r1 = (q1 + (mp == 1 ? bonus : 0)) & 0xFFFF,
                       r2 = (q2 + (mp == 2 ? bonus : 0)) & 0xFFFF, r3 = (q3 + (mp == 3 ? bonus : 0)) & 0xFFFF;
             // interval starts: every symbol below s_i that has not been met owns one unit (decodeSC, :274-299)
-            const int a0 = s0, e0 = a0 + r0;
-            const int a1 = e0 + s1 - s0 - 1, e1 = a1 + r1;
-            const int a2 = e1 + s2 - s1 - 1, e2 = a2 + r2;
-            const int a3 = e2 + s3 - s2 - 1, e3 = a3 + r3;
+            // (a1 = e0 + s1 - s0 - 1 and so on, written as prefix sums so that the four starts do not form a chain of eight adds)
+            const int r01 = r0 + r1;
+            const int a0 = s0, a1 = r0 + s1 - 1, a2 = r01 + s2 - 2, a3 = r01 + r2 + s3 - 3;
+            const int e0 = a0 + r0, e1 = a1 + r1, e2 = a2 + r2, e3 = a3 + r3;
             const bool h0 = sf >= a0 && sf < e0, h1 = d > 1 && sf >= a1 && sf < e1,
                        h2 = d > 2 && sf >= a2 && sf < e2, h3 = d > 3 && sf >= a3 && sf < e3;
             if (h0 || h1 || h2 || h3) {
