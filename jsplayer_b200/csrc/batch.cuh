@@ -162,6 +162,8 @@ struct jsp_batch {
     uint32_t *h_status = nullptr; size_t h_status_cap = 0;   // pinned
     uint32_t *h_done = nullptr, *d_done = nullptr; size_t done_cap = 0;   // mapped pinned: per-frame completion flags of ScreenPressor frames
 
+    cudaGraphExec_t run_graph = nullptr; // jsp_batch_run of a launch-bound plan (hundreds of small dependent launches), captured once
+    bool run_graph_failed = false;
     jsp::DeltaStages *delta = nullptr;   // staging of jsp_batch_decode_host_delta (delta.cu)
     uint64_t delta_d2h_bytes = 0;        // bytes the last jsp_batch_decode_host_delta moved device -> host
 
