@@ -912,7 +912,7 @@ struct AnsCoder {
             uint32_t cp = ta + (uint32_t)offsetof(T, cum) + 2u * (uint32_t)(c + 1);
             for (;;) {
                 const uint32_t a0 = a_lds16(cp), a1 = a_lds16(cp + 2u), a2 = a_lds16(cp + 4u), a3 = a_lds16(cp + 6u);
-                const int k = (int)(a0 <= f) + (int)(a1 <= f) + (int)(a2 <= f) + (int)(a3 <= f);
+                const int k = ((int)(a0 <= f) + (int)(a1 <= f)) + ((int)(a2 <= f) + (int)(a3 <= f));
                 c += k;
                 if (k < 4) break;
                 cp += 8u;
