@@ -93,6 +93,13 @@ enum {
                                     that node for its later allocations (jsp_host_alloc from this thread): the staging memory of
                                     the end-to-end path then sits next to the GPU's PCIe root.  No effect on a
                                     single-node host or with JSP_NUMA_BIND=0 in the environment. */
+    JSP_BATCH_DISPLAY      = 4,  /* fused display epilogue (Manager.fill_bitmap_data Manager.hx:363-381): the
+                                    MSVideo1 decode kernel STORES its pictures as the Int32 view of canvas bytes R,G,B,A (alpha
+                                    255) instead of 0x00RRGGBB -- 0 extra bytes per pixel; every download of the batch then
+                                    delivers MSVideo1 pictures in that format (pixels nobody wrote: 0xFF000000).  ScreenPressor pictures stay
+                                    0x00RRGGBB in HBM (its predictors read back what they wrote) and are converted by the
+                                    separate pass of jsp_batch_download_display. */
+    JSP_BATCH_DISPLAY_FLIP = 8,  /* with JSP_BATCH_DISPLAY: picture row y is stored in row height-1-y (Main.hx:318,946) */
 };
 
 /* Per-frame result flags written by jsp_batch_results(). */

@@ -9,6 +9,8 @@ JSP_N_KERNELS = 8
 KERNEL_NAMES = ["msv1_decode", "frame_copy", "sp_entropy_rc", "sp_entropy_ans", "sp_recon", "signif", "sp_entropy_mixed", "k7"]
 JSP_BATCH_SIGNIFICANCE = 1
 JSP_BATCH_NUMA_BIND = 2
+JSP_BATCH_DISPLAY = 4
+JSP_BATCH_DISPLAY_FLIP = 8
 JSP_FRAME_CHANGED, JSP_FRAME_SIGNIFICANT, JSP_FRAME_ERROR, JSP_FRAME_DIFFERS = 1, 2, 4, 8
 JSP_DISPLAY_FLIP = 1
 

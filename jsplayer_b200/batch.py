@@ -58,13 +58,17 @@ class PinnedBuffer:
 
 
 class BatchDecoder:
-    def __init__(self, device=-1, insignificant_lines=0, significance=False, numa_bind=False):
+    def __init__(self, device=-1, insignificant_lines=0, significance=False, numa_bind=False, display=False, display_flip=False):
         """numa_bind: move the calling thread (and the pinned buffers it allocates afterwards) to the device's NUMA node --
-        for one-process-per-GPU hosts (JSP_BATCH_NUMA_BIND)."""
+        for one-process-per-GPU hosts (JSP_BATCH_NUMA_BIND).
+        display: fused display epilogue (JSP_BATCH_DISPLAY, Manager.fill_bitmap_data Manager.hx:363-381) -- the MSVideo1 kernel
+        stores canvas R,G,B,A words, with display_flip bottom-up (Main.hx:946); every download then delivers that format."""
         self._lib = _lib.require_gpu()
         self._h = self._lib.jsp_batch_create(int(device), int(insignificant_lines),
                                              (_lib.JSP_BATCH_SIGNIFICANCE if significance else 0) |
-                                             (_lib.JSP_BATCH_NUMA_BIND if numa_bind else 0))
+                                             (_lib.JSP_BATCH_NUMA_BIND if numa_bind else 0) |
+                                             (_lib.JSP_BATCH_DISPLAY if display else 0) |
+                                             (_lib.JSP_BATCH_DISPLAY_FLIP if display and display_flip else 0))
         if not self._h:
             raise RuntimeError("jsp_batch_create failed: " + _lib.last_error())
         self._keep = []

@@ -184,13 +184,19 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
                 // whole picture (C1: 37 us per frame); many CTAs of the copy kernel do it in a few.
                 R.precopy = (R.kind == FK_MSV16 || R.kind == FK_MSV8) && !R.key && R.prev >= 0 && R.level > 0 &&
                             (uint64_t)R.len < 3ull * (uint64_t)(S.w >> 2) * (uint64_t)(S.h >> 2);
-                if (R.kind != FK_COPY && R.kind != FK_SP_P && R.kind != FK_SP_FLAT && !R.precopy) continue;
+                // Fused display store (JSP_BATCH_DISPLAY): the pixels outside the 4x4 block grid of a picture whose size is not
+                // a multiple of 4 are written by nobody; the canvas shows them opaque black, so such a picture starts as a fill.
+                const bool msv = R.kind == FK_MSV16 || R.kind == FK_MSV8;
+                const bool disp = (b->flags & JSP_BATCH_DISPLAY) && S.codec != JSP_CODEC_SCREENPRESSOR;
+                const bool edge_fill = disp && msv && !R.precopy && ((S.w | S.h) & 3);
+                if (R.kind != FK_COPY && R.kind != FK_SP_P && R.kind != FK_SP_FLAT && !R.precopy && !edge_fill) continue;
                 if (S.codec == JSP_CODEC_SCREENPRESSOR) continue;          // ScreenPressor levels are planned below
-                if (!R.precopy) fin.push_back(f);                          // a pre-copied picture is final after its decode
+                if (!R.precopy && !edge_fill) fin.push_back(f);            // a pre-copied picture is final after its decode
                 CopyJob J;
                 J.dst = b->d_out + R.out_off;
                 J.src = R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev;
-                J.value = 0;
+                J.value = disp ? 0xFF000000u : 0u;
+                if (edge_fill) J.src = nullptr;
                 if (R.kind == FK_SP_FLAT) { J.src = nullptr; J.value = R.fill_value; }
                 J.n_vec4 = (uint32_t)(((size_t)S.w * S.h * 4 + 15) / 16);
                 maxv = std::max(maxv, J.n_vec4);
@@ -338,6 +344,12 @@ static void build_plan(jsp_batch *b, Plan &plan, int s_lo, int s_hi, HostTables 
     }
 }
 
+// true when the pictures of this stream are stored bottom-up (fused display store with the flip)
+static inline bool flipped(const jsp_batch *b, const StreamRec &S)
+{
+    return (b->flags & JSP_BATCH_DISPLAY) && (b->flags & JSP_BATCH_DISPLAY_FLIP) && S.codec != JSP_CODEC_SCREENPRESSOR;
+}
+
 static void fill_mframes(jsp_batch *b, HostTables &T)
 {
     const size_t N = b->frames.size();
@@ -361,7 +373,10 @@ static void fill_mframes(jsp_batch *b, HostTables &T)
         M.n_tiles = R.n_tiles;
         M.state_base = R.state_base;
         M.insign_blocks = (uint32_t)std::max(0, (b->insign_lines + 3) >> 2);
-        M.flags = (R.prev >= 0 ? MSV1_F_HAS_PRED : 0u) | (R.precopy ? MSV1_F_PRECOPIED : 0u);
+        M.flags = (R.prev >= 0 ? MSV1_F_HAS_PRED : 0u) | (R.precopy ? MSV1_F_PRECOPIED : 0u) |
+                  ((b->flags & JSP_BATCH_DISPLAY) ? MSV1_F_DISPLAY : 0u) |
+                  ((b->flags & JSP_BATCH_DISPLAY) && (b->flags & JSP_BATCH_DISPLAY_FLIP) ? MSV1_F_FLIP : 0u);
+        M.Y = (uint32_t)S.h;
         M.inv_nbx = M.nbx > 1 ? (uint32_t)(0x100000000ull / M.nbx) : 0xFFFFFFFFu;
         if (!b->chunks.empty()) { T.mframes[N + f] = M; T.mframes[N + f].state_base = R.state_base2; }
     }
@@ -416,7 +431,7 @@ template <class F> static bool run_plan_with(jsp_batch *b, const Plan &P, cudaSt
             launch_frame_copy(b->d_jobs + L.first, L.count, L.max_vec4, b->sm_count, st);
             break;
         case JSP_K_MSV1_DECODE:
-            launch_msv1_decode(L.kind == FK_MSV8, b->d_mframes, b->d_tile_tab + L.first, L.count,
+            launch_msv1_decode(L.kind == FK_MSV8, (b->flags & JSP_BATCH_DISPLAY) != 0, b->d_mframes, b->d_tile_tab + L.first, L.count,
                                b->d_tile_map, b->d_tile_cnt, b->d_tickets + L.ticket, b->sm_count, st);
             break;
         case JSP_K_SP_ENTROPY_RC: case JSP_K_SP_ENTROPY_ANS: case JSP_K_SP_ENTROPY_MIXED:
@@ -785,7 +800,10 @@ static int64_t batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_st
                 cur.push_back(b->d_out + R.out_off); prev.push_back(R.prev >= 0 ? b->d_out + b->frames[R.prev].out_off : b->ext_prev);
                 stp.push_back(b->d_status + f);
                 const size_t np = (size_t)S.w * S.h;
-                first.push_back((uint32_t)std::min<size_t>(np, (size_t)std::max(0, b->insign_lines) * S.w)); npx.push_back((uint32_t)np);
+                const size_t skip = std::min<size_t>(np, (size_t)std::max(0, b->insign_lines) * S.w);
+                // a flipped picture (fused display store) keeps its insignificant lines at the END of the buffer
+                if (flipped(b, S)) { first.push_back(0u); npx.push_back((uint32_t)(np - skip)); }
+                else               { first.push_back((uint32_t)skip); npx.push_back((uint32_t)np); }
             }
         }
         if (!grow(b->d_stream_first, b->streams_cap, sfirst.size())) return -1;
@@ -831,7 +849,9 @@ static int64_t batch_configure(jsp_batch *b, const jsp_stream_desc *sd, int n_st
                 const size_t np = (size_t)S.w * S.h;
                 cur.push_back(b->d_out + R.out_off); prev.push_back(b->d_out + b->frames[f - 1].out_off);
                 stp.push_back(b->d_status + f);
-                first.push_back((uint32_t)std::min<size_t>(np, (size_t)std::max(0, b->insign_lines) * S.w)); npx.push_back((uint32_t)np);
+                const size_t skip = std::min<size_t>(np, (size_t)std::max(0, b->insign_lines) * S.w);
+                if (flipped(b, S)) { first.push_back(0u); npx.push_back((uint32_t)(np - skip)); }
+                else               { first.push_back((uint32_t)skip); npx.push_back((uint32_t)np); }
             }
         }
         b->n_kd = cur.size();
@@ -969,7 +989,8 @@ static bool download_range(jsp_batch *b, int64_t lo, int64_t hi, int32_t *const 
         if (!out_frames[i]) { i++; continue; }
         const FrameRec &R = b->frames[i]; const StreamRec &S = b->streams[R.stream];
         const size_t npix = (size_t)S.w * S.h;
-        const bool rem = S.codec != JSP_CODEC_SCREENPRESSOR && ((S.w & 3) || (S.h & 3));
+        // (a JSP_BATCH_DISPLAY batch delivers such pictures whole: the remainder was filled with the canvas's opaque black)
+        const bool rem = S.codec != JSP_CODEC_SCREENPRESSOR && ((S.w & 3) || (S.h & 3)) && !(b->flags & JSP_BATCH_DISPLAY);
         if (rem) {   // the codec never writes the width/height remainder mod 4: leave the caller's pixels alone
             const size_t bw = (size_t)(S.w & ~3), bh = (size_t)(S.h & ~3);
             if (bw && bh && !JSP_CUDA(cudaMemcpy2DAsync(out_frames[i], (size_t)S.w * 4, arena + R.out_off, (size_t)S.w * 4,
@@ -1000,6 +1021,11 @@ int jsp_batch_download(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags)
 int jsp_batch_download_display(jsp_batch *b, int32_t *const *out_frames, uint8_t *flags, int display_flags)
 {
     if (!b || !out_frames) return -1;
+    // MSVideo1 pictures of a JSP_BATCH_DISPLAY batch were STORED in the display format by the decode kernel: no pass for them
+    const bool fused = (b->flags & JSP_BATCH_DISPLAY) != 0;
+    if (fused && ((display_flags & JSP_DISPLAY_FLIP) != 0) != ((b->flags & JSP_BATCH_DISPLAY_FLIP) != 0)) {
+        set_error("jsp_batch_download_display: the flip flag differs from the batch's JSP_BATCH_DISPLAY_FLIP"); return -1;
+    }
     if (!JSP_CUDA(cudaSetDevice(b->device))) return -1;
     if (jsp_batch_results(b, flags)) return -1;
     if (!grow(b->d_disp, b->disp_cap, b->out_used)) return -1;
@@ -1007,6 +1033,7 @@ int jsp_batch_download_display(jsp_batch *b, int32_t *const *out_frames, uint8_t
     for (size_t i = 0; i < b->frames.size(); i++) {
         if (!out_frames[i]) continue;
         const FrameRec &R = b->frames[i]; const StreamRec &S = b->streams[R.stream];
+        if (fused && S.codec != JSP_CODEC_SCREENPRESSOR) continue;
         DisplayJob J;
         J.src = b->d_out + R.out_off; J.dst = b->d_disp + R.out_off; J.X = (uint32_t)S.w; J.Y = (uint32_t)S.h;
         J.from_rgb15 = (S.codec == JSP_CODEC_SCREENPRESSOR && S.bpp == 16) ? 1u : 0u;      // convert_fromRGB15, Manager.hx:120
@@ -1027,7 +1054,8 @@ int jsp_batch_download_display(jsp_batch *b, int32_t *const *out_frames, uint8_t
     while (i < n) {
         if (!outs[i]) { i++; continue; }
         const FrameRec &R = b->frames[i]; const StreamRec &S = b->streams[R.stream];
-        if (!JSP_CUDA(cudaMemcpyAsync(outs[i], b->d_disp + R.out_off, (size_t)S.w * S.h * 4, cudaMemcpyDeviceToHost, b->st_compute))) return -1;
+        const int32_t *from = (fused && S.codec != JSP_CODEC_SCREENPRESSOR) ? b->d_out : b->d_disp;
+        if (!JSP_CUDA(cudaMemcpyAsync(outs[i], from + R.out_off, (size_t)S.w * S.h * 4, cudaMemcpyDeviceToHost, b->st_compute))) return -1;
         i++;
     }
     return JSP_CUDA(cudaStreamSynchronize(b->st_compute)) ? 0 : -1;

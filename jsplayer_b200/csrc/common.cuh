@@ -22,6 +22,8 @@ enum : uint32_t {
 enum : uint32_t {
     MSV1_F_HAS_PRED = 1u << 0,   // the stream has an earlier frame (prev == nullptr then means "not ordered", not "none")
     MSV1_F_PRECOPIED = 1u << 1,  // the output already holds the previous picture: skip runs need no copy
+    MSV1_F_DISPLAY = 1u << 2,    // fused display epilogue (JSP_BATCH_DISPLAY): pixels are stored as canvas bytes R,G,B,A
+    MSV1_F_FLIP = 1u << 3,       // ... and picture row y lands in row Y-1-y (JSP_BATCH_DISPLAY_FLIP)
 };
 
 struct Msv1Frame {
@@ -39,7 +41,7 @@ struct Msv1Frame {
     uint32_t insign_blocks;  // (insignificant_lines+3)>>2
     uint32_t flags;          // MSV1_F_*
     uint32_t inv_nbx;        // floor(2^32 / nbx): block row = umulhi(block, inv_nbx) (+1 fix-up)
-    uint32_t pad;            // sizeof == 80: copied to shared memory in 16-byte units
+    uint32_t Y;              // picture height (row flip of the fused display store); sizeof == 80: copied in 16-byte units
 };
 
 // one 4 KiB bitstream tile of a frame, in launch (ticket) order: everything the prefetch needs in ONE 16-byte load
@@ -64,7 +66,7 @@ constexpr int MSV1_TILE_BYTES = MSV1_TILE_WORDS * 2;                  // 4096
 constexpr int MSV1_STAGE_BYTES = MSV1_TILE_BYTES + 32;                // + look-ahead for an opcode that starts in the last word
 
 // host-callable launchers (implemented in the .cu files)
-void launch_msv1_decode(bool is8, const Msv1Frame *d_frames, const Msv1Tile *d_tiles, uint32_t n_tiles,
+void launch_msv1_decode(bool is8, bool display, const Msv1Frame *d_frames, const Msv1Tile *d_tiles, uint32_t n_tiles,
                         unsigned long long *d_tile_map, unsigned long long *d_tile_cnt,
                         unsigned int *d_ticket, int sm_count, cudaStream_t st);
 void launch_frame_copy(const CopyJob *d_jobs, uint32_t n_jobs, uint32_t max_vec4, int sm_count, cudaStream_t st);

@@ -161,10 +161,15 @@ struct Smem {
 // rewritten as FMA-pipe arithmetic -- bit i to bit 31 by a multiply, down by a multiply-high, pixel = even + bit * (odd - even)
 // by a multiply-add: three FMA instructions instead of a bit test and a select.  2.20 -> 2.27 ms on C2: the extra issue slot
 // per pixel costs more than the ALU relief gains -- both limits are close.)
+// DISP (fused display store, JSP_BATCH_DISPLAY): the colours arrive already converted; with `flip` picture row y is
+// stored in row Y-1-y (the caller's render-time flip, Main.hx:946).
+template <bool DISP>
 __device__ __forceinline__ void store_block(int32_t *out, uint32_t X, uint32_t by, uint32_t bx,
-                                            const uint32_t (&col)[8], uint32_t flags, bool vec_ok)
+                                            const uint32_t (&col)[8], uint32_t flags, bool vec_ok,
+                                            uint32_t Y = 0, bool flip = false)
 {
     int32_t *p = out + (by * 4u * X + bx * 4u);      // pictures stay below 2^32 pixels
+    if constexpr (DISP) { if (flip) p = out + ((Y - 1u - by * 4u) * X + bx * 4u); }
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         uint32_t px[4];
@@ -178,14 +183,19 @@ __device__ __forceinline__ void store_block(int32_t *out, uint32_t X, uint32_t b
         } else {
             p[0] = (int32_t)px[0]; p[1] = (int32_t)px[1]; p[2] = (int32_t)px[2]; p[3] = (int32_t)px[3];
         }
-        p += X;
+        if constexpr (DISP) { if (flip) p -= X; else p += X; }
+        else p += X;
     }
 }
 
+// (the four rows of a block are copied in buffer order, so a flipped block simply starts three rows further up)
+template <bool DISP>
 __device__ __forceinline__ void copy_block(int32_t *out, const int32_t *prev, uint32_t X, uint32_t by,
-                                           uint32_t bx, bool vec_ok)
+                                           uint32_t bx, bool vec_ok, uint32_t Y = 0, bool flip = false)
 {
-    const size_t off = (size_t)by * 4u * X + bx * 4u;
+    size_t off = (size_t)by * 4u * X + bx * 4u;
+    if constexpr (DISP) { if (flip) off = (size_t)(Y - 4u - by * 4u) * X + bx * 4u; }
+    constexpr uint32_t ZERO = DISP ? 0xFF000000u : 0u;             // a pixel nobody wrote, as the canvas shows it
     int32_t *d = out + off;
     if (vec_ok) {
         uint4 v[4];
@@ -195,15 +205,18 @@ __device__ __forceinline__ void copy_block(int32_t *out, const int32_t *prev, ui
             for (int r = 0; r < 4; r++) v[r] = ld_global_cs(s + (size_t)r * X);
         } else {
 #pragma unroll
-            for (int r = 0; r < 4; r++) v[r] = make_uint4(0, 0, 0, 0);
+            for (int r = 0; r < 4; r++) v[r] = make_uint4(ZERO, ZERO, ZERO, ZERO);
         }
 #pragma unroll
         for (int r = 0; r < 4; r++) st_global_cs(d + (size_t)r * X, v[r]);
     } else {
         for (int r = 0; r < 4; r++)
-            for (int x = 0; x < 4; x++) d[(size_t)r * X + x] = prev ? prev[off + (size_t)r * X + x] : 0;
+            for (int x = 0; x < 4; x++) d[(size_t)r * X + x] = prev ? prev[off + (size_t)r * X + x] : (int32_t)ZERO;
     }
 }
+
+// Manager.fill_bitmap_data (Manager.hx:363-381): 0x00RRGGBB -> the Int32 view of canvas bytes R,G,B,A (alpha 255)
+__device__ __forceinline__ uint32_t disp_px(uint32_t c) { return __byte_perm(c, 0xFFu, 0x4012); }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 {
@@ -259,7 +272,7 @@ __device__ __forceinline__ void stage_tile(const Msv1Tile &e, const Msv1Frame *f
 // flight in registers and the atomic for T3's ticket has been issued -- the four dependent global latencies a tile
 // needs before its first instruction are all hidden behind the previous tile's work.  `depth0` (small launches:
 // one tile per CTA, nothing held back) keeps the look-back chain of a single frame short.
-template <bool IS8>
+template <bool IS8, bool DISP>
 __global__ void __launch_bounds__(MSV1_THREADS)
 msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restrict__ tiles, uint32_t n_tiles, int depth0,
                    u64 *__restrict__ tile_map, u64 *__restrict__ tile_cnt, unsigned int *__restrict__ ticket)
@@ -299,6 +312,9 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
     uint8_t *const sbytes = sm.stage[cur];
     const Msv1Frame &F = sm.fd[cur];
     const uint32_t len = F.len, X = F.X, nbx = F.nbx, nblocks = F.nblocks;
+    const uint32_t Y = F.Y;
+    const bool flip = DISP && (F.flags & MSV1_F_FLIP) != 0;
+    constexpr uint32_t ZERO = DISP ? 0xFF000000u : 0u;
     const uint32_t tile = (uint32_t)((e0.src - F.src) / MSV1_TILE_BYTES);
     const uint32_t tile_byte0 = tile * MSV1_TILE_BYTES;
     const uint32_t n_words = (len + 1u) >> 1;                      // an odd trailing byte is a half word (see below)
@@ -315,7 +331,10 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
         pf_cnt = ld_state(tile_cnt + F.state_base + tile - 1);
     }
     if (IS8) {
-        for (int i = tid; i < 256; i += MSV1_THREADS) sm.pal[i] = F.pal ? F.pal[i] : 0;
+        for (int i = tid; i < 256; i += MSV1_THREADS) {
+            const uint32_t c = F.pal ? (uint32_t)F.pal[i] : 0u;
+            sm.pal[i] = (int32_t)(DISP ? disp_px(c) : c);
+        }
         __syncthreads();
     }
     // An odd frame length leaves a half word {a, undefined}.  The reference then takes the 1-colour
@@ -641,7 +660,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
                 const int a = rd(0), b = rd(1);
                 flags = 0;
                 if (IS8) {
-                    auto palu = [&](int ix) -> uint32_t { return ix < 0 ? 0u : (uint32_t)sm.pal[ix]; };
+                    auto palu = [&](int ix) -> uint32_t { return ix < 0 ? ZERO : (uint32_t)sm.pal[ix]; };
                     if (b >= 0 && b < 0x80) {
                         flags = ((uint32_t)b << 8) | (uint32_t)a;
                         const uint32_t c1 = palu(rd(2)), c0 = palu(rd(3));
@@ -669,7 +688,11 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
                     }
                 }
             }
-            store_block(F.out, X, by, bx, col, flags, vec_ok);
+            if constexpr (DISP && !IS8) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) col[k] = disp_px(col[k]);
+            }
+            store_block<DISP>(F.out, X, by, bx, col, flags, vec_ok, Y, flip);
             myflags |= ST_CHANGED | (by >= F.insign_blocks ? ST_SIGNIF_ROWS : 0u);
         }
 
@@ -684,7 +707,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
             n = min(n, nblocks - min(blk0, nblocks));
             for (uint32_t j = lane; j < n; j += 32) {
                 const uint32_t blk = blk0 + j, by = blk / nbx, bx = blk - by * nbx;
-                copy_block(F.out, F.prev, X, by, bx, vec_ok);
+                copy_block<DISP>(F.out, F.prev, X, by, bx, vec_ok, Y, flip);
             }
             if (n && !F.prev && (F.flags & MSV1_F_HAS_PRED)) myflags |= ST_NEEDS_PREV;
         }
@@ -693,7 +716,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
         if (big0 < nblocks) {
             for (uint32_t blk = big0 + tid; blk < nblocks; blk += MSV1_THREADS) {
                 const uint32_t by = blk / nbx, bx = blk - by * nbx;
-                copy_block(F.out, F.prev, X, by, bx, vec_ok);
+                copy_block<DISP>(F.out, F.prev, X, by, bx, vec_ok, Y, flip);
             }
             if (!F.prev && (F.flags & MSV1_F_HAS_PRED)) myflags |= ST_NEEDS_PREV;
         }
@@ -701,10 +724,10 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
     // ---- the bitstream ended before the last block: the reference keeps "reading" undefined bytes, i.e.
     //      1-colour blocks of colour 0 that count as changes (MSVideo1.hx:171-181 with NaN -> 0) ----
     if (last_tile && !sm.terminated && incl_block < nblocks) {
-        const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const uint32_t zero[8] = {ZERO, ZERO, ZERO, ZERO, ZERO, ZERO, ZERO, ZERO};
         for (uint32_t blk = incl_block + tid; blk < nblocks; blk += MSV1_THREADS) {
             const uint32_t by = blk / nbx, bx = blk - by * nbx;
-            store_block(F.out, X, by, bx, zero, 0u, vec_ok);
+            store_block<DISP>(F.out, X, by, bx, zero, 0u, vec_ok, Y, flip);
             myflags |= ST_CHANGED | (by >= F.insign_blocks ? ST_SIGNIF_ROWS : 0u);
         }
     }
@@ -728,7 +751,7 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
 
 }  // namespace
 
-void launch_msv1_decode(bool is8, const Msv1Frame *d_frames, const Msv1Tile *d_tiles, uint32_t n_tiles,
+void launch_msv1_decode(bool is8, bool display, const Msv1Frame *d_frames, const Msv1Tile *d_tiles, uint32_t n_tiles,
                         unsigned long long *d_tile_map, unsigned long long *d_tile_cnt,
                         unsigned int *d_ticket, int sm_count, cudaStream_t st)
 {
@@ -738,10 +761,10 @@ void launch_msv1_decode(bool is8, const Msv1Frame *d_frames, const Msv1Tile *d_t
     const uint32_t capacity = (uint32_t)sm_count * 8u;
     const int depth0 = n_tiles < 6u * capacity ? 1 : 0;
     const uint32_t grid = depth0 ? n_tiles : capacity;
-    if (is8)
-        msv1_decode_kernel<true><<<grid, MSV1_THREADS, 0, st>>>(d_frames, d_tiles, n_tiles, depth0, d_tile_map, d_tile_cnt, d_ticket);
-    else
-        msv1_decode_kernel<false><<<grid, MSV1_THREADS, 0, st>>>(d_frames, d_tiles, n_tiles, depth0, d_tile_map, d_tile_cnt, d_ticket);
+#define JSP_LAUNCH(I8, DISP) msv1_decode_kernel<I8, DISP><<<grid, MSV1_THREADS, 0, st>>>(d_frames, d_tiles, n_tiles, depth0, d_tile_map, d_tile_cnt, d_ticket)
+    if (display) { if (is8) JSP_LAUNCH(true, true); else JSP_LAUNCH(false, true); }
+    else         { if (is8) JSP_LAUNCH(true, false); else JSP_LAUNCH(false, false); }
+#undef JSP_LAUNCH
 }
 
 }  // namespace jsp

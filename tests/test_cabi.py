@@ -29,6 +29,18 @@ def test_header_symbols_exported():
     assert sorted(_lib.PROTOTYPES) == syms
 
 
+def test_binding_constants_follow_the_header():
+    """Every JSP_* enumerator the ctypes binding restates has the header's value."""
+    txt = open(os.path.join(ROOT, "include", "jsplayer_cuda.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    vals = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"\b(JSP_[A-Z0-9_]+)\s*=\s*(0x[0-9A-Fa-f]+|\d+)", txt)}
+    names = [n for n in dir(_lib) if n.startswith("JSP_") and n in vals]
+    assert {"JSP_BATCH_SIGNIFICANCE", "JSP_BATCH_NUMA_BIND", "JSP_BATCH_DISPLAY", "JSP_BATCH_DISPLAY_FLIP", "JSP_DISPLAY_FLIP",
+            "JSP_FRAME_CHANGED", "JSP_FRAME_DIFFERS"} <= set(names)
+    for n in names:
+        assert getattr(_lib, n) == vals[n], n
+
+
 def test_version_and_error_strings():
     lib = _lib.load()
     assert b"sm_100a" in lib.jsp_version()
