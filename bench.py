@@ -455,6 +455,35 @@ def measure(wl, args, rank, local_rank, world, dist, torch, with_e2e=True, with_
     ms_per_step = float(t_local.item()) / args.steps
     value = st["pixels"] * world / (ms_per_step * 1e-3) / 1e6
 
+    # ---- fused display store (JSP_BATCH_DISPLAY): the same batch with the MSVideo1 kernel storing canvas
+    #      words bottom-up, checked against the oracle's decode + display conversion, timed like `value` ----
+    display_fused = None
+    if world == 1 and wl.name in ("c2", "c2p", "c2p8") and not getattr(args, "no_display_leg", False):
+        from oracle import pyoracle as O
+        bdd = BatchDecoder(device=local_rank, insignificant_lines=INSIGN, display=True, display_flip=True)
+        bdd.configure(specs, pinned=True)
+        bdd.upload(); bdd.run(); bdd.sync()
+        sp = specs[chk[-1]]
+        o = [None] * bdd.n_frames
+        for f in range(sp.n_frames):
+            o[first_of[chk[-1]] + f] = np.empty((sp.height, sp.width), dtype=np.int32)
+        bdd.download(o)
+        exp = O.decode_stream(int(sp.codec), sp.width, sp.height, sp.bpp, spec_frames(sp), keys=sp.keys, palette=sp.palette,
+                              insignificant_lines=INSIGN)[0]
+        for f in range(sp.n_frames):
+            if not (o[first_of[chk[-1]] + f] == O.display_convert(exp[f], flip=True)).all():
+                raise SystemExit("bench: fused display store differs from the oracle (stream %d frame %d)" % (chk[-1], f))
+        del o
+        bdd.time_runs(warmup=warmup, iters=1, flush_l2=flush)
+        torch.cuda.synchronize()
+        ms_d, _, _ = bdd.time_runs(warmup=0, iters=args.steps, flush_l2=flush)
+        bdd.close()
+        display_fused = {"value": st["pixels"] / (ms_d / args.steps * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": ms_d / args.steps,
+                         "ms_per_step_plain": ms_per_step,
+                         "what": "device-resident decode with JSP_BATCH_DISPLAY | JSP_BATCH_DISPLAY_FLIP: pictures leave the decode kernel as "
+                                 "canvas R,G,B,A words, bottom-up (Manager.hx:363-381, Main.hx:946); 0 extra bytes per pixel against the "
+                                 "8 B/pixel of the separate pass; stream %d checked against the oracle's display conversion" % chk[-1]}
+
     # ---- end to end: pinned host bitstreams -> H2D -> decode -> D2H pinned host pictures ----
     e2e = None
     e2e_steps = args.steps if args.e2e_steps < 0 else args.e2e_steps
@@ -587,6 +616,8 @@ def measure(wl, args, rank, local_rank, world, dist, torch, with_e2e=True, with_
         line["e2e"] = e2e if e2e else {"value": None, "unit": "Mpixel/s", "skipped": "--e2e-steps 0"}
         if e2e_inplace:
             line["e2e_inplace"] = e2e_inplace
+        if display_fused:
+            line["display_fused"] = display_fused
         if with_cpu and not args.no_cpu_baseline:
             n_s = sample_size(wl, cores, len(specs))
             v, t, reps = cpu_baseline(specs[:n_s], cores, budget_s=cpu_budget or args.cpu_budget)
@@ -615,6 +646,7 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="do not move this rank's thread / pinned memory to its GPU's NUMA node")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-codecs", action="store_true", help="skip the per-codec ScreenPressor legs")
+    ap.add_argument("--no-display-leg", action="store_true", help="skip the fused-display-store leg of the MSVideo1 workloads")
     args = ap.parse_args()
     warmup = max(3, args.warmup)
 
@@ -670,7 +702,7 @@ def main():
             a2.streams, a2.steps, a2.e2e_steps = 0, min(args.steps, steps), -1
             try:
                 l2 = measure(make_workload(name, a2), a2, 0, local_rank, 1, dist, torch, cpu_budget=min(args.cpu_budget, 6.0))
-                codecs[name] = {k: l2[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "config", "kernels", "roofline", "entropy", "e2e", "e2e_inplace", "cpu_baseline") if k in l2}
+                codecs[name] = {k: l2[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "config", "kernels", "roofline", "entropy", "e2e", "e2e_inplace", "display_fused", "cpu_baseline") if k in l2}
             except (Exception, SystemExit) as e:       # a failed extra leg must not lose the headline line
                 codecs[name] = {"error": str(e)}
         line["codecs"] = codecs
