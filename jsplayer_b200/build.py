@@ -9,6 +9,7 @@ nvcc cross-compiles without a GPU, so this runs on the CPU-only build container 
 import fcntl
 import hashlib
 import os
+import shutil
 import subprocess
 import sys
 
@@ -84,9 +85,24 @@ def build_cuda(force=False, verbose=False):
         objdir = tempfile.mkdtemp(prefix="jsp_build_")
         cflags = [f for f in flags if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
 
+        # objects are cached by content (the unit, every header, the flags): touching one kernel recompiles one unit
+        cache = os.environ.get("JSP_OBJ_CACHE", os.path.join(tempfile.gettempdir(), "jsp_obj_cache"))
+        hdrs = [d for d in deps if d not in srcs]
+
         def compile_one(src):
             obj = os.path.join(objdir, os.path.basename(src) + ".o")
+            key = os.path.join(cache, os.path.basename(src) + "." + _digest([src] + hdrs, cflags)[:24] + ".o")
+            if not verbose and os.path.exists(key):
+                shutil.copyfile(key, obj)
+                return obj, subprocess.CompletedProcess([], 0, "", "")
             r = subprocess.run([nvcc] + cflags + ["-c", "-o", obj, src], capture_output=True, text=True)
+            if r.returncode == 0:
+                try:
+                    os.makedirs(cache, exist_ok=True)
+                    shutil.copyfile(obj, key + ".tmp%d" % os.getpid())
+                    os.replace(key + ".tmp%d" % os.getpid(), key)
+                except OSError:
+                    pass
             return obj, r
         with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
             results = list(ex.map(compile_one, srcs))
