@@ -273,7 +273,7 @@ __device__ __forceinline__ void stage_tile(const Msv1Tile &e, const Msv1Frame *f
 // needs before its first instruction are all hidden behind the previous tile's work.  `depth0` (small launches:
 // one tile per CTA, nothing held back) keeps the look-back chain of a single frame short.
 template <bool IS8, bool DISP>
-__global__ void __launch_bounds__(MSV1_THREADS)
+__global__ void __launch_bounds__(MSV1_THREADS, 8)
 msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restrict__ tiles, uint32_t n_tiles, int depth0,
                    u64 *__restrict__ tile_map, u64 *__restrict__ tile_cnt, unsigned int *__restrict__ ticket)
 {
@@ -417,37 +417,31 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
         M = ((u64)(R[8] >> 16) << 32) | lo | MAP_TERM;
     }
 
-    // ---- scan 2: chain the maps.  A lane whose map is constant fixes its successor's entry outright. ----
-    uint32_t myc; const bool myconst = map_const<NENT>(M, myc);
-    bool known; uint32_t entry;
-    {
-        const uint32_t pc = __shfl_up_sync(FULL, myc, 1);
-        const bool pk = __shfl_up_sync(FULL, (int)myconst, 1) != 0;
-        known = lane > 0 && pk; entry = pc;
-    }
-    uint32_t ex; bool exk;
-    for (;;) {
-        exk = known || myconst;
-        ex = known ? nib(M, entry) : myc;
-        const uint32_t pe = __shfl_up_sync(FULL, ex, 1);
-        const bool pk = __shfl_up_sync(FULL, (int)exk, 1) != 0;
-        const bool newly = !known && lane > 0 && pk;
-        if (newly) { known = true; entry = pe; }
-        if (!__any_sync(FULL, newly)) break;
-    }
-    {
-        u64 agg;
-        const bool exit_known = __shfl_sync(FULL, (int)exk, 31) != 0;
-        if (exit_known) {
-            agg = ONES9 * __shfl_sync(FULL, ex, 31) | MAP_TERM;
-        } else {   // no constant map in the whole warp: follow all entries through the 32 segments
-            uint32_t cur = lane < NENT ? lane : 0;
-            for (int i = 0; i < 32; i++) cur = nib(shfl64(M, i), cur);
-            agg = MAP_TERM;
+    // ---- scan 2: chain the maps.  A segment's map is rarely constant (14 % of the segments of the quoted mix, none where every
+    //      opcode has 3 words), so entries are not handed from lane to lane (one lane per shuffle round: 12 + 6 rounds per tile on
+    //      the mix, 31 on all-2-colour input) but tracked: the warp's 32 segments form 4 groups of 8; lane 8g + e follows entry e
+    //      (and, every lane of the group, entry 8) through the 8 segments of group g in 8 steps, keeping the entry INTO each
+    //      segment as a nibble.  Group exits chain to the warp's map here and, once the warp's own entry is known (look-back
+    //      below), to each group's entry; a lane's entry is then one nibble of the record of the lane that followed that value. ----
+    const uint32_t grp = lane & 24u, sub = lane & 7u;
+    uint32_t t_e = sub, t_8 = 8u, inter = 0, inter8 = 0;
 #pragma unroll
-            for (int e = 0; e < NENT; e++) agg |= (u64)__shfl_sync(FULL, cur, e) << (4 * e);
+    for (int i = 0; i < 8; i++) {
+        const u64 Mi = shfl64(M, (int)grp + i);
+        inter |= t_e << (4 * i); inter8 |= t_8 << (4 * i);
+        t_e = nib(Mi, t_e); t_8 = nib(Mi, t_8);            // TERM (15) is absorbing: every map carries MAP_TERM
+    }
+    {
+        uint32_t cur = lane < 9u ? lane : 0u;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const uint32_t a = __shfl_sync(FULL, t_e, 8 * g + (int)(cur & 7u));
+            const uint32_t b = __shfl_sync(FULL, t_8, 8 * g);
+            cur = cur == TERM ? TERM : (cur < 8u ? a : b);
         }
-        if (lane == 0) sm.wmap[warp] = agg;
+        const uint32_t lo = __reduce_or_sync(FULL, lane < (uint32_t)(NENT < 8 ? NENT : 8) ? cur << (4 * lane) : 0u);
+        const uint32_t hi = __shfl_sync(FULL, cur, 8);
+        if (lane == 0) sm.wmap[warp] = ((u64)(NENT > 8 ? hi : 0u) << 32) | lo | MAP_TERM;
     }
     __syncthreads();
     // the tile's map = the four warp maps chained: entry e of lanes 0..NENT-1 of warp 0 walks through them, the nibbles are
@@ -492,12 +486,18 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
         if (stalled) atomicOr(F.status, ST_ERROR);
     }
     __syncthreads();
-    if (lane == 0) { known = true; entry = sm.wentry[warp]; }
-    while (!__all_sync(FULL, known)) {
-        const uint32_t e2 = nib(M, entry);
-        const uint32_t pe = __shfl_up_sync(FULL, e2, 1);
-        const bool pk = __shfl_up_sync(FULL, (int)known, 1) != 0;
-        if (!known && lane > 0 && pk) { known = true; entry = pe; }
+    uint32_t entry;
+    {
+        uint32_t eg = sm.wentry[warp], mine = eg;          // eg: the entry into group g (the same in every lane)
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            if ((uint32_t)g == (lane >> 3)) mine = eg;
+            const uint32_t a = __shfl_sync(FULL, t_e, 8 * g + (int)(eg & 7u));
+            const uint32_t b = __shfl_sync(FULL, t_8, 8 * g);
+            eg = eg == TERM ? TERM : (eg < 8u ? a : b);
+        }
+        const uint32_t pk = __shfl_sync(FULL, inter, (int)(grp + (mine & 7u)));
+        entry = mine == TERM ? TERM : ((mine < 8u ? pk : inter8) >> (4 * sub)) & 15u;
     }
 
     // ---- scan 3: the chain of the true entry gives this lane's opcode starts; count its blocks ----
