@@ -9,8 +9,9 @@
 //     1. every lane walks its 16-word segment BACKWARDS and gets, for each possible entry offset
 //        0..8 (an opcode is at most 9 words), the offset at which the opcode chain leaves the segment
 //        -> a 9-nibble map in one 64-bit register.  Opcode boundaries depend on bytes only.
-//     2. maps are chained lane -> warp -> tile with warp shuffles; opcode chains self-synchronise, so
-//        most maps are constant and the chain resolves in one or two shuffle rounds.
+//     2. maps are chained lane -> group of 8 lanes -> warp -> tile with warp shuffles: lane 8g + e follows entry e through
+//        the 8 segments of group g and records the entry into each (maps are rarely constant -- never when every opcode
+//        has 3 words -- so nothing waits for a chain to self-synchronise).
 //     3. tiles of one frame are chained with a single-pass decoupled look-back (one 64-bit state word
 //        per tile); tiles are ticketed tile-major over all frames so predecessors are long finished.
 //     4. lanes walk forward from their now-known entry, count blocks (skip runs weigh n), and a
