@@ -169,23 +169,36 @@ __device__ __forceinline__ void store_block(int32_t *out, uint32_t X, uint32_t b
                                             const uint32_t (&col)[8], uint32_t flags, bool vec_ok,
                                             uint32_t Y = 0, bool flip = false)
 {
-    int32_t *p = out + (by * 4u * X + bx * 4u);      // pictures stay below 2^32 pixels
-    if constexpr (DISP) { if (flip) p = out + ((Y - 1u - by * 4u) * X + bx * 4u); }
+    // one global-space byte address, advanced by the row pitch (the compiler otherwise keeps a 64-bit pixel index AND rebuilds
+    // the pointer from it for every row), and ONE test of vec_ok per block
+    uint32_t first = by * 4u * X + bx * 4u;           // pictures stay below 2^32 pixels
+    long long pitch = (long long)X * 4;
+    if constexpr (DISP) { if (flip) { first = (Y - 1u - by * 4u) * X + bx * 4u; pitch = -pitch; } }
+    unsigned long long a = (unsigned long long)__cvta_generic_to_global(out) + (unsigned long long)first * 4u;
+    uint32_t px[4][4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        uint32_t px[4];
 #pragma unroll
         for (int x = 0; x < 4; x++) {
             const int q = ((r & 2) << 1) + (x & 2);
-            px[x] = ((flags >> (4 * r + x)) & 1u) ? col[q + 1] : col[q];
+            px[r][x] = ((flags >> (4 * r + x)) & 1u) ? col[q + 1] : col[q];
         }
-        if (vec_ok) {
-            st_global_cs(p, make_uint4(px[0], px[1], px[2], px[3]));
-        } else {
-            p[0] = (int32_t)px[0]; p[1] = (int32_t)px[1]; p[2] = (int32_t)px[2]; p[3] = (int32_t)px[3];
+    }
+    if (vec_ok) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(a), "r"(px[r][0]), "r"(px[r][1]), "r"(px[r][2]), "r"(px[r][3]) : "memory");
+            a += (unsigned long long)pitch;
         }
-        if constexpr (DISP) { if (flip) p -= X; else p += X; }
-        else p += X;
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            asm volatile("st.global.b32 [%0], %1;" ::"l"(a), "r"(px[r][0]) : "memory");
+            asm volatile("st.global.b32 [%0+4], %1;" ::"l"(a), "r"(px[r][1]) : "memory");
+            asm volatile("st.global.b32 [%0+8], %1;" ::"l"(a), "r"(px[r][2]) : "memory");
+            asm volatile("st.global.b32 [%0+12], %1;" ::"l"(a), "r"(px[r][3]) : "memory");
+            a += (unsigned long long)pitch;
+        }
     }
 }
 
