@@ -537,15 +537,25 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
     }
     // ---- scan 4: block / opcode prefix sums (warp shuffles + look-back) ----
     uint32_t op_incl = nops, blk_incl = blocks;
+    const bool anyrun = __any_sync(FULL, runs != 0);
+    if (!anyrun) {                                                 // no copy run in this warp's 32 segments: one block per opcode
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o2 = __shfl_up_sync(FULL, op_incl, d);
-        const uint32_t b2 = __shfl_up_sync(FULL, blk_incl, d);
-        if (lane >= (uint32_t)d) { op_incl += o2; blk_incl = sat_add(blk_incl, b2, nblocks); }
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o2 = __shfl_up_sync(FULL, op_incl, d);
+            if (lane >= (uint32_t)d) op_incl += o2;
+        }
+        blk_incl = min(op_incl, nblocks);                          // (a chain of saturating adds = the saturated sum)
+    } else {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o2 = __shfl_up_sync(FULL, op_incl, d);
+            const uint32_t b2 = __shfl_up_sync(FULL, blk_incl, d);
+            if (lane >= (uint32_t)d) { op_incl += o2; blk_incl = sat_add(blk_incl, b2, nblocks); }
+        }
     }
     if (lane == 31) { sm.wops[warp] = op_incl; sm.wblk[warp] = blk_incl; }
     {
-        const bool anyterm = __any_sync(FULL, lterm), anyrun = __any_sync(FULL, runs != 0);
+        const bool anyterm = __any_sync(FULL, lterm);
         if (lane == 0) { if (anyterm) sm.terminated = 1; if (anyrun) sm.any_runs = 1; }
     }
     __syncthreads();
