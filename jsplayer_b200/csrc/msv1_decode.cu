@@ -631,6 +631,10 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
 
         // ---- fill: one thread per coded block, branch-free over the three block classes ----
         const uint32_t inv_nbx = F.inv_nbx;
+        // (the streaming stores are asm statements that clobber memory: a descriptor field read inside the loop is re-read from
+        //  shared memory after every block)
+        int32_t *const out_pic = F.out;
+        const uint32_t insign_blocks = F.insign_blocks;
         for (uint32_t op = tid; op < tot_ops; op += MSV1_THREADS) {
             const uint32_t pw = sm.pos[op];
             if (pw & 0x8000u) continue;
@@ -716,8 +720,8 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
 #pragma unroll
                 for (int k = 0; k < 8; k++) col[k] = disp_px(col[k]);
             }
-            store_block<DISP>(F.out, X, by, bx, col, flags, vec_ok, Y, flip);
-            myflags |= ST_CHANGED | (by >= F.insign_blocks ? ST_SIGNIF_ROWS : 0u);
+            store_block<DISP>(out_pic, X, by, bx, col, flags, vec_ok, Y, flip);
+            myflags |= ST_CHANGED | (by >= insign_blocks ? ST_SIGNIF_ROWS : 0u);
         }
 
         // ---- skip runs: warp per run, 16-byte copies from the previous picture ----
