@@ -599,6 +599,11 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
     const bool last_tile = tile + 1 == F.n_tiles;
 
     uint32_t myflags = 0;
+    // (the streaming loads / stores are asm statements that clobber memory: a descriptor field read inside a loop over blocks
+    //  would be re-read from shared memory after every block)
+    int32_t *const out_pic = F.out;
+    const int32_t *const prev_pic = F.prev;
+    const uint32_t insign_blocks = F.insign_blocks;
     if (first_block < nblocks) {
         // ---- per-opcode table: word position (and, only when the tile has copy runs, the block index;
         //      otherwise opcode k of the tile is simply block first_block + k) ----
@@ -631,10 +636,6 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
 
         // ---- fill: one thread per coded block, branch-free over the three block classes ----
         const uint32_t inv_nbx = F.inv_nbx;
-        // (the streaming stores are asm statements that clobber memory: a descriptor field read inside the loop is re-read from
-        //  shared memory after every block)
-        int32_t *const out_pic = F.out;
-        const uint32_t insign_blocks = F.insign_blocks;
         for (uint32_t op = tid; op < tot_ops; op += MSV1_THREADS) {
             const uint32_t pw = sm.pos[op];
             if (pw & 0x8000u) continue;
@@ -735,18 +736,18 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
             n = min(n, nblocks - min(blk0, nblocks));
             for (uint32_t j = lane; j < n; j += 32) {
                 const uint32_t blk = blk0 + j, by = blk / nbx, bx = blk - by * nbx;
-                copy_block<DISP>(F.out, F.prev, X, by, bx, vec_ok, Y, flip);
+                copy_block<DISP>(out_pic, prev_pic, X, by, bx, vec_ok, Y, flip);
             }
-            if (n && !F.prev && (F.flags & MSV1_F_HAS_PRED)) myflags |= ST_NEEDS_PREV;
+            if (n && !prev_pic && (F.flags & MSV1_F_HAS_PRED)) myflags |= ST_NEEDS_PREV;
         }
         // ---- "rest of the frame is copied" (skip count 0 / 8-bit terminator): whole CTA ----
         const uint32_t big0 = precopied ? 0xFFFFFFFFu : sm.big_blk0;
         if (big0 < nblocks) {
             for (uint32_t blk = big0 + tid; blk < nblocks; blk += MSV1_THREADS) {
                 const uint32_t by = blk / nbx, bx = blk - by * nbx;
-                copy_block<DISP>(F.out, F.prev, X, by, bx, vec_ok, Y, flip);
+                copy_block<DISP>(out_pic, prev_pic, X, by, bx, vec_ok, Y, flip);
             }
-            if (!F.prev && (F.flags & MSV1_F_HAS_PRED)) myflags |= ST_NEEDS_PREV;
+            if (!prev_pic && (F.flags & MSV1_F_HAS_PRED)) myflags |= ST_NEEDS_PREV;
         }
     }
     // ---- the bitstream ended before the last block: the reference keeps "reading" undefined bytes, i.e.
@@ -755,8 +756,8 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
         const uint32_t zero[8] = {ZERO, ZERO, ZERO, ZERO, ZERO, ZERO, ZERO, ZERO};
         for (uint32_t blk = incl_block + tid; blk < nblocks; blk += MSV1_THREADS) {
             const uint32_t by = blk / nbx, bx = blk - by * nbx;
-            store_block<DISP>(F.out, X, by, bx, zero, 0u, vec_ok, Y, flip);
-            myflags |= ST_CHANGED | (by >= F.insign_blocks ? ST_SIGNIF_ROWS : 0u);
+            store_block<DISP>(out_pic, X, by, bx, zero, 0u, vec_ok, Y, flip);
+            myflags |= ST_CHANGED | (by >= insign_blocks ? ST_SIGNIF_ROWS : 0u);
         }
     }
     myflags = __reduce_or_sync(FULL, myflags);
