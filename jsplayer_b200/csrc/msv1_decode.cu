@@ -674,8 +674,10 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
                     const bool one = (v0 & 0x8000u) != 0;          // b >= 0x80: 1 colour = the opcode word (:171-181)
                     const bool eight = !one && (v0 & 0x80000000u); // colour0 bit 15 (:142)
                     flags = one ? 0u : ((v0 & 0xFFFFu) ^ 0xFFFFu); // :136
-                    const uint32_t c0 = one ? rgb15(v0) : rgb15_hi(v0);
-                    const uint32_t c1 = one ? c0 : rgb15(v1);
+                    // one expansion for both classes (the compiler turned `one ? rgb15(v0) : rgb15_hi(v0)` into a divergent branch);
+                    // a 1-colour block never selects an odd colour (flags = 0), so c1 needs no select
+                    const uint32_t c0 = rgb15_hi(one ? v0 << 16 : v0);
+                    const uint32_t c1 = rgb15(v1);
                     col[0] = c0; col[1] = c1;
                     col[2] = eight ? rgb15_hi(v1) : c0; col[3] = eight ? rgb15(v2) : c1;
                     col[4] = eight ? rgb15_hi(v2) : c0; col[5] = eight ? rgb15(v3) : c1;
