@@ -620,9 +620,9 @@ msv1_decode_kernel(const Msv1Frame *__restrict__ frames, const Msv1Tile *__restr
                 const bool run = (skipmask >> p) & 1u, big = (termmask >> p) & 1u;
                 sm.pos[opi] = (uint16_t)((tid * MSV1_SEG_WORDS + p) | (run ? 0x8000u : 0u));
                 sm.blk[opi] = blk;
-                // only the chain's FIRST terminator counts: lanes past it may parse trailing bytes as opcodes (their entry was
-                // fixed by a constant map before the terminator was known) and meet another terminator pattern, but their
-                // block index is already saturated to nblocks -- atomicMin keeps the real one whatever the store order
+                // only the chain's FIRST terminator counts.  With the grouped entry tracking TERM is absorbing, so no lane behind
+                // a terminator parses the trailing bytes any more (the lane-to-lane hand-over did: an entry fixed by a constant map
+                // before the terminator was known); atomicMin stays as the order-independent way to publish it
                 if (big) { atomicMin(&sm.big_blk0, blk); blk = nblocks; }
                 else if (run) {
                     const uint8_t *o = sbytes + (tid * MSV1_SEG_WORDS + p) * 2;
