@@ -57,7 +57,7 @@ class C2(Workload):
     MIX = (25, 50, 25)                            # % 1-/2-/8-colour blocks -> 8 B per block
     SEED = 0xC0DEC2
     desc = "MSVideo1 RGB555 1920x1080 key frames, 25/50/25% 1/2/8-colour blocks, independent streams"
-    dominant, dominant_name = 0, "msv1_decode_kernel<false>"
+    dominant, dominant_name = 0, "msv1_decode_kernel<false,false>"
 
     def __init__(self, frames=1024, mix=None):
         self.n = frames
@@ -91,7 +91,7 @@ class MSV1Streams(Workload):
     def __init__(self, name, is8, width, height, streams, frames_per_stream, seed, metric, desc):
         self.name, self.is8, self.W, self.H, self.n, self.fps, self.seed = name, is8, width, height, streams, frames_per_stream, seed
         self.metric, self.desc = metric, desc
-        self.dominant_name = "msv1_decode_kernel<%s>" % ("true" if is8 else "false")
+        self.dominant_name = "msv1_decode_kernel<%s,false>" % ("true" if is8 else "false")
 
     def specs(self, rank, n=None):
         from jsplayer_b200 import StreamSpec, CodecType
@@ -154,7 +154,7 @@ class C5(Workload):
     metric = "decoded Mpixel/s (mixed 4K AVI corpus, GOP-sharded)"
     W, H, FRAMES, GOP = 3840, 2160, 64, 16
     desc = "mixed 3840x2160 corpus: MSVideo1 RGB555 + ScreenPressor AVI files, 64 frames, key every 16, via the AVI indexer, GOP-sharded"
-    dominant, dominant_name = 0, "msv1_decode_kernel<false>"
+    dominant, dominant_name = 0, "msv1_decode_kernel<false,false>"
 
     def __init__(self, files):
         self.n = files
